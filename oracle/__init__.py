@@ -77,6 +77,7 @@ def _lib():
     L.orc_eq_fill.argtypes = [vp, i32, vp, vp, vp]
     L.orc_merge_fuzzy.restype = i32
     L.orc_merge_fuzzy.argtypes = [i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, u32, u32, vp, i32, vp]
+    L.orc_stdsort.argtypes = [vp, i32]
     _LIB = L
     return L
 
@@ -290,3 +291,10 @@ def merge_fuzzy(left, right, left_matches, right_matches, read_len=100, max_num_
                                len(left), rt.ctypes.data, rp.ctypes.data, rf.ctypes.data, len(right), read_len,
                                max_num_hits, out.ctypes.data, cap, ctypes.byref(tm))
     return out[:n].copy(), bool(tm.value)
+
+
+def stdsort(a):
+    """libstdc++ std::sort of packed kmerScores entries by (entry >> 8)."""
+    a = np.ascontiguousarray(a, np.uint32).copy()
+    _lib().orc_stdsort(a.ctypes.data, a.size)
+    return a

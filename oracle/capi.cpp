@@ -192,3 +192,14 @@ int orc_merge_fuzzy(int leftMatches, int rightMatches, const uint32_t* ltid, con
 }
 
 } // extern "C"
+
+// libstdc++ std::sort on entries compared by (entry >> 8) only — the reference behaviour the product's
+// StdSort replica is tested against (SACollectorCircall.hpp:450; SURVEY §7 hard part 2).
+#include <algorithm>
+namespace { struct KsEntry { uint32_t v; bool operator<(const KsEntry& o) const { return (v >> 8) < (o.v >> 8); } }; }
+extern "C" void orc_stdsort(uint32_t* a, int n) {
+    std::vector<KsEntry> v(n);
+    for (int i = 0; i < n; ++i) v[i].v = a[i];
+    std::sort(v.begin(), v.end());
+    for (int i = 0; i < n; ++i) a[i] = v[i].v;
+}

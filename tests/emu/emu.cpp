@@ -1,0 +1,229 @@
+// TEST SCAFFOLDING — host emulation of the device code.
+//
+// Compiles circall_b200/csrc/cg_core.cuh + cg_pipeline.cuh with g++ (CG_HOST_EMU) and runs the very
+// same per-thread functions the CUDA kernels call, one "thread" per read, on a CPU-only box.  It is
+// how the device logic is checked against the oracle where no GPU exists (the `-m "not gpu"` tier);
+// the `-m gpu` tests call libcircall_gpu.so itself.  It is not part of the product: nothing in
+// circall_b200/ links or loads it, and libcircall_gpu.so has no CPU path.
+//
+// The index arrays are built here on the host with the same packing primitives the GPU build
+// kernels use (make_block / text_kmer / hmix); the suffix array is passed in by the test.
+#define CG_HOST_EMU 1
+#include "../../circall_b200/csrc/cg_pipeline.cuh"
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cg;
+
+struct EmuIndex {
+    std::vector<u32x4> text, hslots;
+    std::vector<uint32_t> sa, offsets;
+    IndexView v;
+    uint64_t n_kmers = 0;
+};
+
+extern "C" {
+
+void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
+    auto* E = new EmuIndex();
+    for (uint64_t i = 0; i < n; ++i) if (text[i] == '$') E->offsets.push_back(0);
+    uint32_t ntx = (uint32_t)E->offsets.size();
+    E->offsets.assign(ntx + 1, 0);
+    std::vector<uint32_t> ends;
+    { uint32_t t = 0, st = 0; for (uint64_t i = 0; i < n; ++i) if (text[i] == '$') { E->offsets[t++] = st; ends.push_back((uint32_t)i); st = (uint32_t)i + 1; } }
+    E->offsets[ntx] = (uint32_t)n;
+    uint64_t nb = (n + 63) / 64 + 1;
+    E->text.resize(2 * nb);
+    for (uint64_t b = 0; b < nb; ++b) {
+        uint64_t c0, c1, mask; bool bad;
+        unsigned char buf[64];
+        int nv = (int)std::min<int64_t>(64, std::max<int64_t>(0, (int64_t)n - (int64_t)b * 64));
+        memset(buf, '$', 64);
+        if (nv > 0) memcpy(buf, text + b * 64, nv);
+        make_block(buf, nv, c0, c1, mask, bad);
+        uint32_t tid0 = (uint32_t)(std::lower_bound(ends.begin(), ends.end(), (uint32_t)std::min<uint64_t>(b * 64, 0xffffffffu)) - ends.begin());
+        uint32_t start0 = tid0 < ntx ? E->offsets[tid0] : (uint32_t)n;
+        E->text[2 * b] = u32x4{(uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32)};
+        E->text[2 * b + 1] = u32x4{(uint32_t)mask, (uint32_t)(mask >> 32), tid0, start0};
+    }
+    E->sa.assign(sa, sa + n);
+    E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
+    E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0;
+    // k-mer table: heads of runs of equal valid k-mers in SA order
+    std::vector<uint64_t> keys; std::vector<uint32_t> begins, endsI;
+    bool have = false; uint64_t prev = 0;
+    for (uint64_t j = 0; j <= n; ++j) {
+        uint64_t w = 0; bool v = j < n && text_kmer(E->v, E->sa[j], w);
+        bool same = v && have && w == prev;
+        if (have && !same) { endsI.push_back((uint32_t)j); have = false; }
+        if (v && !same) { keys.push_back(w); begins.push_back((uint32_t)j); have = true; }
+        if (v) prev = w;
+    }
+    uint64_t cap = 16; while (cap < keys.size() * 2 + 2) cap <<= 1;
+    E->hslots.assign(cap, u32x4{0xffffffffu, 0xffffffffu, 0, 0});
+    for (size_t i = 0; i < keys.size(); ++i) {
+        uint64_t h = hmix(keys[i]) & (cap - 1);
+        while (!(E->hslots[h].x == 0xffffffffu && E->hslots[h].y == 0xffffffffu)) h = (h + 1) & (cap - 1);
+        E->hslots[h] = u32x4{(uint32_t)keys[i], (uint32_t)(keys[i] >> 32), begins[i], endsI[i]};
+    }
+    E->v.hslots = E->hslots.data(); E->v.hmask = cap - 1; E->n_kmers = keys.size();
+    return E;
+}
+void emu_index_free(void* h) { delete (EmuIndex*)h; }
+uint64_t emu_index_num_kmers(void* h) { return ((EmuIndex*)h)->n_kmers; }
+
+static bool pack_read(const char* s, int L, int W2f, int WMf, std::vector<uint64_t>& pk) {
+    pk.assign(W2f + WMf, 0);
+    bool anybad = false;
+    for (int j = 0; j < W2f; ++j) {
+        uint64_t code; uint32_t nm; bool bad;
+        int nb = std::min(32, std::max(0, L - 32 * j));
+        pack_word((const unsigned char*)s + 32 * j, nb, code, nm, bad);
+        anybad |= bad;
+        pk[j] = code;
+        pk[W2f + j / 2] |= (uint64_t)nm << (32 * (j & 1));
+    }
+    if (W2f & 1) pk[W2f + W2f / 2] |= 0xffffffff00000000ULL;
+    return !anybad;
+}
+
+static const int EMAXINT = 232, EMAXKS = 928;
+
+// Same outputs as cg_collect.  Caller provides capacities; returns -1 on overflow, -4 on a bad base.
+int emu_collect(void* h, const char* bases, const uint64_t* off, uint64_t n_reads, int strict, int lceMode,
+                uint8_t* found, uint64_t* fwd_off, int32_t* fwd_ints, uint64_t* rc_off, int32_t* rc_ints,
+                uint64_t cap_ints, uint64_t* hits_off, uint32_t* hit_tid, int32_t* hit_pos, uint8_t* hit_fwd,
+                uint64_t cap_hits) {
+    EmuIndex* E = (EmuIndex*)h;
+    auto* sc = new Scratch<EMAXINT, EMAXKS, true>();
+    std::vector<uint64_t> pk, strands;
+    uint64_t nf = 0, nr = 0, nh = 0;
+    int rcode = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        int L = (int)(off[r + 1] - off[r]);
+        int W2f = (L + 31) / 32, WMf = (W2f + 1) / 2;
+        if (W2f == 0) { W2f = 1; WMf = 1; }
+        if (!pack_read(bases + off[r], L, W2f, WMf, pk)) { rcode = -4; break; }
+        strands.assign(2 * (W2f + 1 + WMf + 1), 0);
+        build_strands(pk.data(), 1, L, W2f, WMf, strands.data());
+        ReadView rv; rv.w = strands.data(); rv.stride = 1; rv.L = L; rv.W2 = W2f + 1; rv.WM = WMf + 1;
+        bool f = collect_hits<EMAXINT, EMAXKS, true>(E->v, rv, strict != 0, lceMode, *sc);
+        if (sc->st.err) { rcode = -6; break; }
+        found[r] = f;
+        fwd_off[r] = nf; rc_off[r] = nr; hits_off[r] = nh;
+        if (f) {
+            if (nf + sc->st.nF > cap_ints || nr + sc->st.nR > cap_ints) { rcode = -1; break; }
+            for (int i = 0; i < sc->st.nF; ++i, ++nf) { auto& I = sc->st.fwd[i]; fwd_ints[4*nf] = I.begin; fwd_ints[4*nf+1] = I.end; fwd_ints[4*nf+2] = I.len; fwd_ints[4*nf+3] = I.qpos; }
+            for (int i = 0; i < sc->st.nR; ++i, ++nr) { auto& I = sc->st.rc[i]; rc_ints[4*nr] = I.begin; rc_ints[4*nr+1] = I.end; rc_ints[4*nr+2] = I.len; rc_ints[4*nr+3] = I.qpos; }
+            bool ovf = false;
+            merged_hits(*sc, [&](uint32_t t, bool fw, int i) {
+                if (nh >= cap_hits) { ovf = true; return; }
+                hit_tid[nh] = t; hit_pos[nh] = (int32_t)(fw ? sc->posF[i] : sc->posR[i]); hit_fwd[nh] = fw; ++nh;
+            });
+            if (ovf) { rcode = -1; break; }
+        }
+    }
+    fwd_off[n_reads] = nf; rc_off[n_reads] = nr; hits_off[n_reads] = nh;
+    delete sc;
+    return rcode;
+}
+
+struct VecSink {
+    std::vector<int64_t>* v; uint64_t rec;
+    void line(uint32_t dir, uint32_t q, uint32_t len, int hitPos, uint32_t tid) {
+        v->push_back((int64_t)rec); v->push_back(dir); v->push_back(q); v->push_back(len); v->push_back(hitPos); v->push_back(tid);
+    }
+};
+
+struct EmuRun {
+    std::vector<uint8_t> mateFlags; std::vector<uint16_t> mateNHits;
+    std::vector<uint64_t> expPair; std::vector<uint8_t> expCode;
+    std::vector<int64_t> junc; std::vector<uint64_t> cand;
+    std::vector<uint32_t> recNHits; std::vector<uint8_t> recSplit;
+    std::vector<uint32_t> eqLens, eqTids;     // one entry per candidate record
+    uint64_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int err = 0;
+};
+
+static bool view_of(const char* s, int L, std::vector<uint64_t>& pk, std::vector<uint64_t>& strands, ReadView& rv) {
+    int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
+    bool ok = pack_read(s, L, W2f, WMf, pk);
+    strands.assign(2 * (W2f + 1 + WMf + 1), 0);
+    build_strands(pk.data(), 1, L, W2f, WMf, strands.data());
+    rv.w = strands.data(); rv.stride = 1; rv.L = L; rv.W2 = W2f + 1; rv.WM = WMf + 1;
+    return ok;
+}
+
+// fused wt -> bsj on the host, mirroring what the session's kernels + commit step compute
+void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2,
+              uint64_t n, int lceMode) {
+    EmuIndex* TX = (EmuIndex*)txh; EmuIndex* BS = (EmuIndex*)bsjh;
+    auto* R = new EmuRun();
+    auto* sc = new Scratch<EMAXINT, EMAXKS, false>();
+    std::vector<uint64_t> pk, strands;
+    for (uint64_t i = 0; i < n; ++i) {
+        int l1 = (int)(off1[i + 1] - off1[i]), l2 = (int)(off2[i + 1] - off2[i]);
+        uint8_t fl[2]; uint32_t nh[2];
+        for (int m = 0; m < 2; ++m) {
+            ReadView rv;
+            if (!view_of(m ? r2 + off2[i] : r1 + off1[i], m ? l2 : l1, pk, strands, rv)) R->err = -4;
+            wt_mate<EMAXINT, EMAXKS>(TX->v, rv, l1, lceMode, *sc, fl[m], nh[m]);
+            if (fl[m] & MATE_ERR) R->err = -6;
+            R->mateFlags.push_back(fl[m] & 3);
+        }
+        // pair-level counters (Circall_wt.cpp:369-372,467-470,544-547,642-645)
+        R->ctr[3] += (nh[0] > 0) + (nh[1] > 0);
+        uint32_t a = nh[0] > (uint32_t)MAX_READ_OCCS ? 0 : nh[0], b = nh[1] > (uint32_t)MAX_READ_OCCS ? 0 : nh[1];
+        R->mateNHits.push_back((uint16_t)a); R->mateNHits.push_back((uint16_t)b);
+        R->ctr[1] += (a > 0) + ((a > 0) || (b > 0));
+        R->ctr[2] += a + b;
+        R->ctr[0] += 2;
+        for (int m = 0; m < 2; ++m)
+            if ((fl[m] & MATE_SEEDED) && !(fl[m] & MATE_FULL)) { R->expPair.push_back(i); R->expCode.push_back((uint8_t)(m + 1)); }
+    }
+    if (BS) {
+        uint32_t tids[MAX_READ_OCCS];
+        for (uint64_t rec = 0; rec < R->expPair.size(); ++rec) {
+            uint64_t i = R->expPair[rec]; int m = R->expCode[rec] - 1;
+            ReadView rv;
+            view_of(m ? r2 + off2[i] : r1 + off1[i], (int)(m ? off2[i + 1] - off2[i] : off1[i + 1] - off1[i]), pk, strands, rv);
+            VecSink sink{&R->junc, rec};
+            uint32_t nh; bool split; uint8_t err;
+            bsj_record<EMAXINT, EMAXKS>(BS->v, rv, lceMode, *sc, sink, nh, split, tids, err);
+            if (err) R->err = -6;
+            R->recNHits.push_back(nh); R->recSplit.push_back(split);
+            R->ctr[7] += nh > 0;
+            uint32_t c = nh > (uint32_t)MAX_READ_OCCS ? 0 : nh;
+            bool cand = c > 0 && split;
+            if (cand) { R->cand.push_back(rec); R->eqLens.push_back(c); for (uint32_t t = 0; t < c; ++t) R->eqTids.push_back(tids[t]); }
+            R->ctr[5] += cand; R->ctr[6] += c; R->ctr[4] += 1;
+        }
+    }
+    delete sc;
+    return R;
+}
+void emu_run_free(void* r) { delete (EmuRun*)r; }
+int emu_run_err(void* r) { return ((EmuRun*)r)->err; }
+void emu_run_sizes(void* r, uint64_t* out) {
+    EmuRun* R = (EmuRun*)r;
+    out[0] = R->expPair.size(); out[1] = R->junc.size() / 6; out[2] = R->cand.size(); out[3] = R->eqTids.size();
+    out[4] = R->mateFlags.size();
+}
+void emu_run_fill(void* r, uint8_t* mateFlags, uint16_t* mateNHits, uint64_t* expPair, uint8_t* expCode, int64_t* junc,
+                  uint64_t* cand, uint32_t* recNHits, uint8_t* recSplit, uint32_t* eqLens, uint32_t* eqTids, uint64_t* ctr) {
+    EmuRun* R = (EmuRun*)r;
+    auto cp = [](void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); };
+    cp(mateFlags, R->mateFlags.data(), R->mateFlags.size()); cp(mateNHits, R->mateNHits.data(), R->mateNHits.size() * 2);
+    cp(expPair, R->expPair.data(), R->expPair.size() * 8); cp(expCode, R->expCode.data(), R->expCode.size());
+    cp(junc, R->junc.data(), R->junc.size() * 8); cp(cand, R->cand.data(), R->cand.size() * 8);
+    cp(recNHits, R->recNHits.data(), R->recNHits.size() * 4); cp(recSplit, R->recSplit.data(), R->recSplit.size());
+    cp(eqLens, R->eqLens.data(), R->eqLens.size() * 4); cp(eqTids, R->eqTids.data(), R->eqTids.size() * 4);
+    memcpy(ctr, R->ctr, sizeof R->ctr);
+}
+
+// std::sort replica check: sorts packed kmerScores entries with cg::StdSort
+void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort(n); }
+
+} // extern "C"
