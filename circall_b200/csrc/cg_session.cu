@@ -1,0 +1,561 @@
+// circall_b200 — the pipeline session: Circall_wt and Circall_bsj per-pair bodies fused on the device.
+//
+// One batch = one pass of (paths relative to /root/reference/Circall_v1.0.1/):
+//   k_pack        K1  2-bit packing + N mask                       SACollectorCircall.hpp:117-128,243-260
+//   k_wt          K2-K5 collector on txIdx for both mates, K6 flags src/Circall_wt.cpp:275-342,485-517
+//   k_wt_commit   K6/K8 export decision + scalar counters          src/Circall_wt.cpp:350-372,467-470,525-547,642-645
+//   k_flag_*      K6  ordered stream compaction of the export list
+//   k_bsj         K2-K5 collector on bsjIdx for every exported record, K7 span filter, K8 counters
+//                                                                   src/Circall_bsj.cpp:300-399,488-491
+// Nothing here falls back to the host: without a CUDA device session creation fails.
+#include "cg_kernels.cuh"
+#include <algorithm>
+#include <cstring>
+
+using namespace cg;
+using namespace cgk;
+using cgi::GrowBuf;
+using cgi::PinBuf;
+
+namespace {
+
+enum { ST_BADBASE = 1, ST_TOOLONG = 2, ST_CAPACITY = 4 };
+enum { C_WT_OBS = 0, C_WT_MAP, C_WT_HITS, C_WT_UPPER, C_BSJ_OBS, C_BSJ_MAP, C_BSJ_HITS, C_BSJ_UPPER, C_NUM };
+
+// device-side per-batch header
+struct BatchHdr {
+    unsigned long long n_junc;     // rows the span filter produced (may exceed the buffer capacity)
+    unsigned long long n_eq;       // multi-transcript classes recorded
+    unsigned long long n_eq_tids;
+    uint32_t n_exp;
+    int status;
+};
+
+template <int MAXINT, int MAXKS>
+__global__ void __launch_bounds__(128)
+k_wt(IndexView ix, const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
+     int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits) {
+    extern __shared__ uint64_t smem[];
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    int L = lens[r];
+    int pairLen = lens[r & ~1ULL];                 // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+    ReadView rv = make_view(pk + r * (uint64_t)g.WT, g, L, smem);
+    Scratch<MAXINT, MAXKS, false> sc;
+    uint8_t fl; uint32_t nh;
+    wt_mate<MAXINT, MAXKS>(ix, rv, pairLen, lceMode, sc, fl, nh);
+    flags[r] = fl;
+    nhits[r] = nh;
+}
+
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* sh) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    uint32_t t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0;
+    if (w == 0) t = __reduce_add_sync(0xffffffffu, t);
+    return t;   // valid in warp 0
+}
+
+// one thread per pair: export flags, per-mate detail, scalar counters
+__global__ void __launch_bounds__(256)
+k_wt_commit(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ nhits, uint64_t n_pairs,
+            uint8_t* __restrict__ expflag, uint8_t* __restrict__ mflags_out, uint16_t* __restrict__ mnhits_out,
+            unsigned long long* ctr, BatchHdr* hdr) {
+    __shared__ uint32_t sh[8];
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t upper = 0, mapped = 0, hits = 0, obs = 0;
+    if (i < n_pairs) {
+        uint8_t f0 = flags[2 * i], f1 = flags[2 * i + 1];
+        uint32_t h0 = nhits[2 * i], h1 = nhits[2 * i + 1];
+        if ((f0 | f1) & MATE_ERR) atomicOr(&hdr->status, ST_CAPACITY);
+        upper = (h0 > 0) + (h1 > 0);                                               // Circall_wt.cpp:369,544
+        uint32_t a = h0 > (uint32_t)MAX_READ_OCCS ? 0 : h0, b = h1 > (uint32_t)MAX_READ_OCCS ? 0 : h1;   // :372,547
+        mapped = (a > 0) + ((a > 0) || (b > 0));                                   // mappedFrag is sticky across mates :467,642
+        hits = a + b;                                                              // :468,643
+        obs = 2;                                                                   // :470,645
+        expflag[2 * i] = ((f0 & MATE_SEEDED) && !(f0 & MATE_FULL)) ? 1 : 0;        // :350
+        expflag[2 * i + 1] = ((f1 & MATE_SEEDED) && !(f1 & MATE_FULL)) ? 1 : 0;    // :525
+        if (mflags_out) {
+            mflags_out[2 * i] = f0 & 3; mflags_out[2 * i + 1] = f1 & 3;
+            mnhits_out[2 * i] = (uint16_t)a; mnhits_out[2 * i + 1] = (uint16_t)b;
+        }
+    }
+    uint32_t s;
+    s = block_sum(obs, sh);    if (threadIdx.x == 0 && s) atomicAdd(&ctr[C_WT_OBS], (unsigned long long)s);
+    s = block_sum(mapped, sh); if (threadIdx.x == 0 && s) atomicAdd(&ctr[C_WT_MAP], (unsigned long long)s);
+    s = block_sum(hits, sh);   if (threadIdx.x == 0 && s) atomicAdd(&ctr[C_WT_HITS], (unsigned long long)s);
+    s = block_sum(upper, sh);  if (threadIdx.x == 0 && s) atomicAdd(&ctr[C_WT_UPPER], (unsigned long long)s);
+}
+
+// ---- ordered compaction of a byte-flag array: indices of the set flags, in order -----------------
+static const int CP_THREADS = 256, CP_ITEMS = 4, CP_TILE = CP_THREADS * CP_ITEMS;
+
+__global__ void __launch_bounds__(CP_THREADS)
+k_flag_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ bc) {
+    __shared__ uint32_t sh[8];
+    uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) c += f[base + x] ? 1 : 0;
+    uint32_t s = block_sum(c, sh);
+    if (threadIdx.x == 0) bc[blockIdx.x] = s;
+}
+// exclusive scan of nb block counts by one block; total -> *total
+__global__ void __launch_bounds__(1024)
+k_flag_scan(uint32_t* bc, uint32_t nb, uint32_t* total) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nb ? bc[i] : 0, x = v;
+        int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (l >= d) x += y; }
+        if (l == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = wsum[l], z = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, d); if (l >= d) z += y; }
+            wsum[l] = z - s;
+        }
+        __syncthreads();
+        uint32_t excl = carry + wsum[w] + x - v;
+        if (i < nb) bc[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(CP_THREADS)
+k_flag_write(const uint8_t* __restrict__ f, uint64_t n, const uint32_t* __restrict__ bc, uint32_t* __restrict__ out) {
+    __shared__ uint32_t wsum[8];
+    uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
+    uint8_t v[CP_ITEMS];
+    uint32_t c = 0;
+#pragma unroll
+    for (int x = 0; x < CP_ITEMS; ++x) { v[x] = (base + x < n) ? f[base + x] : 0; c += v[x] ? 1 : 0; }
+    int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (l >= d) x += y; }
+    if (l == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int y = 0; y < w; ++y) pre += wsum[y];
+    uint32_t o = bc[blockIdx.x] + pre + x - c;
+#pragma unroll
+    for (int y = 0; y < CP_ITEMS; ++y) if (v[y]) out[o++] = (uint32_t)(base + y);
+}
+
+// ---- Circall_bsj ----------------------------------------------------------------------------------
+struct JSink {
+    cg_junction* buf; unsigned long long* cursor; uint64_t cap; uint32_t rec;
+    __device__ __forceinline__ void line(uint32_t dir, uint32_t q, uint32_t len, int hitPos, uint32_t tid) {
+        unsigned long long s = atomicAdd(cursor, 1ULL);
+        if (s < cap) { cg_junction j; j.rec = rec; j.dir = dir; j.query_pos = q; j.len = len; j.hit_pos = hitPos; j.tid = tid; buf[s] = j; }
+    }
+};
+
+struct BsjOut {
+    cg_junction* junc; uint64_t junc_cap;
+    uint4* eq_ent; uint64_t eq_cap;            // {rec, first tid slot, number of tids, 0}
+    uint32_t* eq_tids; uint64_t eq_tids_cap;
+    uint32_t* rec_nhits; uint8_t* rec_split;
+    unsigned long long* per_bsj;               // dense single-transcript class counters
+    unsigned long long* ctr;
+    BatchHdr* hdr;
+};
+
+// one thread per exported record.  exp_mate == nullptr: record rec is mate 1 of pair rec (stage 2).
+// do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes
+template <int MAXINT, int MAXKS>
+__global__ void __launch_bounds__(128)
+k_bsj(IndexView ix, const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
+      const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, int lceMode, BsjOut o, int do_counts) {
+    extern __shared__ uint64_t smem[];
+    uint64_t rec = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t nrec = exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed;
+    bool valid = rec < nrec;
+    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
+    if (valid) {
+        uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
+        int L = lens[r];
+        ReadView rv = make_view(pk + r * (uint64_t)g.WT, g, L, smem);
+        Scratch<MAXINT, MAXKS, false> sc;
+        uint32_t tids[MAX_READ_OCCS];
+        JSink sink{o.junc, &o.hdr->n_junc, o.junc_cap, (uint32_t)rec};
+        uint32_t nh; bool split; uint8_t err;
+        bsj_record<MAXINT, MAXKS>(ix, rv, lceMode, sc, sink, nh, split, tids, err);
+        if (err) atomicOr(&o.hdr->status, ST_CAPACITY);
+        o.rec_nhits[rec] = nh;
+        o.rec_split[rec] = split ? 1 : 0;
+        upper = nh > 0;                                                          // Circall_bsj.cpp:383
+        uint32_t c = nh > (uint32_t)MAX_READ_OCCS ? 0 : nh;                      // :385
+        bool cand = c > 0 && split;                                              // :390
+        obs = 1; mapped = cand; hits = c;                                        // :488-491
+        if (cand) {
+            if (c == 1) {
+                if (do_counts & 1) atomicAdd(&o.per_bsj[tids[0]], 1ULL);         // single-transcript class (EquivalenceClassBuilder.hpp:112-130)
+            } else if (do_counts & 2) {
+                unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL);
+                unsigned long long s = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)c);
+                if (e < o.eq_cap && s + c <= o.eq_tids_cap) {
+                    o.eq_ent[e] = make_uint4((uint32_t)rec, (uint32_t)s, c, 0u);
+                    for (uint32_t t = 0; t < c; ++t) o.eq_tids[s + t] = tids[t];
+                }
+            }
+        }
+    }
+    if (do_counts & 1) {
+        uint32_t s;
+        s = __reduce_add_sync(0xffffffffu, obs);    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)s);
+        s = __reduce_add_sync(0xffffffffu, mapped); if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)s);
+        s = __reduce_add_sync(0xffffffffu, hits);   if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)s);
+        s = __reduce_add_sync(0xffffffffu, upper);  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)s);
+    }
+}
+
+inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+} // namespace
+
+struct cg_session {
+    const cg_index* tx = nullptr;
+    const cg_index* bsj = nullptr;
+    cg_opts opts{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    bool pending = false;
+    // batch state
+    uint64_t n_pairs = 0;
+    int max_len = 0;
+    PackGeom geom{};
+    bool input_on_device = false;
+    const unsigned char* in_r1 = nullptr; const unsigned char* in_r2 = nullptr;   // device pointers of the batch
+    const uint64_t* in_off1 = nullptr; const uint64_t* in_off2 = nullptr;
+    // device buffers
+    GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
+        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr;
+    unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
+    uint64_t n_bsj = 0;
+    uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
+    // host result buffers
+    PinBuf h_hdr;
+    std::vector<uint32_t> h_exp_mate, h_exp_pair, h_cand, h_recnh, h_eq_tids_raw, h_eq_tids;
+    std::vector<uint8_t> h_exp_code, h_recsp, h_mflags;
+    std::vector<uint16_t> h_mnhits;
+    std::vector<cg_junction> h_junc;
+    std::vector<uint4> h_eqent;
+    std::vector<uint64_t> h_eq_off;
+    uint32_t wt_read_len = 0, bsj_read_len = 0;
+};
+
+namespace {
+
+template <class K, class... A>
+int launch(cg_session* s, K kern, dim3 grid, dim3 block, size_t smem, A... args) {
+    if (grid.x == 0) return CG_OK;      // empty batch: nothing to do (the batch header is already zero)
+    if (smem > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, s->stream>>>(args...);
+    CG_CUDA(cudaGetLastError());
+    ++s->launches;
+    return CG_OK;
+}
+
+int run_bsj_stage(cg_session* s, int do_counts) {
+    const int BS = 128;
+    const uint64_t n_reads = 2 * s->n_pairs;
+    const bool stage2 = s->opts.stage == 2;
+    const uint64_t worst = stage2 ? s->n_pairs : n_reads;
+    BsjOut o;
+    o.junc = s->d_junc.as<cg_junction>(); o.junc_cap = s->junc_cap;
+    o.eq_ent = s->d_eqent.as<uint4>(); o.eq_cap = s->eq_cap;
+    o.eq_tids = s->d_eqtids.as<uint32_t>(); o.eq_tids_cap = s->eq_tids_cap;
+    o.rec_nhits = s->d_recnh.as<uint32_t>(); o.rec_split = s->d_recsp.as<uint8_t>();
+    o.per_bsj = s->d_acc; o.ctr = s->d_acc + s->n_bsj; o.hdr = s->d_hdr.as<BatchHdr>();
+    size_t smem = (size_t)BS * s->geom.chunk() * 8;
+    const uint32_t* em = stage2 ? nullptr : s->d_exp.as<uint32_t>();
+    IndexView v = s->bsj->view();
+    if (s->max_len <= 160)
+        return launch(s, k_bsj<136, 544>, dim3(grid_for(worst, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(),
+                      s->geom, em, s->n_pairs, s->opts.lce_mode, o, do_counts);
+    return launch(s, k_bsj<232, 928>, dim3(grid_for(worst, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(),
+                  s->geom, em, s->n_pairs, s->opts.lce_mode, o, do_counts);
+}
+
+int run_batch(cg_session* s) {
+    const uint64_t n_pairs = s->n_pairs, n_reads = 2 * n_pairs;
+    const int stage = s->opts.stage;
+    s->geom = PackGeom::make(s->max_len);
+    const PackGeom g = s->geom;
+    CG_CUDA(s->d_pk.reserve(n_reads * g.WT * 8));
+    CG_CUDA(s->d_lens.reserve(n_reads * 2));
+    CG_CUDA(s->d_flags.reserve(n_reads));
+    CG_CUDA(s->d_nhits.reserve(n_reads * 4));
+    CG_CUDA(s->d_expflag.reserve(n_reads + 16));
+    CG_CUDA(s->d_exp.reserve(n_reads * 4));
+    CG_CUDA(s->d_bc.reserve((n_reads / CP_TILE + 2) * 4));
+    CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
+    if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
+    if (stage != 1) {
+        CG_CUDA(s->d_recnh.reserve(n_reads * 4));
+        CG_CUDA(s->d_recsp.reserve(n_reads));
+        uint64_t want_j = std::max<uint64_t>(1u << 20, 2 * n_reads);
+        if (s->junc_cap < want_j) { CG_CUDA(s->d_junc.reserve(want_j * sizeof(cg_junction))); s->junc_cap = want_j; }
+        uint64_t want_e = std::max<uint64_t>(1u << 18, n_reads / 4);
+        if (s->eq_cap < want_e) { CG_CUDA(s->d_eqent.reserve(want_e * 16)); s->eq_cap = want_e; }
+        uint64_t want_t = want_e * 8;
+        if (s->eq_tids_cap < want_t) { CG_CUDA(s->d_eqtids.reserve(want_t * 4)); s->eq_tids_cap = want_t; }
+    }
+    CG_CUDA(cudaMemsetAsync(s->d_hdr.p, 0, sizeof(BatchHdr), s->stream));
+    CG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    int rc;
+    // K1
+    rc = launch(s, k_pack, dim3(grid_for(n_reads * g.W2f, 256)), dim3(256), 0, s->in_r1, s->in_off1, s->in_r2, s->in_off2, n_pairs, g,
+                s->max_len, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), &s->d_hdr.as<BatchHdr>()->status);
+    if (rc) return rc;
+    if (stage != 2) {
+        const int BS = 128;
+        size_t smem = (size_t)BS * g.chunk() * 8;
+        IndexView v = s->tx->view();
+        if (s->max_len <= 160)
+            rc = launch(s, k_wt<136, 544>, dim3(grid_for(n_reads, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g,
+                        n_reads, s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>());
+        else
+            rc = launch(s, k_wt<232, 928>, dim3(grid_for(n_reads, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g,
+                        n_reads, s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>());
+        if (rc) return rc;
+        rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
+                    s->d_expflag.as<uint8_t>(), s->opts.keep_mate_detail ? s->d_mflags.as<uint8_t>() : (uint8_t*)nullptr,
+                    s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_acc + s->n_bsj, s->d_hdr.as<BatchHdr>());
+        if (rc) return rc;
+        uint32_t nb = grid_for(n_reads, CP_TILE);
+        rc = launch(s, k_flag_count, dim3(nb), dim3(CP_THREADS), 0, s->d_expflag.as<uint8_t>(), n_reads, s->d_bc.as<uint32_t>());
+        if (rc) return rc;
+        rc = launch(s, k_flag_scan, dim3(1), dim3(1024), 0, s->d_bc.as<uint32_t>(), nb, &s->d_hdr.as<BatchHdr>()->n_exp);
+        if (rc) return rc;
+        rc = launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, s->d_expflag.as<uint8_t>(), n_reads, s->d_bc.as<uint32_t>(), s->d_exp.as<uint32_t>());
+        if (rc) return rc;
+    }
+    if (stage != 1) {
+        rc = run_bsj_stage(s, 3);
+        if (rc) return rc;
+    }
+    CG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    CG_CUDA(cudaMemcpyAsync(s->h_hdr.p, s->d_hdr.p, sizeof(BatchHdr), cudaMemcpyDeviceToHost, s->stream));
+    s->pending = true;
+    return CG_OK;
+}
+
+template <class T>
+int d2h(cg_session* s, std::vector<T>& dst, const void* src, uint64_t n) {
+    dst.resize(n);
+    if (n) CG_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    return CG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* opts, cg_session** out) {
+    if (!out) CG_FAIL(CG_ERR_ARG, "null argument");
+    cg_opts o{};
+    if (opts) o = *opts;
+    if (o.stage < 0 || o.stage > 2) CG_FAIL(CG_ERR_ARG, "stage must be 0, 1 or 2");
+    if (o.stage != 2 && !tx) CG_FAIL(CG_ERR_ARG, "this stage needs the transcript index");
+    if (o.stage != 1 && !bsj) CG_FAIL(CG_ERR_ARG, "this stage needs the BSJ index");
+    if (tx && bsj && tx->device != bsj->device) CG_FAIL(CG_ERR_ARG, "both indices must live on the same device");
+    if (o.lce_mode != 0 && o.lce_mode != 1) CG_FAIL(CG_ERR_ARG, "lce_mode must be 0 or 1");
+    int device = tx ? tx->device : bsj->device;
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); CG_FAIL(CG_ERR_CUDA, "no CUDA device available (libcircall_gpu has no CPU fallback)"); }
+    CG_CUDA(cudaSetDevice(device));
+    cg_session* s = new cg_session();
+    s->tx = tx; s->bsj = bsj; s->opts = o; s->device = device;
+    s->n_bsj = (o.stage != 1 && bsj) ? bsj->n_tx : 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_acc, (s->n_bsj + C_NUM) * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_acc, 0, (s->n_bsj + C_NUM) * 8);
+    if (e == cudaSuccess) e = s->h_hdr.reserve(sizeof(BatchHdr));
+    if (e != cudaSuccess) { int rc = cgi::cuda_fail(e, "session set-up", __FILE__, __LINE__); cg_session_destroy(s); return rc; }
+    *out = s;
+    return CG_OK;
+}
+
+void cg_session_destroy(cg_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
+                       &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr})
+        b->release();
+    s->h_hdr.release();
+    if (s->d_acc) cudaFree(s->d_acc);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int cg_session_submit(cg_session* s, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2, uint64_t n_pairs) {
+    if (!s || !off1 || !off2 || (n_pairs && (!r1 || !r2))) CG_FAIL(CG_ERR_ARG, "null argument");
+    if (s->pending) CG_FAIL(CG_ERR_STATE, "previous batch not fetched");
+    if (n_pairs >= (1ULL << 30)) CG_FAIL(CG_ERR_ARG, "batch too large (limit 2^30 pairs)");
+    CG_CUDA(cudaSetDevice(s->device));
+    uint64_t bytes1 = off1[n_pairs] - off1[0], bytes2 = off2[n_pairs] - off2[0];
+    if (off1[0] != 0 || off2[0] != 0) CG_FAIL(CG_ERR_ARG, "offsets must start at 0");
+    uint64_t mx = 0;
+    for (uint64_t i = 0; i < n_pairs; ++i) {
+        if (off1[i + 1] < off1[i] || off2[i + 1] < off2[i]) CG_FAIL(CG_ERR_ARG, "offsets must be non-decreasing");
+        mx = std::max(mx, std::max(off1[i + 1] - off1[i], off2[i + 1] - off2[i]));
+    }
+    if (mx > CG_MAX_READ_LEN) CG_FAIL(CG_ERR_LENGTH, "a read is longer than CG_MAX_READ_LEN");
+    CG_CUDA(s->d_r1.reserve(bytes1 + 64)); CG_CUDA(s->d_r2.reserve(bytes2 + 64));
+    CG_CUDA(s->d_off1.reserve((n_pairs + 1) * 8)); CG_CUDA(s->d_off2.reserve((n_pairs + 1) * 8));
+    if (bytes1) CG_CUDA(cudaMemcpyAsync(s->d_r1.p, r1, bytes1, cudaMemcpyHostToDevice, s->stream));
+    if (bytes2) CG_CUDA(cudaMemcpyAsync(s->d_r2.p, r2, bytes2, cudaMemcpyHostToDevice, s->stream));
+    CG_CUDA(cudaMemcpyAsync(s->d_off1.p, off1, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    CG_CUDA(cudaMemcpyAsync(s->d_off2.p, off2, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    s->in_r1 = s->d_r1.as<unsigned char>(); s->in_r2 = s->d_r2.as<unsigned char>();
+    s->in_off1 = s->d_off1.as<uint64_t>(); s->in_off2 = s->d_off2.as<uint64_t>();
+    s->n_pairs = n_pairs; s->max_len = (int)mx; s->input_on_device = false;
+    if (s->wt_read_len == 0 && n_pairs) s->wt_read_len = (uint32_t)(off1[1] - off1[0]);
+    return run_batch(s);
+}
+
+int cg_session_submit_device(cg_session* s, const char* d_r1, const uint64_t* d_off1, const char* d_r2, const uint64_t* d_off2,
+                             uint64_t n_pairs, uint32_t max_read_len) {
+    if (!s || !d_off1 || !d_off2 || (n_pairs && (!d_r1 || !d_r2))) CG_FAIL(CG_ERR_ARG, "null argument");
+    if (s->pending) CG_FAIL(CG_ERR_STATE, "previous batch not fetched");
+    if (n_pairs >= (1ULL << 30)) CG_FAIL(CG_ERR_ARG, "batch too large (limit 2^30 pairs)");
+    if (max_read_len == 0 || max_read_len > CG_MAX_READ_LEN) CG_FAIL(CG_ERR_LENGTH, "max_read_len must be in 1..CG_MAX_READ_LEN");
+    CG_CUDA(cudaSetDevice(s->device));
+    s->in_r1 = (const unsigned char*)d_r1; s->in_r2 = (const unsigned char*)d_r2; s->in_off1 = d_off1; s->in_off2 = d_off2;
+    s->n_pairs = n_pairs; s->max_len = (int)max_read_len; s->input_on_device = true;
+    return run_batch(s);
+}
+
+int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
+    if (!s || !out) CG_FAIL(CG_ERR_ARG, "null argument");
+    if (!s->pending) CG_FAIL(CG_ERR_STATE, "no batch submitted");
+    CG_CUDA(cudaSetDevice(s->device));
+    CG_CUDA(cudaStreamSynchronize(s->stream));
+    s->pending = false;
+    BatchHdr hdr = *s->h_hdr.as<BatchHdr>();
+    if (hdr.status & ST_BADBASE) CG_FAIL(CG_ERR_BASE, "a read holds a character outside ACGTNacgtn");
+    if (hdr.status & ST_TOOLONG) CG_FAIL(CG_ERR_LENGTH, "a read is longer than the batch's max_read_len");
+    if (hdr.status & ST_CAPACITY) CG_FAIL(CG_ERR_CAPACITY, "collector capacity exceeded (intervals / k-mer scores / hits)");
+    float ms = 0;
+    CG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    const int stage = s->opts.stage;
+    uint64_t n_exp = stage == 2 ? s->n_pairs : hdr.n_exp;
+    // the span filter / class lists never drop rows: when a list outgrew its buffer, grow it and redo the
+    // Circall_bsj stage of this batch with the counters switched off (they were already accumulated)
+    if (stage != 1 && (hdr.n_junc > s->junc_cap || hdr.n_eq > s->eq_cap || hdr.n_eq_tids > s->eq_tids_cap)) {
+        if (hdr.n_junc > s->junc_cap) { CG_CUDA(s->d_junc.reserve((hdr.n_junc + 1024) * sizeof(cg_junction))); s->junc_cap = hdr.n_junc + 1024; }
+        if (hdr.n_eq > s->eq_cap) { CG_CUDA(s->d_eqent.reserve((hdr.n_eq + 1024) * 16)); s->eq_cap = hdr.n_eq + 1024; }
+        if (hdr.n_eq_tids > s->eq_tids_cap) { CG_CUDA(s->d_eqtids.reserve((hdr.n_eq_tids + 1024) * 4)); s->eq_tids_cap = hdr.n_eq_tids + 1024; }
+        BatchHdr* dh = s->d_hdr.as<BatchHdr>();
+        CG_CUDA(cudaMemsetAsync(&dh->n_junc, 0, 3 * sizeof(unsigned long long), s->stream));
+        int rc = run_bsj_stage(s, 2);
+        if (rc) return rc;
+        CG_CUDA(cudaMemcpyAsync(s->h_hdr.p, s->d_hdr.p, sizeof(BatchHdr), cudaMemcpyDeviceToHost, s->stream));
+        CG_CUDA(cudaStreamSynchronize(s->stream));
+        BatchHdr h2 = *s->h_hdr.as<BatchHdr>();
+        if (h2.n_junc != hdr.n_junc || h2.n_eq != hdr.n_eq || h2.n_eq_tids != hdr.n_eq_tids) CG_FAIL(CG_ERR_STATE, "redo of the bsj stage disagreed with the first pass");
+    }
+    memset(out, 0, sizeof *out);
+    out->n_pairs = s->n_pairs;
+    out->device_ms = ms;
+    out->n_export = n_exp;
+    out->n_junc = hdr.n_junc;
+    out->n_eq = hdr.n_eq;
+    if (s->input_on_device && s->wt_read_len == 0 && s->n_pairs) {
+        uint16_t l0 = 0;
+        CG_CUDA(cudaMemcpy(&l0, s->d_lens.p, 2, cudaMemcpyDeviceToHost));
+        s->wt_read_len = l0;
+    }
+    if (stage != 1 && s->bsj_read_len == 0 && n_exp) {
+        uint32_t m0 = 0; uint16_t l0 = 0;
+        if (stage != 2) CG_CUDA(cudaMemcpy(&m0, s->d_exp.p, 4, cudaMemcpyDeviceToHost));
+        CG_CUDA(cudaMemcpy(&l0, s->d_lens.as<uint16_t>() + m0, 2, cudaMemcpyDeviceToHost));
+        s->bsj_read_len = l0;
+    }
+    if (!want_lists) return CG_OK;
+    int rc;
+    if (stage != 2) {
+        if ((rc = d2h(s, s->h_exp_mate, s->d_exp.p, n_exp))) return rc;
+    }
+    if (s->opts.keep_mate_detail && stage != 2) {
+        if ((rc = d2h(s, s->h_mflags, s->d_mflags.p, 2 * s->n_pairs))) return rc;
+        if ((rc = d2h(s, s->h_mnhits, s->d_mnhits.p, 2 * s->n_pairs))) return rc;
+    }
+    if (stage != 1) {
+        if ((rc = d2h(s, s->h_junc, s->d_junc.p, hdr.n_junc))) return rc;
+        if ((rc = d2h(s, s->h_recnh, s->d_recnh.p, n_exp))) return rc;
+        if ((rc = d2h(s, s->h_recsp, s->d_recsp.p, n_exp))) return rc;
+        if ((rc = d2h(s, s->h_eqent, s->d_eqent.p, hdr.n_eq))) return rc;
+        if ((rc = d2h(s, s->h_eq_tids_raw, s->d_eqtids.p, hdr.n_eq_tids))) return rc;
+    }
+    CG_CUDA(cudaStreamSynchronize(s->stream));
+    s->h_exp_pair.resize(n_exp); s->h_exp_code.resize(n_exp);
+    for (uint64_t r = 0; r < n_exp; ++r) {
+        uint32_t m = stage == 2 ? (uint32_t)(2 * r) : s->h_exp_mate[r];
+        s->h_exp_pair[r] = m >> 1; s->h_exp_code[r] = (uint8_t)((m & 1) + 1);
+    }
+    out->exp_pair = s->h_exp_pair.data(); out->exp_code = s->h_exp_code.data();
+    if (s->opts.keep_mate_detail && stage != 2) { out->mate_flags = s->h_mflags.data(); out->mate_nhits = s->h_mnhits.data(); }
+    if (stage != 1) {
+        out->junc = s->h_junc.data();
+        out->rec_nhits = s->h_recnh.data(); out->rec_split = s->h_recsp.data();
+        s->h_cand.clear();
+        for (uint64_t r = 0; r < n_exp; ++r)
+            if (s->h_recsp[r] && s->h_recnh[r] > 0 && s->h_recnh[r] <= (uint32_t)MAX_READ_OCCS) s->h_cand.push_back((uint32_t)r);
+        out->n_cand = s->h_cand.size(); out->cand_rec = s->h_cand.data();
+        // classes in record order
+        std::sort(s->h_eqent.begin(), s->h_eqent.end(), [](const uint4& a, const uint4& b) { return a.x < b.x; });
+        s->h_eq_off.assign(1, 0); s->h_eq_tids.clear();
+        for (auto& e : s->h_eqent) {
+            s->h_eq_tids.insert(s->h_eq_tids.end(), s->h_eq_tids_raw.begin() + e.y, s->h_eq_tids_raw.begin() + e.y + e.z);
+            s->h_eq_off.push_back(s->h_eq_tids.size());
+        }
+        out->eq_off = s->h_eq_off.data(); out->eq_tids = s->h_eq_tids.data();
+    }
+    return CG_OK;
+}
+
+int cg_session_counters(cg_session* s, cg_counters* c, uint64_t* per_bsj, uint64_t n_bsj) {
+    if (!s || !c) CG_FAIL(CG_ERR_ARG, "null argument");
+    if (s->pending) CG_FAIL(CG_ERR_STATE, "fetch the pending batch first");
+    if (per_bsj && n_bsj != s->n_bsj) CG_FAIL(CG_ERR_ARG, "per_bsj must hold one entry per BSJ reference");
+    CG_CUDA(cudaSetDevice(s->device));
+    unsigned long long v[C_NUM];
+    CG_CUDA(cudaMemcpy(v, s->d_acc + s->n_bsj, sizeof v, cudaMemcpyDeviceToHost));
+    c->wt_num_observed = v[C_WT_OBS]; c->wt_num_mapped = v[C_WT_MAP]; c->wt_num_hits = v[C_WT_HITS]; c->wt_upper_bound = v[C_WT_UPPER];
+    c->bsj_num_observed = v[C_BSJ_OBS]; c->bsj_num_mapped = v[C_BSJ_MAP]; c->bsj_num_hits = v[C_BSJ_HITS]; c->bsj_upper_bound = v[C_BSJ_UPPER];
+    c->wt_read_len = s->wt_read_len; c->bsj_read_len = s->bsj_read_len;
+    if (per_bsj && n_bsj) CG_CUDA(cudaMemcpy(per_bsj, s->d_acc, n_bsj * 8, cudaMemcpyDeviceToHost));
+    return CG_OK;
+}
+
+int cg_session_accumulator(cg_session* s, void** dptr, uint64_t* n_u64) {
+    if (!s || !dptr || !n_u64) CG_FAIL(CG_ERR_ARG, "null argument");
+    *dptr = s->d_acc; *n_u64 = s->n_bsj + C_NUM;
+    return CG_OK;
+}
+
+uint64_t cg_session_launches(const cg_session* s) { return s ? s->launches : 0; }
+
+} // extern "C"

@@ -155,9 +155,10 @@ void cg_session_destroy(cg_session* s);
  * (the jobs pair_sequence_parser hands to processReadsQuasi, Circall_wt.cpp:237-241) */
 int cg_session_submit(cg_session* s, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2,
                       uint64_t n_pairs);
-/* same, buffers already resident in this session's GPU memory (bench.py `value` leg) */
+/* same, buffers already resident in this session's GPU memory (bench.py `value` leg); max_read_len bounds
+ * every read of the batch (a longer read fails the batch with CG_ERR_LENGTH at fetch) */
 int cg_session_submit_device(cg_session* s, const char* d_r1, const uint64_t* d_off1, const char* d_r2,
-                             const uint64_t* d_off2, uint64_t n_pairs, uint64_t bytes1, uint64_t bytes2);
+                             const uint64_t* d_off2, uint64_t n_pairs, uint32_t max_read_len);
 /* wait for the batch and expose its results (host memory owned by the session until the next submit).
  * want_lists = 0 skips the device->host copy of the per-record lists (counters still accumulate). */
 int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out);
@@ -169,10 +170,15 @@ int cg_session_counters(cg_session* s, cg_counters* c, uint64_t* per_bsj, uint64
 int cg_session_accumulator(cg_session* s, void** dptr, uint64_t* n_u64);
 /* kernels launched by this session so far (bench.py gpu_launches) */
 uint64_t cg_session_launches(const cg_session* s);
-/* device allocation helpers for the resident-input leg */
+/* device / pinned-host allocation helpers (resident-input leg, pinned staging buffers of the host streamer) */
 int cg_device_alloc(int device, uint64_t bytes, void** dptr);
 int cg_device_free(int device, void* dptr);
 int cg_device_upload(int device, void* dptr, const void* src, uint64_t bytes);
+int cg_device_download(int device, void* dst, const void* dptr, uint64_t bytes);
+int cg_host_alloc(uint64_t bytes, void** ptr);
+int cg_host_free(void* ptr);
+/* overwrite a buffer larger than the L2 so that the next timed pass starts cold */
+int cg_device_flush_l2(int device);
 
 /* random 32-B-sector gather microbenchmark (SURVEY.md §8 d "random-sector ceiling"): every thread
  * issues `per_thread` dependent-free 32-B loads at hashed addresses inside a `bytes`-sized buffer.

@@ -1,0 +1,183 @@
+"""GPU parity tests: libcircall_gpu.so (through its C ABI) against the CPU oracle on the same inputs.
+
+Integer / index work: everything is compared bit-exactly (multisets where the reference's own order is
+nondeterministic, SURVEY.md §8 c)."""
+import numpy as np
+import pytest
+
+from tests.helpers import make_reads, ragged
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_world(small_world):
+    import circall_b200 as cg
+    if cg.device_count() == 0:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    T, otx, obsj = small_world
+    gtx = cg.Index.build(T.tx_text)
+    gbsj = cg.Index.build(T.bsj_text)
+    return cg, T, otx, obsj, gtx, gbsj
+
+
+def test_index_matches_oracle(gpu_world):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    for o, g in ((otx, gtx), (obsj, gbsj)):
+        assert g.text_len == o.text_len and g.n_tx == o.n_tx
+        assert np.array_equal(g.suffix_array(), o.sa)          # the suffix array is unique
+        assert g.n_kmers == o.n_kmers
+        for t in (0, o.n_tx // 2, o.n_tx - 1):
+            assert g.tx_len(t) == int(o.lens[t]) and g.tx_offset(t) == int(o.offsets[t])
+
+
+def _cmp_collect(cg, oidx, gidx, reads, lce_mode):
+    res = cg.collect(gidx, reads, strict=True, lce_mode=lce_mode)
+    n = reads.shape[0]
+    for i in range(n):
+        found, f, r, hits = oidx.collect(reads[i].tobytes(), strict=True, lce_mode=lce_mode)
+        assert bool(res["found"][i]) == found, i
+        if not found:
+            continue
+        gf = res["fwd_ints"][int(res["fwd_off"][i]):int(res["fwd_off"][i + 1])]
+        gr = res["rc_ints"][int(res["rc_off"][i]):int(res["rc_off"][i + 1])]
+        assert np.array_equal(gf, f), (i, gf, f)
+        assert np.array_equal(gr, r), (i, gr, r)
+        a, b = int(res["hits_off"][i]), int(res["hits_off"][i + 1])
+        gh = list(zip(res["hit_tid"][a:b].tolist(), res["hit_pos"][a:b].tolist(), [bool(x) for x in res["hit_fwd"][a:b]]))
+        assert gh == hits, (i, gh[:4], hits[:4])
+
+
+@pytest.mark.parametrize("lce_mode", [0, 1])
+def test_collect_parity(gpu_world, lce_mode):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 5, 1500)
+    _cmp_collect(cg, otx, gtx, r1, lce_mode)
+    _cmp_collect(cg, obsj, gbsj, r2, lce_mode)
+
+
+def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0):
+    import oracle
+    R = oracle.Run(otx, obsj, 2, r1, r2, lce_mode=lce_mode)
+    S = cg.Session(gtx, gbsj, stage=0, lce_mode=lce_mode, keep_mate_detail=True)
+    B = S.run(r1, r2)
+    p, c = R.wt_export()
+    assert np.array_equal(B.exp_pair, p.astype(np.uint32)) and np.array_equal(B.exp_code, c)
+    fl, nh = R.wt_mates()
+    assert np.array_equal(B.mate_flags, fl) and np.array_equal(B.mate_nhits, nh)
+    oj = R.bsj_junctions()
+    gj = np.stack([B.junc[k].astype(np.int64) for k in ("rec", "dir", "query_pos", "len", "hit_pos", "tid")], 1) if B.n_junc else np.zeros((0, 6), np.int64)
+    assert sorted(map(tuple, oj.tolist())) == sorted(map(tuple, gj.tolist()))
+    assert np.array_equal(B.cand_rec, R.bsj_candidates().astype(np.uint32))
+    onh, osp = R.bsj_records()
+    assert np.array_equal(B.rec_nhits, onh) and np.array_equal(B.rec_split, osp)
+    ctr, per_bsj = S.counters()
+    ow, ob = R.counters(0), R.counters(1)
+    assert (ctr["wt_num_observed"], ctr["wt_num_mapped"], ctr["wt_num_hits"], ctr["wt_upper_bound"]) == \
+           (ow["numObserved"], ow["numMapped"], ow["numHits"], ow["upperBound"])
+    assert (ctr["bsj_num_observed"], ctr["bsj_num_mapped"], ctr["bsj_num_hits"], ctr["bsj_upper_bound"]) == \
+           (ob["numObserved"], ob["numMapped"], ob["numHits"], ob["upperBound"])
+    assert ctr["wt_read_len"] == ow["readLen"] and ctr["bsj_read_len"] == ob["readLen"]
+    oeq = R.eq_classes(1)
+    geq = B.eq_classes()
+    for t in np.nonzero(per_bsj)[0]:
+        geq[(int(t),)] = int(per_bsj[t])
+    assert geq == oeq
+    S.close()
+    return B, R
+
+
+@pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0)])
+def test_pipeline_parity(gpu_world, L, lce_mode):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 100 + L, 20000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode)
+    assert B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0
+
+
+def test_pipeline_ragged_and_edge_reads(gpu_world):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 77, 6000, n_rate=0.01)
+    # whole-N reads, homopolymers and reads shorter than k
+    r1[0, :] = ord("N"); r2[1, :] = ord("A"); r1[2, 40:] = ord("N"); r1[3, :] = ord("n")
+    r1[4] = np.frombuffer(bytes(r1[4]).lower(), np.uint8)
+    a, b = ragged(r1, r2, 3)
+    _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, a, b)
+
+
+def test_pipeline_empty_batch(gpu_world):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    S = cg.Session(gtx, gbsj)
+    B = S.run(np.zeros((0, 100), np.uint8), np.zeros((0, 100), np.uint8))
+    assert B.n_export == 0 and B.n_junc == 0
+    ctr, per = S.counters()
+    assert ctr["wt_num_observed"] == 0 and int(per.sum()) == 0
+
+
+def test_pipeline_rejects_bad_base_and_long_read(gpu_world):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 9, 64)
+    r1[5, 17] = ord("R")
+    S = cg.Session(gtx, gbsj)
+    with pytest.raises(cg.CircallError) as e:
+        S.run(r1, r2)
+    assert e.value.code == -4
+    S.close()
+    S = cg.Session(gtx, gbsj)
+    with pytest.raises(cg.CircallError) as e:
+        S.run(np.full((2, 300), ord("A"), np.uint8), np.full((2, 300), ord("C"), np.uint8))
+    assert e.value.code == -5
+
+
+def test_stages_compose(gpu_world):
+    """wt-only then bsj-only on the exported records == fused (the Circall.sh file hand-off)."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 31, 8000)
+    F = cg.Session(gtx, gbsj, stage=0).run(r1, r2)
+    W = cg.Session(gtx, None, stage=1).run(r1, r2)
+    assert np.array_equal(W.exp_pair, F.exp_pair) and np.array_equal(W.exp_code, F.exp_code)
+    e1 = np.where(W.exp_code[:, None] == 1, r1[W.exp_pair], r2[W.exp_pair])
+    e2 = np.where(W.exp_code[:, None] == 1, r2[W.exp_pair], r1[W.exp_pair])
+    Bs = cg.Session(None, gbsj, stage=2).run(e1, e2)
+    key = lambda j: sorted(zip(j["rec"].tolist(), j["dir"].tolist(), j["query_pos"].tolist(), j["len"].tolist(), j["hit_pos"].tolist(), j["tid"].tolist()))
+    assert key(Bs.junc) == key(F.junc)
+    assert np.array_equal(Bs.cand_rec, F.cand_rec)
+
+
+def test_batches_accumulate(gpu_world):
+    """Counters are linear in the input: two half batches == one full batch."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 41, 10000)
+    S1 = cg.Session(gtx, gbsj)
+    S1.run(r1, r2, want_lists=False)
+    c1, p1 = S1.counters()
+    S2 = cg.Session(gtx, gbsj)
+    S2.run(r1[:5000], r2[:5000], want_lists=False)
+    S2.run(r1[5000:], r2[5000:], want_lists=False)
+    c2, p2 = S2.counters()
+    assert c1 == c2 and np.array_equal(p1, p2)
+
+
+def test_merge_pairs_parity(gpu_world):
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    import oracle
+    rng = np.random.default_rng(8)
+    left, right, ls, rs = [], [], [], []
+    for i in range(400):
+        def mk():
+            n = int(rng.integers(0, 7)) if rng.random() < 0.9 else int(rng.integers(150, 260))
+            tids = np.sort(rng.choice(300 if n < 100 else 400, n, replace=False))
+            return [(int(t), int(rng.integers(-30, 3000)), bool(rng.integers(0, 2))) for t in tids]
+        l, r = mk(), mk()
+        if rng.random() < 0.3:
+            r = [(t, int(rng.integers(-30, 3000)), bool(rng.integers(0, 2))) for t, _, _ in l]
+        left.append(l); right.append(r)
+        ls.append(bool(l) or rng.random() < 0.5); rs.append(bool(r) or rng.random() < 0.5)
+    joff, joint, tm = cg.merge_pairs(left, right, ls, rs, read_len=100, max_num_hits=200)
+    for i in range(400):
+        oj, otm = oracle.merge_fuzzy(left[i], right[i], ls[i], rs[i], 100, 200)
+        gj = joint[int(joff[i]):int(joff[i + 1])]
+        # orphan rows carry no mate fields
+        assert np.array_equal(gj[:, [0, 1, 2, 6]], oj[:, [0, 1, 2, 6]]) and otm == bool(tm[i]), i
+        paired = oj[:, 6] == 3
+        assert np.array_equal(gj[paired], oj[paired])
