@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — read-pairs/s through the fused Circall_wt + Circall_bsj hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path over the whole synthetic workload (BASELINE.json configs[1]:
+hg19-scale synthetic transcriptome + BSJ index, 20 M 2x100 bp pairs per GPU), issued to the library in
+batches.  Three legs are measured by the default arm:
+  value        inputs resident in HBM, device-timed bracket around K steps
+  e2e          the same work through the C ABI with HOST (pinned) buffers: host->device copies of the reads
+               and device->host copies of the result lists are inside the timed region
+  cpu_baseline the oracle (CPU restatement of the reference algorithm) on a bounded sample, rank 0, N = 1
+`--impl reference` times only the CPU restatement (the reference binary cannot be built here).
+Nothing here reads /root/reference.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read-pairs/sec quasi-mapped+BSJ-filtered (fused Circall_wt+Circall_bsj)"
+UNIT = "read-pairs/s"
+
+
+def workload(args):
+    import synth
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.genes:
+        cfg["n_genes"] = args.genes
+    if args.pairs:
+        cfg["n_pairs"] = args.pairs
+    return cfg
+
+
+def config_json(cfg, args, extra=None):
+    c = {"workload": cfg["name"], "baseline_config_index": args.config - 1, "n_genes": cfg["n_genes"],
+         "pairs_per_gpu_per_step": cfg["n_pairs"], "read_len": cfg["L"], "circ_frac": cfg["circ_frac"], "error_rate": 0.005,
+         "batch_pairs": args.batch, "index": "replicated per GPU", "l2": "inputs (>= 4 GB) and index (>= 10 GB) exceed the 126 MB L2; no flush needed"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.p, self.path = gpu, None, "/tmp/cg_clocks_%d_%d.csv" % (os.getpid(), gpu)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def algorithmic_bytes(c, L, n_junc_rows):
+    """bytes = 16 P + w S + T/4 + (w + 8 + 4) H per collector call, + 2 L/4 per mapped read
+    (packed read written once, read once), + emitted rows; w = 4 (int32 suffix array).  c = oracle counters."""
+    return 16 * c["P"] + 4 * c["S"] + c["T"] / 4 + (4 + 8 + 4) * c["H"] + c["calls"] * (2 * L / 4) + 24 * n_junc_rows
+
+
+def reference_arm(args):
+    """--impl reference: the CPU restatement on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import circall_b200 as cg
+    import oracle
+    import synth
+    cfg = workload(args)
+    cores = os.cpu_count() or 1
+    oracle.build(); synth.build()
+    T = synth.Txome(cfg["tx_seed"], cfg["n_genes"])
+    otx, obsj = oracle_indices(cg, oracle, T, cores)
+    S = args.ref_sample
+    times = []
+    for it in range(args.warmup + args.steps):
+        r1, r2 = T.reads(cfg["read_seed"], S, L=cfg["L"], frag_mean=cfg["frag_mean"], frag_sd=cfg["frag_sd"], circ_frac=cfg["circ_frac"],
+                         first=it * S)
+        t0 = time.perf_counter()
+        R = oracle.Run(otx, obsj, 2, r1, r2, nthreads=cores)
+        dt = time.perf_counter() - t0
+        R.close()
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    v = S / (ms * 1e-3)
+    sample = "%d pairs per step of the same synthetic workload (fresh reads every step), mapping only (reads pre-parsed in memory)" % S
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+            "config": config_json(cfg, args, {"reference": "CPU restatement of the reference algorithm (oracle/), std::thread pool over 1000-pair jobs; "
+                                                            "the Circall binary itself cannot be built here"}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def oracle_indices(cg, oracle, T, cores, gtx=None, gbsj=None):
+    """Oracle indices for the workload.  At this scale a CPU comparison sort of the suffixes takes many minutes,
+    so the (unique) suffix array is taken from the GPU builder and verified by the oracle before use."""
+    own = gtx is None
+    if own:
+        gtx = cg.Index.build(T.tx_text)
+    otx = oracle.Index.from_text_with_sa(T.tx_text, gtx.suffix_array(), nthreads=cores)
+    if own:
+        gtx.close()
+        gbsj = cg.Index.build(T.bsj_text)
+    obsj = oracle.Index.from_text_with_sa(T.bsj_text, gbsj.suffix_array(), nthreads=cores)
+    if own:
+        gbsj.close()
+    return otx, obsj
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
+    ap.add_argument("--genes", type=int, default=0, help="override the gene count (smaller index for quick runs)")
+    ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 22, help="pairs per library batch")
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="pairs in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=400_000, help="pairs per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import circall_b200 as cg
+    import synth
+    synth.build()
+    cfg = workload(args)
+    L, n = cfg["L"], cfg["n_pairs"]
+    T = synth.Txome(cfg["tx_seed"], cfg["n_genes"])
+    t0 = time.time()
+    gtx = cg.Index.build(T.tx_text, device=local)
+    gbsj = cg.Index.build(T.bsj_text, device=local)
+    t_index = time.time() - t0
+    # this rank's reads (weak scaling: every GPU maps its own n pairs)
+    pin1, pin2 = cg.PinnedBuffer(n * L), cg.PinnedBuffer(n * L)
+    r1, r2 = pin1.array.reshape(n, L), pin2.array.reshape(n, L)
+    T.reads(cfg["read_seed"], n, L=L, frag_mean=cfg["frag_mean"], frag_sd=cfg["frag_sd"], circ_frac=cfg["circ_frac"], first=rank * n, out=(r1, r2))
+    batch = min(args.batch, n)
+    off = np.arange(batch + 1, dtype=np.uint64) * np.uint64(L)
+    pinoff = cg.PinnedBuffer(off.nbytes); pinoff.array[:] = off.view(np.uint8)
+    d1, d2, doff = cg.DeviceBuffer(n * L + 64, local), cg.DeviceBuffer(n * L + 64, local), cg.DeviceBuffer(off.nbytes, local)
+    d1.upload(r1); d2.upload(r2); doff.upload(off)
+    batches = [(b0, min(batch, n - b0)) for b0 in range(0, n, batch)]
+
+    S = cg.Session(gtx, gbsj, stage=0)
+    accp, accn = S.accumulator()
+
+    class _Acc:
+        __cuda_array_interface__ = {"shape": (accn,), "typestr": "<i8", "data": (accp, False), "version": 3}
+    acc_t = torch.as_tensor(_Acc(), device=torch.device("cuda", local)) if world > 1 else None
+    reduced = torch.empty(accn, dtype=torch.int64, device=torch.device("cuda", local)) if world > 1 else None
+
+    def step_resident(stats=None):
+        for b0, nb in batches:
+            S.submit_device(d1.ptr + b0 * L, doff.ptr, d2.ptr + b0 * L, doff.ptr, nb, L)
+            B = S.fetch(want_lists=False)
+            if stats is not None:
+                stats.append(B)
+        if world > 1:   # the one collective of the path: per-BSJ count vector + scalar counters (SURVEY §8 e)
+            reduced.copy_(acc_t)
+            dist.all_reduce(reduced)
+
+    def bracket(fn, k):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(k):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t
+        if world > 1:
+            m = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            dt = float(m.item())
+        return dt
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    stats = []
+    l0 = S.launches
+    dt = bracket(lambda: step_resident(stats), args.steps)
+    launches = S.launches - l0
+    clk = clocks.stop()
+    ms_step = 1e3 * dt / args.steps
+    value = world * n / (ms_step * 1e-3)
+    kms = np.array([b.kernel_ms for b in stats])            # per launch: pack, wt, commit, bsj
+    dev_ms = float(sum(b.device_ms for b in stats)) / args.steps
+    k_avg = kms.mean(axis=0)
+    n_exp = sum(b.n_export for b in stats) // args.steps
+    n_junc = sum(b.n_junc for b in stats) // args.steps
+
+    # ---- end to end through the C ABI from pinned host buffers, two sessions so copies overlap kernels
+    e2e = None
+    if not args.no_e2e:
+        SS = [S, cg.Session(gtx, gbsj, stage=0)]
+        h2d = 2 * n * L + 2 * len(batches) * off.nbytes
+        d2h = [0]
+
+        def step_host():
+            pend = []
+            tot = 0
+            for i, (b0, nb) in enumerate(batches):
+                s = SS[i % 2]
+                if len(pend) == 2:
+                    B = pend.pop(0).fetch(want_lists=True, materialize=False)
+                    tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
+                s.submit_raw(pin1.ptr + b0 * L, pinoff.ptr, pin2.ptr + b0 * L, pinoff.ptr, nb)
+                pend.append(s)
+            for s in pend:
+                B = s.fetch(want_lists=True, materialize=False)
+                tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
+            d2h[0] = tot
+            if world > 1:
+                reduced.copy_(acc_t)
+                dist.all_reduce(reduced)
+        for _ in range(2):
+            step_host()
+        dte = bracket(step_host, args.steps)
+        e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
+               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": 2}
+        SS[1].close()
+
+    # ---- cpu baseline + algorithmic bytes from the oracle's counters (rank 0, N = 1 only)
+    cpu = None
+    roof = None
+    gather = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    if rank == 0:
+        gather = cg.bench_gather(16 << 30, 64, 3, device=local)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        t0 = time.time()
+        otx, obsj = oracle_indices(cg, oracle, T, cores, gtx, gbsj)
+        t_oidx = time.time() - t0
+        ns = min(args.cpu_sample, n)
+        t0 = time.perf_counter()
+        R = oracle.Run(otx, obsj, 2, r1[:ns], r2[:ns], nthreads=cores)
+        tc = time.perf_counter() - t0
+        cw, cb = R.counters(0), R.counters(1)
+        nj = R.bsj_junctions().shape[0]
+        # parity spot check of the benchmarked path on the sample (the tests do this exhaustively)
+        Sp = cg.Session(gtx, gbsj, stage=0)
+        Bp = Sp.run(r1[:ns], r2[:ns])
+        cp, pb = Sp.counters()
+        ok = (Bp.n_export == cb["numObserved"] and Bp.n_junc == nj and cp["bsj_num_mapped"] == cb["numMapped"] and
+              cp["wt_num_hits"] == cw["numHits"] and cp["bsj_num_hits"] == cb["numHits"])
+        Sp.close()
+        cpu = {"value": ns / tc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d pairs of the workload, wt + bsj on all host threads, mapping only (reads pre-parsed); oracle index set-up %.0f s not timed" % (ns, t_oidx),
+               "parity_on_sample": bool(ok)}
+        by_wt = algorithmic_bytes(cw, L, 0) / ns          # per pair
+        by_bsj = algorithmic_bytes(cb, L, nj) / ns
+        pairs_per_launch = n / len(batches)
+        kern = {"k_wt": (by_wt, k_avg[1]), "k_bsj": (by_bsj, k_avg[3])}
+        dom = max(kern, key=lambda k: kern[k][1])
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        ach = kern[dom][0] * pairs_per_launch / (kern[dom][1] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_pair": {"k_wt": by_wt, "k_bsj": by_bsj},
+                "pairs_per_launch": pairs_per_launch, "avg_launch_ms": {"k_pack": k_avg[0], "k_wt": k_avg[1], "k_wt_commit+compaction": k_avg[2], "k_bsj": k_avg[3]},
+                "random_sector_peak_gbs": gather, "frac_of_random_sector_peak": ach / gather if gather else None,
+                "all_kernels": {k: {"achieved": v[0] * pairs_per_launch / (v[1] * 1e-3) / 1e9, "frac": v[0] * pairs_per_launch / (v[1] * 1e-3) / 1e9 / peak} for k, v in kern.items()},
+                "bytes_source": "oracle work counters on the cpu_baseline sample (SURVEY.md §8 d formula), scaled to the launch size"}
+    if rank == 0:
+        ctr = S.counters(per_bsj=False)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+                "config": config_json(cfg, args, {"n_tx": gtx.n_tx, "n_bsj": gbsj.n_tx, "tx_text_len": gtx.text_len, "bsj_text_len": gbsj.text_len,
+                                                  "index_build_s": round(t_index, 2), "index_device_gb": round((gtx.device_bytes + gbsj.device_bytes) / 1e9, 2),
+                                                  "exported_records_per_step": int(n_exp), "junction_rows_per_step": int(n_junc)}),
+                "device_ms_per_step": dev_ms, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "counters": {k: int(v) for k, v in ctr.items()}}
+        print(json.dumps(line), flush=True)
+    S.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

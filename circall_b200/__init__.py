@@ -60,7 +60,7 @@ class _BatchResult(ctypes.Structure):
                 ("n_eq", ctypes.c_uint64), ("eq_off", ctypes.c_void_p), ("eq_tids", ctypes.c_void_p),
                 ("mate_flags", ctypes.c_void_p), ("mate_nhits", ctypes.c_void_p),
                 ("rec_nhits", ctypes.c_void_p), ("rec_split", ctypes.c_void_p),
-                ("device_ms", ctypes.c_double)]
+                ("device_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 4)]
 
 
 class _Counters(ctypes.Structure):
@@ -271,6 +271,7 @@ class BatchResult:
     def __init__(self, r, want_lists, detail):
         self.n_pairs, self.n_export, self.n_junc, self.n_eq = r.n_pairs, r.n_export, r.n_junc, r.n_eq
         self.device_ms = r.device_ms
+        self.kernel_ms = tuple(r.kernel_ms)      # pack, wt, commit+compaction, bsj
         if not want_lists:
             return
         self.exp_pair = _view(r.exp_pair, np.uint32, r.n_export)
@@ -334,13 +335,15 @@ class Session:
     def submit_device(self, d_r1, d_off1, d_r2, d_off2, n_pairs, max_read_len):
         _check(lib().cg_session_submit_device(self._h, d_r1, d_off1, d_r2, d_off2, n_pairs, max_read_len))
 
-    def fetch(self, want_lists=True):
+    def fetch(self, want_lists=True, materialize=True):
+        """Wait for the batch.  want_lists: also bring the per-record lists to host memory (inside the
+        library); materialize=False skips copying them into numpy arrays (bench.py's end-to-end leg)."""
         r = _BatchResult()
         try:
             _check(lib().cg_session_fetch(self._h, int(want_lists), ctypes.byref(r)))
         finally:
             self._keep = None
-        return BatchResult(r, want_lists, self.detail)
+        return BatchResult(r, want_lists and materialize, self.detail)
 
     def run(self, r1, r2, want_lists=True):
         self.submit(r1, r2)

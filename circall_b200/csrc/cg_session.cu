@@ -232,7 +232,7 @@ struct cg_session {
     cg_opts opts{};
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr, evw = nullptr, evc = nullptr;
     uint64_t launches = 0;
     bool pending = false;
     // batch state
@@ -323,6 +323,7 @@ int run_batch(cg_session* s) {
     rc = launch(s, k_pack, dim3(grid_for(n_reads * g.W2f, 256)), dim3(256), 0, s->in_r1, s->in_off1, s->in_r2, s->in_off2, n_pairs, g,
                 s->max_len, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), &s->d_hdr.as<BatchHdr>()->status);
     if (rc) return rc;
+    CG_CUDA(cudaEventRecord(s->evp, s->stream));
     if (stage != 2) {
         const int BS = 128;
         size_t smem = (size_t)BS * g.chunk() * 8;
@@ -334,6 +335,7 @@ int run_batch(cg_session* s) {
             rc = launch(s, k_wt<232, 928>, dim3(grid_for(n_reads, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g,
                         n_reads, s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>());
         if (rc) return rc;
+        CG_CUDA(cudaEventRecord(s->evw, s->stream));
         rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
                     s->d_expflag.as<uint8_t>(), s->opts.keep_mate_detail ? s->d_mflags.as<uint8_t>() : (uint8_t*)nullptr,
                     s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_acc + s->n_bsj, s->d_hdr.as<BatchHdr>());
@@ -346,6 +348,8 @@ int run_batch(cg_session* s) {
         rc = launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, s->d_expflag.as<uint8_t>(), n_reads, s->d_bc.as<uint32_t>(), s->d_exp.as<uint32_t>());
         if (rc) return rc;
     }
+    if (stage == 2) CG_CUDA(cudaEventRecord(s->evw, s->stream));
+    CG_CUDA(cudaEventRecord(s->evc, s->stream));
     if (stage != 1) {
         rc = run_bsj_stage(s, 3);
         if (rc) return rc;
@@ -386,6 +390,9 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->evp);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->evw);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->evc);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_acc, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->d_acc, 0, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = s->h_hdr.reserve(sizeof(BatchHdr));
@@ -405,6 +412,9 @@ void cg_session_destroy(cg_session* s) {
     if (s->d_acc) cudaFree(s->d_acc);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->evp) cudaEventDestroy(s->evp);
+    if (s->evw) cudaEventDestroy(s->evw);
+    if (s->evc) cudaEventDestroy(s->evc);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -457,8 +467,12 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     if (hdr.status & ST_BADBASE) CG_FAIL(CG_ERR_BASE, "a read holds a character outside ACGTNacgtn");
     if (hdr.status & ST_TOOLONG) CG_FAIL(CG_ERR_LENGTH, "a read is longer than the batch's max_read_len");
     if (hdr.status & ST_CAPACITY) CG_FAIL(CG_ERR_CAPACITY, "collector capacity exceeded (intervals / k-mer scores / hits)");
-    float ms = 0;
+    float ms = 0, ms_k[4] = {0, 0, 0, 0};
     CG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    CG_CUDA(cudaEventElapsedTime(&ms_k[0], s->ev0, s->evp));
+    CG_CUDA(cudaEventElapsedTime(&ms_k[1], s->evp, s->evw));
+    CG_CUDA(cudaEventElapsedTime(&ms_k[2], s->evw, s->evc));
+    CG_CUDA(cudaEventElapsedTime(&ms_k[3], s->evc, s->ev1));
     const int stage = s->opts.stage;
     uint64_t n_exp = stage == 2 ? s->n_pairs : hdr.n_exp;
     // the span filter / class lists never drop rows: when a list outgrew its buffer, grow it and redo the
@@ -479,6 +493,7 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     memset(out, 0, sizeof *out);
     out->n_pairs = s->n_pairs;
     out->device_ms = ms;
+    for (int x = 0; x < 4; ++x) out->kernel_ms[x] = ms_k[x];
     out->n_export = n_exp;
     out->n_junc = hdr.n_junc;
     out->n_eq = hdr.n_eq;

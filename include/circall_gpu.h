@@ -139,7 +139,8 @@ typedef struct {
     const uint8_t* mate_flags; const uint16_t* mate_nhits;
     /* per export record: jointHits.size() before the >200 clear; isSplit */
     const uint32_t* rec_nhits; const uint8_t* rec_split;
-    double device_ms;            /* kernels of this batch, CUDA events */
+    double device_ms;            /* kernels of this batch, CUDA events on the session's stream */
+    double kernel_ms[4];         /* of which: read packing, wt collector, wt commit + export compaction, bsj collector + span filter */
 } cg_batch_result;
 
 /* scalar counters (ReadExperiment.hpp:265-270) for the two tools */

@@ -35,7 +35,7 @@ def _lib():
     L.orc_index_from_text.restype = vp
     L.orc_index_from_text.argtypes = [vp, u64, i32, i32]
     L.orc_index_from_text_sa.restype = vp
-    L.orc_index_from_text_sa.argtypes = [vp, u64, i32, vp]
+    L.orc_index_from_text_sa.argtypes = [vp, u64, i32, vp, i32]
     L.orc_index_from_records.restype = vp
     L.orc_index_from_records.argtypes = [ctypes.POINTER(cp), ctypes.POINTER(cp), u32, i32, i32]
     L.orc_index_free.argtypes = [vp]
@@ -104,11 +104,11 @@ class Index:
         return cls(_lib().orc_index_from_text(text.ctypes.data, text.size, k, nthreads or os.cpu_count() or 1))
 
     @classmethod
-    def from_text_with_sa(cls, text, sa, k=31):
+    def from_text_with_sa(cls, text, sa, k=31, nthreads=None):
         text = np.ascontiguousarray(text, dtype=np.uint8)
         sa = np.ascontiguousarray(sa, dtype=np.int32)
         assert sa.size == text.size
-        return cls(_lib().orc_index_from_text_sa(text.ctypes.data, text.size, k, sa.ctypes.data))
+        return cls(_lib().orc_index_from_text_sa(text.ctypes.data, text.size, k, sa.ctypes.data, nthreads or os.cpu_count() or 1))
 
     @classmethod
     def from_records(cls, records, k=31, nthreads=None):

@@ -33,10 +33,10 @@ void* orc_index_from_text(const char* seq, uint64_t n, int k, int nthreads) {
     return ix;
     ORC_CATCH(nullptr)
 }
-void* orc_index_from_text_sa(const char* seq, uint64_t n, int k, const int32_t* sa) {
+void* orc_index_from_text_sa(const char* seq, uint64_t n, int k, const int32_t* sa, int nthreads) {
     ORC_TRY
     auto* ix = new Index();
-    try { index_from_text_with_sa(*ix, seq, n, k, sa); } catch (...) { delete ix; throw; }
+    try { index_from_text_with_sa(*ix, seq, n, k, sa, nthreads); } catch (...) { delete ix; throw; }
     return ix;
     ORC_CATCH(nullptr)
 }

@@ -42,7 +42,7 @@ void export_records(const ReadBatch& rb, const WtResult& wt, std::string& r1, st
                     std::string& r2, std::vector<uint64_t>& o2);
 
 void index_from_text(Index& ix, const char* seq, uint64_t n, int k, int nthreads);
-void index_from_text_with_sa(Index& ix, const char* seq, uint64_t n, int k, const OffsetT* sa);
+void index_from_text_with_sa(Index& ix, const char* seq, uint64_t n, int k, const OffsetT* sa, int nthreads);
 void index_from_records(Index& ix, const std::vector<std::pair<std::string, std::string>>& recs, int k, int nthreads);
 
 } // namespace orc

@@ -14,6 +14,7 @@
 #include <random>
 #include <thread>
 #include <stdexcept>
+#include <atomic>
 
 namespace orc {
 
@@ -97,9 +98,21 @@ static void build_sa(const std::string& seq, std::vector<OffsetT>& SA, int nthre
     for (auto& t : th) t.join();
 }
 
+template <class F>
+static void parallel_ranges(size_t n, int nthreads, F f) {
+    if (nthreads < 1) nthreads = 1;
+    if (n < (size_t)1 << 16) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() { f(n * (size_t)t / (size_t)nthreads, n * (size_t)(t + 1) / (size_t)nthreads, t); });
+    for (auto& t : th) t.join();
+}
+
 // walk the SA once; consecutive suffixes whose first k characters are equal
-// and '$'-free form one [begin,end).
-static void build_khash(Index& ix) {
+// and '$'-free form one [begin,end).  The walk is split over threads: a first pass classifies
+// every SA slot (0 = continues the previous slot's k-mer, 1 = opens a run, 2 = no valid k-mer),
+// a second pass inserts every run (slot claimed with a compare-and-swap on its key).
+static void build_khash(Index& ix, int nthreads) {
     const size_t n = ix.seq.size();
     const int k = ix.k;
     const char* s = ix.seq.data();
@@ -107,35 +120,50 @@ static void build_khash(Index& ix) {
         if ((size_t)p + k > n) return false;
         return std::memchr(s + p, '$', k) == nullptr;
     };
-    // pass 1: count distinct k-mers
-    uint64_t nk = 0;
-    {
-        bool have = false; OffsetT prev = 0;
-        for (size_t i = 0; i < n; ++i) {
+    std::vector<uint8_t> cls(n);
+    std::vector<uint64_t> heads((size_t)std::max(1, nthreads), 0);
+    parallel_ranges(n, nthreads, [&](size_t b, size_t e, int t) {
+        uint64_t h = 0;
+        bool pv = b > 0 && valid(ix.SA[b - 1]);
+        for (size_t i = b; i < e; ++i) {
             OffsetT p = ix.SA[i];
-            if (!valid(p)) { have = false; continue; }
-            if (!have || std::memcmp(s + prev, s + p, k) != 0) { ++nk; }
-            have = true; prev = p;
+            bool v = valid(p);
+            uint8_t c = 2;
+            if (v) { c = (pv && std::memcmp(s + ix.SA[i - 1], s + p, k) == 0) ? 0 : 1; h += c; }
+            cls[i] = c;
+            pv = v;
         }
-    }
+        heads[t] = h;
+    });
+    uint64_t nk = 0;
+    for (auto h : heads) nk += h;
     ix.khash.init(nk);
-    bool have = false; OffsetT prev = 0; size_t start = 0;
-    for (size_t i = 0; i <= n; ++i) {
-        bool v = (i < n) && valid(ix.SA[i]);
-        bool same = v && have && std::memcmp(s + prev, s + ix.SA[i], k) == 0;
-        if (have && !same) {
-            ix.khash.insert(mer_from_chars(s + prev, k), (OffsetT)start, (OffsetT)i);
-            have = false;
+    KHash& H = ix.khash;
+    parallel_ranges(n, nthreads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            if (cls[i] != 1) continue;
+            size_t j = i + 1;
+            while (j < n && cls[j] == 0) ++j;
+            uint64_t key = mer_from_chars(s + ix.SA[i], k);
+            uint64_t h = KHash::mix(key) & H.mask;
+            for (;;) {
+                uint64_t expect = KHash::EMPTY;
+                if (__atomic_compare_exchange_n(&H.slots[h].key, &expect, key, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                    H.slots[h].begin = (OffsetT)i; H.slots[h].end = (OffsetT)j;
+                    break;
+                }
+                if (expect == key) throw std::runtime_error("khash: duplicate k-mer interval");
+                h = (h + 1) & H.mask;
+            }
         }
-        if (v && !same) { have = true; start = i; }
-        if (v) prev = ix.SA[i];
-    }
+    });
+    H.size = nk;
 }
 
 void finish_index(Index& ix, int nthreads) {
     ix.rankDict.build(ix.seq);
     build_sa(ix.seq, ix.SA, nthreads);
-    build_khash(ix);
+    build_khash(ix, nthreads);
 }
 
 // text already normalised and '$'-joined: offsets/lengths recovered from the '$' positions
@@ -155,30 +183,41 @@ void index_from_text(Index& ix, const char* seq, uint64_t n, int k, int nthreads
 // scale, where a CPU comparison sort would take minutes).  The array is NOT trusted: it is
 // checked with the linear-time suffix-array criterion (permutation; first characters
 // ordered; ties ordered by the rank of the next suffix) before use.
-bool verify_sa(const std::string& seq, const std::vector<OffsetT>& SA) {
+bool verify_sa(const std::string& seq, const std::vector<OffsetT>& SA, int nthreads) {
     const size_t n = seq.size();
     if (SA.size() != n) return false;
     std::vector<OffsetT> inv(n, -1);
-    for (size_t i = 0; i < n; ++i) {
-        OffsetT p = SA[i];
-        if (p < 0 || (size_t)p >= n || inv[p] != -1) return false;
-        inv[p] = (OffsetT)i;
-    }
-    for (size_t i = 0; i + 1 < n; ++i) {
-        OffsetT a = SA[i], b = SA[i + 1];
-        unsigned char ca = seq[a], cb = seq[b];
-        if (ca > cb) return false;
-        if (ca == cb) {
-            // suffix a+1 must sort before suffix b+1 (empty suffix sorts first)
-            if ((size_t)a + 1 == n) continue;
-            if ((size_t)b + 1 == n) return false;
-            if (inv[a + 1] > inv[b + 1]) return false;
+    std::atomic<bool> ok{true};
+    parallel_ranges(n, nthreads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            OffsetT p = SA[i];
+            if (p < 0 || (size_t)p >= n) { ok = false; return; }
+            inv[p] = (OffsetT)i;      // a value hit twice leaves another one unhit, caught below
         }
-    }
-    return true;
+    });
+    if (!ok) return false;
+    parallel_ranges(n, nthreads, [&](size_t b, size_t e, int) {
+        for (size_t p = b; p < e; ++p)
+            if (inv[p] < 0 || (size_t)SA[inv[p]] != p) { ok = false; return; }
+    });
+    if (!ok) return false;
+    parallel_ranges(n - 1, nthreads, [&](size_t b0, size_t e0, int) {
+        for (size_t i = b0; i < e0; ++i) {
+            OffsetT a = SA[i], b = SA[i + 1];
+            unsigned char ca = seq[a], cb = seq[b];
+            if (ca > cb) { ok = false; return; }
+            if (ca == cb) {
+                // suffix a+1 must sort before suffix b+1 (empty suffix sorts first)
+                if ((size_t)a + 1 == n) continue;
+                if ((size_t)b + 1 == n) { ok = false; return; }
+                if (inv[a + 1] > inv[b + 1]) { ok = false; return; }
+            }
+        }
+    });
+    return ok;
 }
 
-void index_from_text_with_sa(Index& ix, const char* seq, uint64_t n, int k, const OffsetT* sa) {
+void index_from_text_with_sa(Index& ix, const char* seq, uint64_t n, int k, const OffsetT* sa, int nthreads) {
     ix.k = k;
     ix.seq.assign(seq, n);
     if (n == 0 || ix.seq.back() != '$') throw std::runtime_error("text must end with '$'");
@@ -188,9 +227,9 @@ void index_from_text_with_sa(Index& ix, const char* seq, uint64_t n, int k, cons
     ix.txpNames.resize(ix.txpOffsets.size());
     for (size_t t = 0; t < ix.txpNames.size(); ++t) ix.txpNames[t] = "t" + std::to_string(t);
     ix.SA.assign(sa, sa + n);
-    if (!verify_sa(ix.seq, ix.SA)) throw std::runtime_error("imported suffix array failed verification");
+    if (!verify_sa(ix.seq, ix.SA, nthreads)) throw std::runtime_error("imported suffix array failed verification");
     ix.rankDict.build(ix.seq);
-    build_khash(ix);
+    build_khash(ix, nthreads);
 }
 
 // FASTA records -> index text, per SURVEY B6 (name up to first whitespace, upper-case,
