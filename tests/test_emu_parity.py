@@ -1,0 +1,95 @@
+"""CPU tier: the device code (cg_core.cuh / cg_pipeline.cuh compiled for the host by tests/emu) against the
+oracle.  This is how the CUDA logic is checked where no GPU exists; the `-m gpu` tests repeat it through
+libcircall_gpu.so on the B200."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import emu
+from tests.helpers import make_reads, ragged
+
+
+@pytest.fixture(scope="module")
+def world(small_world):
+    T, otx, obsj = small_world
+    etx = emu.EmuIndex(T.tx_text, otx.sa)
+    ebsj = emu.EmuIndex(T.bsj_text, obsj.sa)
+    assert etx.n_kmers == otx.n_kmers and ebsj.n_kmers == obsj.n_kmers
+    return T, otx, obsj, etx, ebsj
+
+
+@pytest.mark.parametrize("lce_mode", [0, 1])
+def test_collect_intervals_and_hits(world, lce_mode):
+    T, otx, obsj, etx, ebsj = world
+    r1, r2 = make_reads(T, 5, 1200, n_rate=0.004)
+    for oi, ei, rd in ((otx, etx, r1), (obsj, ebsj, r2)):
+        n, L = rd.shape
+        res = ei.collect(rd.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L, strict=True, lce_mode=lce_mode)
+        for i in range(n):
+            found, f, r, hits = oi.collect(rd[i].tobytes(), strict=True, lce_mode=lce_mode)
+            assert bool(res["found"][i]) == found
+            if not found:
+                continue
+            assert np.array_equal(res["fwd_ints"][int(res["fwd_off"][i]):int(res["fwd_off"][i + 1])], f)
+            assert np.array_equal(res["rc_ints"][int(res["rc_off"][i]):int(res["rc_off"][i + 1])], r)
+            a, b = int(res["hits_off"][i]), int(res["hits_off"][i + 1])
+            assert list(zip(res["hit_tid"][a:b].tolist(), res["hit_pos"][a:b].tolist(), [bool(x) for x in res["hit_fwd"][a:b]])) == hits
+
+
+def _pipeline(world, r1, r2, lce_mode=0):
+    T, otx, obsj, etx, ebsj = world
+    (b1, o1), (b2, o2) = oracle._flat(r1), oracle._flat(r2)
+    R = oracle.Run(otx, obsj, 2, r1, r2, lce_mode=lce_mode)
+    E = emu.run(etx, ebsj, b1, o1, b2, o2, lce_mode)
+    p, c = R.wt_export()
+    assert np.array_equal(E["exp_pair"], p) and np.array_equal(E["exp_code"], c)
+    fl, nh = R.wt_mates()
+    assert np.array_equal(E["mate_flags"], fl) and np.array_equal(E["mate_nhits"], nh)
+    assert sorted(map(tuple, R.bsj_junctions().tolist())) == sorted(map(tuple, E["junc"].tolist()))
+    assert np.array_equal(E["cand"], R.bsj_candidates())
+    onh, osp = R.bsj_records()
+    assert np.array_equal(E["rec_nhits"], onh) and np.array_equal(E["rec_split"], osp)
+    ow, ob = R.counters(0), R.counters(1)
+    assert E["ctr"].tolist() == [ow["numObserved"], ow["numMapped"], ow["numHits"], ow["upperBound"],
+                                 ob["numObserved"], ob["numMapped"], ob["numHits"], ob["upperBound"]]
+    eq = {}
+    p0 = 0
+    for ln in E["eq_lens"]:
+        key = tuple(int(x) for x in E["eq_tids"][p0:p0 + ln]); p0 += int(ln)
+        eq[key] = eq.get(key, 0) + 1
+    assert eq == R.eq_classes(1)
+    return R
+
+
+@pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0)])
+def test_pipeline(world, L, lce_mode):
+    T = world[0]
+    r1, r2 = make_reads(T, 100 + L, 5000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
+    R = _pipeline(world, r1, r2, lce_mode)
+    assert len(R.bsj_candidates()) > 0
+
+
+def test_pipeline_ragged_n_rich(world):
+    T = world[0]
+    r1, r2 = make_reads(T, 77, 3000, n_rate=0.02)
+    r1[0, :] = ord("N"); r2[1, :] = ord("A"); r1[2, 40:] = ord("N"); r1[3, :] = ord("n")
+    r1[4] = np.frombuffer(bytes(r1[4]).lower(), np.uint8)
+    a, b = ragged(r1, r2, 3)
+    _pipeline(world, a, b)
+
+
+def test_pipeline_shipped_style_reads(world):
+    """Reads shaped like the reference's shipped fixture (V1/Data/test_read*.fasta.gz: 2x100, ~12 % of reads hold
+    an N, a few reads of 99/76/80/82 bases): N-containing windows are "oracle-defined" (SURVEY B5)."""
+    T = world[0]
+    r1, r2 = make_reads(T, 55, 3000, n_rate=0.0013, circ_frac=0.5)
+    rng = np.random.default_rng(1)
+    out = []
+    for r in (r1, r2):
+        n, L = r.shape
+        lens = np.full(n, L)
+        lens[rng.random(n) < 0.045] = 99
+        lens[rng.random(n) < 0.001] = rng.choice([76, 80, 82])
+        off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+        out.append((np.concatenate([r[i, :lens[i]] for i in range(n)]), off))
+    _pipeline(world, out[0], out[1])
