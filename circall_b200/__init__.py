@@ -60,7 +60,8 @@ class _BatchResult(ctypes.Structure):
                 ("n_eq", ctypes.c_uint64), ("eq_off", ctypes.c_void_p), ("eq_tids", ctypes.c_void_p),
                 ("mate_flags", ctypes.c_void_p), ("mate_nhits", ctypes.c_void_p),
                 ("rec_nhits", ctypes.c_void_p), ("rec_split", ctypes.c_void_p),
-                ("device_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 4)]
+                ("device_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 4),
+                ("n_fallback_wt", ctypes.c_uint64), ("n_fallback_bsj", ctypes.c_uint64)]
 
 
 class _Counters(ctypes.Structure):
@@ -272,6 +273,7 @@ class BatchResult:
         self.n_pairs, self.n_export, self.n_junc, self.n_eq = r.n_pairs, r.n_export, r.n_junc, r.n_eq
         self.device_ms = r.device_ms
         self.kernel_ms = tuple(r.kernel_ms)      # pack, wt, commit+compaction, bsj
+        self.n_fallback_wt, self.n_fallback_bsj = r.n_fallback_wt, r.n_fallback_bsj
         if not want_lists:
             return
         self.exp_pair = _view(r.exp_pair, np.uint32, r.n_export)

@@ -18,8 +18,8 @@
 //           sector gives bases, terminators and the rank for any position inside it.
 //   SA      uint32 suffix array.
 //   khash   open addressing, 16-B slots {key(62-bit k-mer, base j at bits 2j), begin, end}.
-//   reads   per strand: 2-bit words (base j at bits 2j) + N-mask words, forward and reverse-
-//           complement strands both materialised in shared memory by the kernel prologue.
+//   reads   2-bit words (base j at bits 2j) + N-mask words of the forward strand, staged in shared
+//           memory by the kernel prologue; the reverse-complement strand is derived by bit reversal.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
@@ -119,107 +119,130 @@ CG_HD void tid_of(const IndexView& ix, uint32_t p, uint32_t& tid, uint32_t& loca
     local = p - start;
 }
 
+// SA[i0 .. i0+n) (n <= 4) -> transcript id and transcript-local offset of each position, with the
+// suffix-array entries, then the text blocks, then the offsets fetched as three waves of independent loads
+CG_HD void sa_tids4(const IndexView& ix, uint32_t i0, int n, uint32_t* tid, uint32_t* local) {
+    uint32_t p[4]; TB t[4]; int c[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) p[x] = x < n ? CG_LDG(&ix.sa[i0 + x]) : 0u;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) if (x < n) t[x] = load_tb(ix, p[x] >> 6);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+        if (x < n) {
+            uint32_t o = p[x] & 63;
+            c[x] = popc64(o ? (t[x].mask & ((1ULL << o) - 1)) : 0ULL);
+            tid[x] = t[x].tid0 + (uint32_t)c[x];
+        }
+    uint32_t st[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) if (x < n) st[x] = c[x] ? CG_LDG(&ix.offsets[tid[x]]) : t[x].start0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) if (x < n) local[x] = p[x] - st[x];
+}
+
 // ---------------------------------------------------------------------------------------------
-// packed read view.  Word j of strand s lives at w[(s * (W2 + WM) + j) * stride]; the mask words
-// follow the code words.  Positions >= L carry code 0 and mask 1.
+// packed read view.  Only the forward strand is stored: w[0..W2) code words (32 bases each, base j
+// at bits 2j, last word a zero pad) then w[W2..W2+WM) N-mask words (64 positions each, last word an
+// all-ones pad).  Positions >= L carry code 0 and mask 1.  The reverse-complement strand (s = 1,
+// oriented position i = distance from the read's end) is derived on the fly by bit reversal.
 // ---------------------------------------------------------------------------------------------
+CG_HD uint32_t brev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    return (uint32_t)(brev64((uint64_t)x) >> 32);
+#endif
+}
+// reverse the order of the 32 2-bit codes of x and complement them
+CG_HD uint64_t rc64(uint64_t x) {
+    uint64_t r = brev64(x);
+    return ~(((r >> 1) & EVEN) | ((r & EVEN) << 1));
+}
+
 struct ReadView {
     const uint64_t* w;
-    int stride;
     int L;
-    int W2;    // code words per strand  = ceil(L/32) + 1 (zero pad)
-    int WM;    // mask words per strand  = ceil(L/64) + 1 (all-ones pad)
-    CG_HD uint64_t code(int s, int j) const { return w[(size_t)(s * (W2 + WM) + j) * stride]; }
-    CG_HD uint64_t msk(int s, int j) const { return w[(size_t)(s * (W2 + WM) + W2 + j) * stride]; }
-    // 32 bases (64 bits) of strand s starting at oriented position i
-    CG_HD uint64_t chunk(int s, int i) const {
+    int W2;    // code words incl. the zero pad  = ceil(maxL/32) + 1
+    int WM;    // mask words incl. the ones pad  = ceil(W2f/2) + 1
+    bool anyN; // some position < L is not a base (false lets every N test return at once)
+    CG_HD uint64_t code(int j) const { return w[j]; }
+    CG_HD uint64_t msk(int j) const { return w[W2 + j]; }
+    CG_HD uint64_t chunkF(int i) const {
         int j = i >> 5, sh = (i & 31) * 2;
-        uint64_t lo = code(s, j);
+        uint64_t lo = code(j);
         if (sh == 0) return lo;
-        return (lo >> sh) | (code(s, j + 1) << (64 - sh));
+        return (lo >> sh) | (code(j + 1) << (64 - sh));
+    }
+    CG_HD uint32_t mask32F(int i) const {
+        int j = i >> 6, sh = i & 63;
+        uint64_t lo = msk(j);
+        if (sh == 0) return (uint32_t)lo;
+        return (uint32_t)((lo >> sh) | (msk(j + 1) << (64 - sh)));
+    }
+    // 32 bases (64 bits) of strand s starting at oriented position i (i <= L)
+    CG_HD uint64_t chunk(int s, int i) const {
+        if (s == 0) return chunkF(i);
+        int a = L - 32 - i;                       // forward window [a, a+32) read backwards
+        if (a >= 0) return rc64(chunkF(a));
+        int nv = 32 + a;
+        if (nv <= 0) return 0;
+        return rc64(chunkF(0)) >> (2 * (32 - nv));
     }
     // 32 N-mask bits of strand s starting at oriented position i
     CG_HD uint32_t mask32(int s, int i) const {
-        int j = i >> 6, sh = i & 63;
-        uint64_t lo = msk(s, j);
-        if (sh == 0) return (uint32_t)lo;
-        return (uint32_t)((lo >> sh) | (msk(s, j + 1) << (64 - sh)));
+        if (s == 0) return mask32F(i);
+        int a = L - 32 - i;
+        if (a >= 0) return brev32(mask32F(a));
+        int nv = 32 + a;
+        if (nv <= 0) return 0xffffffffu;
+        return (brev32(mask32F(0)) >> (32 - nv)) | (0xffffffffu << nv);
     }
-    // first n/N at or after oriented position i on strand s (>= L when there is none)
+    // first n/N at or after oriented position i on strand s (L when there is none)
     CG_HD int first_n(int s, int i) const {
-        int j = i >> 6;
-        uint64_t m = msk(s, j) & (~0ULL << (i & 63));
-        while (m == 0) {
-            ++j;
-            if (j * 64 >= L) return L;
-            m = msk(s, j);
+        if (!anyN) return L;
+        for (int p = i; p < L; p += 32) {
+            uint32_t m = mask32(s, p);
+            if (m) { int r = p + ctz32(m); return r < L ? r : L; }
         }
-        int r = j * 64 + ctz64(m);
-        return r < L ? r : L;
+        return L;
     }
 };
 
-// Expand one packed forward read (W2f code words then WMf mask words, word j at pk[j * pkstride])
-// into the two-strand layout ReadView expects (stride 1): per strand W2f+1 code words (zero pad)
-// and WMf+1 mask words (all-ones pad).  The reverse-complement strand is derived with bit reversal.
-CG_HD void build_strands(const uint64_t* pk, size_t pkstride, int L, int W2f, int WMf, uint64_t* dst) {
-    const int W2 = W2f + 1, WM = WMf + 1, S = W2 + WM;
+// words a view needs for reads of up to maxL bases
+CG_HD int view_words(int W2f, int WMf) { return (W2f + 1) + (WMf + 1); }
+
+// Copy one packed forward read (W2f code words then WMf mask words, word j at pk[j * pkstride]) into
+// the padded layout ReadView expects.
+CG_HD ReadView build_view(const uint64_t* pk, size_t pkstride, int L, int W2f, int WMf, uint64_t* dst) {
+    const int W2 = W2f + 1, WM = WMf + 1;
     for (int j = 0; j < W2f; ++j) dst[j] = pk[(size_t)j * pkstride];
     dst[W2f] = 0;
     for (int j = 0; j < WMf; ++j) dst[W2 + j] = pk[(size_t)(W2f + j) * pkstride];
     dst[W2 + WMf] = ~0ULL;
-    ReadView f; f.w = dst; f.stride = 1; f.L = L; f.W2 = W2; f.WM = WM;
-    for (int j = 0; j < W2f; ++j) {
-        int lo = L - 32 * (j + 1);
-        uint64_t r;
-        if (lo >= 0) {
-            uint64_t x = brev64(f.chunk(0, lo));
-            r = ~(((x >> 1) & EVEN) | ((x & EVEN) << 1));
-        } else {
-            int nv = 32 + lo;
-            if (nv <= 0) r = 0;
-            else {
-                uint64_t x = brev64(f.chunk(0, 0));
-                r = ~(((x >> 1) & EVEN) | ((x & EVEN) << 1));
-                r >>= 2 * (32 - nv);
-            }
-        }
-        dst[S + j] = r;
-    }
-    dst[S + W2f] = 0;
+    ReadView rv; rv.w = dst; rv.L = L; rv.W2 = W2; rv.WM = WM;
+    rv.anyN = false;
     for (int j = 0; j < WMf; ++j) {
-        int lo = L - 64 * (j + 1);
-        uint64_t r;
-        if (lo >= 0) {
-            int w = lo >> 6, sh = lo & 63;
-            uint64_t x = f.msk(0, w) >> sh;
-            if (sh) x |= f.msk(0, w + 1) << (64 - sh);
-            r = brev64(x);
-        } else {
-            int nv = 64 + lo;
-            if (nv <= 0) r = ~0ULL;
-            else { r = brev64(f.msk(0, 0)) >> (64 - nv); if (nv < 64) r |= ~0ULL << nv; }
-        }
-        dst[S + W2 + j] = r;
+        int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t m = dst[W2 + j];
+        if (L - lo < 64) m &= (1ULL << (L - lo)) - 1;
+        if (m) rv.anyN = true;
     }
-    dst[S + W2 + WMf] = ~0ULL;
+    return rv;
 }
 
 CG_HD uint64_t kmask(int k) { return (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1); }
 
-CG_HD uint64_t revcomp(uint64_t w, int k) {
-    uint64_t r = brev64(w);
-    r = ((r >> 1) & EVEN) | ((r & EVEN) << 1);
-    return ((~r) >> (64 - 2 * k)) & kmask(k);
-}
+CG_HD uint64_t revcomp(uint64_t w, int k) { return (rc64(w) >> (64 - 2 * k)) & kmask(k); }
 CG_HD bool homopolymer(uint64_t w, int k) { return w == (w & 3) * (kmask(k) / 3); }
 
 // forward-strand k-mer word at pos; when the window holds a non-ACGT base the word is cut at the
 // first one and the rest is zero ('A'), which is how the oracle defines Jellyfish's
 // mer_dna(const char*) on such input (reached from SACollectorCircall.hpp:167,293,406)
 CG_HD uint64_t kmer_trunc(const ReadView& rv, int pos, int k) {
-    uint64_t w = rv.chunk(0, pos) & kmask(k);
-    uint32_t m = rv.mask32(0, pos) & (uint32_t)((1ULL << k) - 1);
+    uint64_t w = rv.chunkF(pos) & kmask(k);
+    uint32_t m = rv.mask32F(pos) & (uint32_t)((1ULL << k) - 1);
     if (m) w &= (1ULL << (2 * ctz32(m))) - 1;
     return w;
 }
@@ -283,15 +306,29 @@ CG_HD uint64_t hmix(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-CG_HD bool probe(const IndexView& ix, uint64_t key, uint32_t& b, uint32_t& e) {
-    uint64_t h = hmix(key) & ix.hmask;
+CG_HD uint64_t home_slot(const IndexView& ix, uint64_t key) { return hmix(key) & ix.hmask; }
+// finish a probe whose home slot `s` (at index h) has already been loaded
+CG_HD bool resolve(const IndexView& ix, uint64_t key, uint64_t h, u32x4 s, uint32_t& b, uint32_t& e) {
     for (;;) {
-        u32x4 s = CG_LDG(&ix.hslots[h]);
         uint64_t kk = (uint64_t)s.x | ((uint64_t)s.y << 32);
         if (kk == key) { b = s.z; e = s.w; return true; }
         if (kk == ~0ULL) return false;
         h = (h + 1) & ix.hmask;
+        s = CG_LDG(&ix.hslots[h]);
     }
+}
+CG_HD bool probe(const IndexView& ix, uint64_t key, uint32_t& b, uint32_t& e) {
+    uint64_t h = home_slot(ix, key);
+    return resolve(ix, key, h, CG_LDG(&ix.hslots[h]), b, e);
+}
+// two probes with both home-slot loads in flight together
+CG_HD void probe2(const IndexView& ix, uint64_t k1, uint64_t k2, bool& f1, uint32_t& b1, uint32_t& e1,
+                  bool& f2, uint32_t& b2, uint32_t& e2) {
+    uint64_t h1 = home_slot(ix, k1), h2 = home_slot(ix, k2);
+    u32x4 s1 = CG_LDG(&ix.hslots[h1]);
+    u32x4 s2 = CG_LDG(&ix.hslots[h2]);
+    f1 = resolve(ix, k1, h1, s1, b1, e1);
+    f2 = resolve(ix, k2, h2, s2, b2, e2);
 }
 CG_HD bool present(const IndexView& ix, uint64_t key) { uint32_t b, e; return probe(ix, key, b, e); }
 
@@ -301,20 +338,70 @@ CG_HD bool present(const IndexView& ix, uint64_t key) { uint32_t b, e; return pr
 // Advance i while query[qstart+i] == text[p+i], i < lim.  On a stop before lim, `ord` tells how
 // the query character sorts against the text character by raw char value
 // ('$' < A < C < G < N < T): -1 query smaller, +1 query larger.
-CG_HD int match_run(const IndexView& ix, const ReadView& rv, int s, int qstart, uint32_t p, int i, int lim, int& ord) {
+struct TB2 { uint64_t c0, c1, mask; };     // codes + terminator mask of one text block (what comparisons need)
+CG_HD TB2 load_tb2(const IndexView& ix, uint32_t b) {
+    u32x4 a = CG_LDG(&ix.text[2 * (uint64_t)b]);
+    u32x4 c = CG_LDG(&ix.text[2 * (uint64_t)b + 1]);
+    TB2 t;
+    t.c0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    t.c1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    t.mask = (uint64_t)c.x | ((uint64_t)c.y << 32);
+    return t;
+}
+// b0 / b1: text blocks already in registers (block index pb0 and pb0 + 1); pass pb0 = 0xffffffff for none
+CG_HD int match_run_pre(const IndexView& ix, const ReadView& rv, int s, int qstart, uint32_t p, int i, int lim, int& ord,
+                        uint32_t pb0, const TB2& b0, const TB2& b1) {
     uint32_t curb = 0xffffffffu;
-    TB tb; tb.c0 = tb.c1 = tb.mask = 0; tb.tid0 = tb.start0 = 0;
+    TB2 tb; tb.c0 = tb.c1 = tb.mask = 0;
     ord = 0;
     while (i < lim) {
         uint32_t tp = p + (uint32_t)i;
         uint32_t b = tp >> 6;
-        if (b != curb) { tb = load_tb(ix, b); curb = b; }
+        if (b != curb) {
+            if (b == pb0) tb = b0;
+            else if (b == pb0 + 1 && pb0 != 0xffffffffu) tb = b1;
+            else tb = load_tb2(ix, b);
+            curb = b;
+        }
         int half = (tp >> 5) & 1, o5 = tp & 31;
         uint64_t tw = (half ? tb.c1 : tb.c0) >> (2 * o5);
         uint32_t tm = (uint32_t)(tb.mask >> (32 * half + o5));
         int n = cmin(32 - o5, lim - i);
         uint64_t q = rv.chunk(s, qstart + i);
         uint32_t qm = rv.mask32(s, qstart + i);
+        uint64_t x = tw ^ q;
+        uint64_t d = (x | (x >> 1)) & EVEN;
+        int j1 = d ? (ctz64(d) >> 1) : 32;
+        uint32_t mm = tm | qm;
+        int j2 = mm ? ctz32(mm) : 32;
+        int j = cmin(j1, j2);
+        if (j < n) {
+            i += j;
+            bool tdollar = (tm >> j) & 1, qn = (qm >> j) & 1;
+            int tc = (int)((tw >> (2 * j)) & 3), qc = (int)((q >> (2 * j)) & 3);
+            if (tdollar) ord = 1;
+            else if (qn) ord = (tc == 3) ? -1 : 1;
+            else ord = qc < tc ? -1 : 1;
+            return i;
+        }
+        i += n;
+    }
+    return i;
+}
+CG_HD int match_run(const IndexView& ix, const ReadView& rv, int s, int qstart, uint32_t p, int i, int lim, int& ord) {
+    uint32_t curb = 0xffffffffu;
+    TB2 tb; tb.c0 = tb.c1 = tb.mask = 0;
+    ord = 0;
+    while (i < lim) {
+        uint32_t tp = p + (uint32_t)i;
+        uint32_t b = tp >> 6;
+        if (b != curb) { tb = load_tb2(ix, b); curb = b; }
+        int half = (tp >> 5) & 1, o5 = tp & 31;
+        uint64_t tw = (half ? tb.c1 : tb.c0) >> (2 * o5);
+        uint32_t tm = (uint32_t)(tb.mask >> (32 * half + o5));
+        int n = cmin(32 - o5, lim - i);
+        uint64_t q = rv.chunk(s, qstart + i);
+        uint32_t qm = rv.anyN ? rv.mask32(s, qstart + i) : 0u;
         uint64_t x = tw ^ q;
         uint64_t d = (x | (x >> 1)) & EVEN;
         int j1 = d ? (ctz64(d) >> 1) : 32;
@@ -348,13 +435,33 @@ CG_HD void extend(const IndexView& ix, const ReadView& rv, int s, int qstart, ui
     if (m <= startAt) { lbOut = lbIn + 1; ubOut = ubIn; lenOut = startAt; return; }
     const uint32_t w = ubIn - lbIn - 1;
     int ord;
+    if (w == 0) { lbOut = ubIn; ubOut = ubIn; lenOut = startAt; return; }     // empty open interval (reference: lower = upper = ubIn)
     if (w <= CG_LINEAR_MAX) {
         int best = -1; uint32_t first = 0, last = 0;
-        for (uint32_t c = lbIn + 1; c < ubIn; ++c) {
-            uint32_t p = CG_LDG(&ix.sa[c]);
-            int l = match_run(ix, rv, s, qstart, p, startAt, m, ord);
-            if (l > best) { best = l; first = c; last = c; }
-            else if (l == best) last = c;
+        const uint32_t nblk = (uint32_t)((ix.n + 63) >> 6);       // index of the pad block
+        for (uint32_t g0 = lbIn + 1; g0 < ubIn; g0 += 4) {
+            uint32_t p[4]; uint32_t pb[4]; TB2 t0[4], t1[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p[c] = (g0 + c < ubIn) ? CG_LDG(&ix.sa[g0 + c]) : 0u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                pb[c] = 0xffffffffu; t0[c].c0 = t0[c].c1 = t0[c].mask = 0; t1[c] = t0[c];
+                if (g0 + c < ubIn) {
+                    pb[c] = (p[c] + (uint32_t)startAt) >> 6;
+                    t0[c] = load_tb2(ix, pb[c]);
+                    // the second block only when the compared range [p+startAt, p+m) reaches into it
+                    if ((int)((p[c] + (uint32_t)startAt) & 63) + (m - startAt) > 64)
+                        t1[c] = load_tb2(ix, pb[c] + 1 <= nblk ? pb[c] + 1 : nblk);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (g0 + c < ubIn) {
+                    int l = match_run_pre(ix, rv, s, qstart, p[c], startAt, m, ord, pb[c], t0[c], t1[c]);
+                    if (l > best) { best = l; first = g0 + c; last = g0 + c; }
+                    else if (l == best) last = g0 + c;
+                }
+            }
         }
         lbOut = first; ubOut = last + 1; lenOut = best;
         return;
@@ -498,9 +605,11 @@ struct StdSort {
             else linear_insert(i);
         }
     }
+    // BIG = false: the caller guarantees n <= 16 (plain insertion sort, no introsort stack)
+    template <bool BIG>
     CG_HD void sort(int n) {
         if (n <= 1) return;
-        if (n > 16) {
+        if (BIG && n > 16) {
             int lg = 0; for (int t = n; t > 1; t >>= 1) ++lg;
             // explicit stack for __introsort_loop(cut, last, depth) recursion on the right part
             int stF[48], stL[48], stD[48]; int sp = 0;
@@ -559,15 +668,17 @@ CG_HD bool collect(const IndexView& ix, const ReadView& rv, bool strict, int lce
 
     // ---- Phase A (:112-200)
     int rb = 0;
+    bool preA = false, preF = false, preR = false; uint32_t pb_ = 0, pe_ = 0, prb_ = 0, pre_ = 0;
     while (rb + k < L) {
         int inv = rv.first_n(0, rb);
-        if (inv < L && inv <= rb + k) { rb = inv + 1; continue; }                 // :118
+        if (inv < L && inv <= rb + k) { rb = inv + 1; preA = false; continue; }    // :118
         uint64_t mer = rv.chunk(0, rb) & KM;
-        if (homopolymer(mer, k)) { rb += homoSkip; continue; }                      // :127
+        if (homopolymer(mer, k)) { rb += homoSkip; preA = false; continue; }        // :127
         uint64_t rcm = revcomp(mer, k);
-        uint32_t b, e, rb_, re_;
-        bool hasF = probe(ix, mer, b, e);                                           // :131
-        bool hasR = probe(ix, rcm, rb_, re_);                                       // :132
+        uint32_t b = pb_, e = pe_, rb_ = prb_, re_ = pre_;
+        bool hasF = preF, hasR = preR;
+        if (!preA) probe2(ix, mer, rcm, hasF, b, e, hasR, rb_, re_);                // :131-132
+        preA = false;
         if (hasF) {
             uint32_t lbRestart = b > 0 ? b - 1 : 0;                                 // :140
             extend(ix, rv, 0, rb, lbRestart, e, k, lbF, ubF, matched);              // :143
@@ -586,6 +697,40 @@ CG_HD bool collect(const IndexView& ix, const ReadView& rv, bool strict, int lce
         }
         if (fwdHit + rcHit > 0) { found = true; break; }
         ++rb;
+        if (hasF) continue;     // the table holds the forward k-mer (its interval was too wide): plain step
+        // neither k-mer is in the table: the loop now walks rb+1, rb+2, ... whatever the look-ups return,
+        // so the next two positions (four look-ups) go out together
+        for (;;) {
+            int q[2]; uint64_t kf[2], kr[2], hf[2], hr[2]; u32x4 sf[2], sr[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                q[c] = -1; kf[c] = kr[c] = hf[c] = hr[c] = 0;
+                sf[c].x = sf[c].y = sf[c].z = sf[c].w = 0; sr[c] = sf[c];
+                while (rb + k < L) {
+                    int iv = rv.first_n(0, rb);
+                    if (iv < L && iv <= rb + k) { rb = iv + 1; continue; }
+                    uint64_t kw = rv.chunk(0, rb) & KM;
+                    if (homopolymer(kw, k)) { rb += homoSkip; continue; }
+                    q[c] = rb; kf[c] = kw; kr[c] = revcomp(kw, k);
+                    hf[c] = home_slot(ix, kf[c]); hr[c] = home_slot(ix, kr[c]);
+                    sf[c] = CG_LDG(&ix.hslots[hf[c]]); sr[c] = CG_LDG(&ix.hslots[hr[c]]);
+                    ++rb;
+                    break;
+                }
+            }
+            int got = -1;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (got < 0 && q[c] >= 0) {
+                    uint32_t b1 = 0, e1 = 0, b2 = 0, e2 = 0;
+                    bool f1 = resolve(ix, kf[c], hf[c], sf[c], b1, e1);
+                    bool f2 = resolve(ix, kr[c], hr[c], sr[c], b2, e2);
+                    if (f1 || f2) { got = q[c]; preF = f1; preR = f2; pb_ = b1; pe_ = e1; prb_ = b2; pre_ = e2; }
+                }
+            }
+            if (got >= 0) { rb = got; preA = true; break; }
+            if (q[1] < 0) break;                // ran off the read
+        }
     }
     if (!found) return false;                                                       // :204
 
@@ -606,13 +751,16 @@ CG_HD bool collect(const IndexView& ix, const ReadView& rv, bool strict, int lce
             if (!(rcHit >= fwdHit)) continue;                                       // :332
             o = 0;
         }
+        bool pre = false; uint32_t preB = 0, preE = 0;     // k-mer at o already looked up by the scan-ahead below
         while (o + k <= L) {                                                        // :234 / :341-344
             int inv = rv.first_n(s, o);
-            if (inv < o + k) { o = inv + 1; continue; }                             // :247 / :357 (inv < L here)
+            if (inv < o + k) { o = inv + 1; pre = false; continue; }               // :247 / :357 (inv < L here)
             uint64_t own = rv.chunk(s, o) & KM;         // k-mer as read on this strand
-            if (homopolymer(own, k)) { o += homoSkip; continue; }                   // :260 / :370 (rc of a homopolymer is one too)
-            uint32_t b, e;
-            if (probe(ix, own, b, e)) {                                             // :261 / :372
+            if (homopolymer(own, k)) { o += homoSkip; pre = false; continue; }      // :260 / :370 (rc of a homopolymer is one too)
+            uint32_t b = preB, e = preE;
+            bool hit = pre ? true : probe(ix, own, b, e);                           // :261 / :372
+            pre = false;
+            if (hit) {
                 int fpos = s == 0 ? o : L - (o + k);     // forward offset of this k-mer (:366)
                 if (strict) {
                     bool other = present(ix, revcomp(own, k));                      // :268 / :379
@@ -639,7 +787,37 @@ CG_HD bool collect(const IndexView& ix, const ReadView& rv, bool strict, int lce
                     lastSearch = true; o = L - k;
                 }
             } else {
-                o += 1;                                                             // sampFactor :324 / :436
+                // sampFactor = 1 (:324 / :436): the loop would now try o+1, o+2, ... one dependent table
+                // look-up at a time.  The positions it visits do not depend on the look-ups' results, so the
+                // next four are looked up together and the first one present is where the loop resumes.
+                o += 1;
+                for (;;) {
+                    int q[4]; uint64_t key[4], hh[4]; u32x4 sl[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        q[c] = -1; key[c] = 0; hh[c] = 0; sl[c].x = sl[c].y = sl[c].z = sl[c].w = 0;
+                        while (o + k <= L) {
+                            int iv = rv.first_n(s, o);
+                            if (iv < o + k) { o = iv + 1; continue; }
+                            uint64_t kw = rv.chunk(s, o) & KM;
+                            if (homopolymer(kw, k)) { o += homoSkip; continue; }
+                            q[c] = o; key[c] = kw; hh[c] = home_slot(ix, kw);
+                            sl[c] = CG_LDG(&ix.hslots[hh[c]]);
+                            ++o;
+                            break;
+                        }
+                    }
+                    int got = -1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (got < 0 && q[c] >= 0) {
+                            uint32_t bb, ee;
+                            if (resolve(ix, key[c], hh[c], sl[c], bb, ee)) { got = q[c]; preB = bb; preE = ee; }
+                        }
+                    }
+                    if (got >= 0) { o = got; pre = true; break; }
+                    if (q[3] < 0) break;            // ran off the read: o + k > L, the outer loop ends
+                }
             }
         }
     }
@@ -649,7 +827,7 @@ CG_HD bool collect(const IndexView& ix, const ReadView& rv, bool strict, int lce
         if (fwdHit > 0 && rcHit == 0) st.nR = 0;
         else if (rcHit > 0 && fwdHit == 0) st.nF = 0;
         else {
-            StdSort ss; ss.a = st.ks; ss.sort(st.nKS);                              // :450
+            StdSort ss; ss.a = st.ks; ss.template sort<(MAXKS > 16)>(st.nKS);                              // :450
             int fs = 0, rs = 0;
             uint32_t prevKey = 0xffffffffu;
             for (int i = 0; i < st.nKS; ++i) {                                      // std::unique keeps the first of each run
@@ -742,13 +920,22 @@ CG_HD int hit_tids(const IndexView& ix, const Interval* ints, int n, HitScratch<
         if (ints[i].end - ints[i].begin < ints[mi].end - ints[mi].begin) mi = i;
     const Interval mh = ints[mi];
     int nc = 0;
-    for (uint32_t i = mh.begin; i < mh.end; ++i) {
-        uint32_t p = CG_LDG(&ix.sa[i]), tid, local;
-        tid_of(ix, p, tid, local);
-        if (nc >= maxc) { err |= CG_ERR_HITS; break; }
-        h.tid[nc] = tid; h.act[nc] = 1;
-        if (WITH_POS) { h.pos[nc] = local; h.qp[nc] = mh.qpos; }
-        ++nc;
+    for (uint32_t i0 = mh.begin; i0 < mh.end; i0 += 4) {
+        int nn = (int)cmin<uint32_t>(4u, mh.end - i0);
+        uint32_t tt[4], ll[4];
+        sa_tids4(ix, i0, nn, tt, ll);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            if (x < nn) {
+                if (nc >= maxc) { err |= CG_ERR_HITS; }
+                else {
+                    h.tid[nc] = tt[x]; h.act[nc] = 1;
+                    if (WITH_POS) { h.pos[nc] = ll[x]; h.qp[nc] = mh.qpos; }
+                    ++nc;
+                }
+            }
+        }
+        if (err & CG_ERR_HITS) break;
     }
     hs_sort(h, nc);
     // unique by tid keeping the smallest pos (first after the (tid,pos) sort)
@@ -772,14 +959,21 @@ CG_HD int hit_tids(const IndexView& ix, const Interval* ints, int n, HitScratch<
         if (dup) {
             for (int c = 0; c < nc; ++c) if (h.act[c] == counter - 1) h.act[c] = (uint8_t)counter;
         } else {
-            for (uint32_t i = it.begin; i < it.end; ++i) {
-                uint32_t p = CG_LDG(&ix.sa[i]), tid, local;
-                tid_of(ix, p, tid, local);
-                int lo = 0, hi = nc;
-                while (lo < hi) { int md = (lo + hi) >> 1; if (h.tid[md] < tid) lo = md + 1; else hi = md; }
-                if (lo < nc && h.tid[lo] == tid) {
-                    if (h.act[lo] == counter - 1) h.act[lo] = (uint8_t)counter;
-                    if (WITH_POS && h.act[lo] == counter && local < h.pos[lo]) { h.pos[lo] = local; h.qp[lo] = it.qpos; }
+            for (uint32_t i0 = it.begin; i0 < it.end; i0 += 4) {
+                int nn = (int)cmin<uint32_t>(4u, it.end - i0);
+                uint32_t tt[4], ll[4];
+                sa_tids4(ix, i0, nn, tt, ll);
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    if (z < nn) {
+                        uint32_t tid = tt[z], local = ll[z];
+                        int lo = 0, hi = nc;
+                        while (lo < hi) { int md = (lo + hi) >> 1; if (h.tid[md] < tid) lo = md + 1; else hi = md; }
+                        if (lo < nc && h.tid[lo] == tid) {
+                            if (h.act[lo] == counter - 1) h.act[lo] = (uint8_t)counter;
+                            if (WITH_POS && h.act[lo] == counter && local < h.pos[lo]) { h.pos[lo] = local; h.qp[lo] = it.qpos; }
+                        }
+                    }
                 }
             }
         }

@@ -19,9 +19,9 @@ struct PackGeom {
         g.WT = g.W2f + g.WMf;
         return g;
     }
-    // shared-memory words per thread for the two-strand view, padded to an odd count so that lanes
-    // reading the same word index of their own strands hit distinct banks
-    __host__ __device__ int chunk() const { return (2 * (W2f + 1 + WMf + 1)) | 1; }
+    // shared-memory words per thread for the read view, padded to an odd count so that lanes reading
+    // the same word index of their own reads hit distinct banks
+    __host__ __device__ int chunk() const { return (W2f + 1 + WMf + 1) | 1; }
 };
 
 // 4 ASCII bases -> 4 x 2-bit codes (bits 0..7), N flags (bits 0..3) and "other character" flags
@@ -105,13 +105,9 @@ static __global__ void k_pack(const unsigned char* __restrict__ b1, const uint64
     if ((g.W2f & 1) && j == g.W2f - 1) mw[1] = 0xFFFFFFFFu;
 }
 
-// set up this thread's two-strand view in shared memory
+// set up this thread's read view in shared memory
 __device__ __forceinline__ ReadView make_view(const uint64_t* __restrict__ rec, const PackGeom& g, int L, uint64_t* smem) {
-    uint64_t* dst = smem + (size_t)threadIdx.x * g.chunk();
-    build_strands(rec, 1, L, g.W2f, g.WMf, dst);
-    ReadView rv;
-    rv.w = dst; rv.stride = 1; rv.L = L; rv.W2 = g.W2f + 1; rv.WM = g.WMf + 1;
-    return rv;
+    return build_view(rec, 1, L, g.W2f, g.WMf, smem + (size_t)threadIdx.x * g.chunk());
 }
 
 } // namespace cgk

@@ -92,19 +92,107 @@ CG_HD void bsj_record(const IndexView& ix, const ReadView& rv, int lceMode, Scra
         int n = dir == 0 ? sc.st.nF : sc.st.nR;
         for (int x = 0; x < n; ++x) {
             const Interval it = ints[x];
-            for (uint32_t i = it.begin; i != it.end; ++i) {                         // :326 / :355
-                uint32_t p = CG_LDG(&ix.sa[i]), tid, local;
-                tid_of(ix, p, tid, local);
-                uint32_t refLen = CG_LDG(&ix.offsets[tid + 1]) - CG_LDG(&ix.offsets[tid]) - 1;
-                int hitPos = (int)local;
-                int junctPos = (int)(refLen / 2);                                   // :333
-                if (hitPos < junctPos - 5 && hitPos + (int)it.len > junctPos + 5) { // :336 / :364
-                    sink.line((uint32_t)dir, it.qpos, it.len, hitPos, tid);
-                    isSplit = true;
+            for (uint32_t i0 = it.begin; i0 < it.end; i0 += 4) {                    // :326 / :355
+                int nn = (int)cmin<uint32_t>(4u, it.end - i0);
+                uint32_t tt[4], ll[4], o0[4], o1[4];
+                sa_tids4(ix, i0, nn, tt, ll);
+#pragma unroll
+                for (int z = 0; z < 4; ++z) if (z < nn) { o0[z] = CG_LDG(&ix.offsets[tt[z]]); o1[z] = CG_LDG(&ix.offsets[tt[z] + 1]); }
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    if (z < nn) {
+                        uint32_t refLen = o1[z] - o0[z] - 1;
+                        int hitPos = (int)ll[z];
+                        int junctPos = (int)(refLen / 2);                           // :333
+                        if (hitPos < junctPos - 5 && hitPos + (int)it.len > junctPos + 5) { // :336 / :364
+                            sink.line((uint32_t)dir, it.qpos, it.len, hitPos, tt[z]);
+                            isSplit = true;
+                        }
+                    }
                 }
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: the same collector with small fixed capacities so that all of its state fits in shared
+// memory (no local-memory scratch).  A read that needs more than FI intervals per strand, FK k-mer
+// scores, HC hit candidates, or keeps both strands after the vote is reported back (return false,
+// nothing emitted) and redone by the general path above — results are identical either way.
+// ---------------------------------------------------------------------------------------------
+template <int FI, int FK, int HC>
+struct FastScratch {
+    CollectState<FI, FK> st;
+    uint32_t tid[HC];
+    uint8_t act[HC];
+};
+
+template <int FI, int FK, int HC>
+CG_HD bool fast_collect_hits(const IndexView& ix, const ReadView& rv, int lceMode, FastScratch<FI, FK, HC>& sc, bool& found, int& nh) {
+    nh = 0;
+    found = collect<FI, FK>(ix, rv, true, lceMode, sc.st);
+    if (sc.st.err) return false;
+    if (!found) return true;
+    if (sc.st.nF > 0 && sc.st.nR > 0) return false;
+    HitScratch<false> hs; hs.tid = sc.tid; hs.act = sc.act; hs.pos = nullptr; hs.qp = nullptr;
+    int err = 0;
+    if (sc.st.nF) nh = hit_tids<false>(ix, sc.st.fwd, sc.st.nF, hs, HC, err);
+    else if (sc.st.nR) nh = hit_tids<false>(ix, sc.st.rc, sc.st.nR, hs, HC, err);
+    return err == 0;
+}
+
+template <int FI, int FK, int HC>
+CG_HD bool wt_mate_fast(const IndexView& ix, const ReadView& rv, int pairReadLen, int lceMode, FastScratch<FI, FK, HC>& sc,
+                        uint8_t& flags, uint32_t& nhits) {
+    flags = 0; nhits = 0;
+    bool found; int nh;
+    if (!fast_collect_hits(ix, rv, lceMode, sc, found, nh)) return false;
+    if (!found) return true;
+    if (sc.st.nF + sc.st.nR > 0) flags |= MATE_SEEDED;
+    bool full = false;
+    for (int i = 0; i < sc.st.nF; ++i) if ((int)sc.st.fwd[i].len == pairReadLen) { full = true; break; }
+    for (int i = 0; i < sc.st.nR && !full; ++i) if ((int)sc.st.rc[i].len == pairReadLen) full = true;
+    if (full) flags |= MATE_FULL;
+    nhits = (uint32_t)nh;
+    return true;
+}
+
+// tids of jointHits are left in sc.tid[0..nhits)
+template <int FI, int FK, int HC, class Sink>
+CG_HD bool bsj_record_fast(const IndexView& ix, const ReadView& rv, int lceMode, FastScratch<FI, FK, HC>& sc, Sink& sink,
+                           uint32_t& nhits, bool& isSplit) {
+    nhits = 0; isSplit = false;
+    bool found; int nh;
+    if (!fast_collect_hits(ix, rv, lceMode, sc, found, nh)) return false;
+    nhits = (uint32_t)nh;
+    if (!found || nh == 0) return true;                                             // :319
+    const int dir = sc.st.nF ? 0 : 1;
+    const Interval* ints = dir == 0 ? sc.st.fwd : sc.st.rc;
+    const int n = dir == 0 ? sc.st.nF : sc.st.nR;
+    for (int x = 0; x < n; ++x) {
+        const Interval it = ints[x];
+        for (uint32_t i0 = it.begin; i0 < it.end; i0 += 4) {                        // :326 / :355
+            int nn = (int)cmin<uint32_t>(4u, it.end - i0);
+            uint32_t tt[4], ll[4], o0[4], o1[4];
+            sa_tids4(ix, i0, nn, tt, ll);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) if (z < nn) { o0[z] = CG_LDG(&ix.offsets[tt[z]]); o1[z] = CG_LDG(&ix.offsets[tt[z] + 1]); }
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+                if (z < nn) {
+                    uint32_t refLen = o1[z] - o0[z] - 1;
+                    int hitPos = (int)ll[z];
+                    int junctPos = (int)(refLen / 2);                               // :333
+                    if (hitPos < junctPos - 5 && hitPos + (int)it.len > junctPos + 5) { // :336 / :364
+                        sink.line((uint32_t)dir, it.qpos, it.len, hitPos, tt[z]);
+                        isSplit = true;
+                    }
+                }
+            }
+        }
+    }
+    return true;
 }
 
 } // namespace cg

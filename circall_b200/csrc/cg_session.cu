@@ -9,6 +9,7 @@
 //                                                                   src/Circall_bsj.cpp:300-399,488-491
 // Nothing here falls back to the host: without a CUDA device session creation fails.
 #include "cg_kernels.cuh"
+#include "cg_warp.cuh"
 #include <algorithm>
 #include <cstring>
 
@@ -29,23 +30,117 @@ struct BatchHdr {
     unsigned long long n_eq_tids;
     uint32_t n_exp;
     int status;
+    uint32_t n_ovf_wt;             // mates / records the fast path handed to the general kernels
+    uint32_t n_ovf_bsj;
 };
 
-template <int MAXINT, int MAXKS>
-__global__ void __launch_bounds__(128)
-k_wt(IndexView ix, const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
-     int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits) {
+// ---- warp-per-read kernels --------------------------------------------------------------------------
+static const int WARPS_PER_BLOCK = 8;
+typedef cgw::WStateT<cgw::FAST_FI, cgw::FAST_FK> FastState;
+typedef cgw::WStateT<cgw::GEN_FI, cgw::GEN_FK> GenState;
+// per-warp global scratch of the general kernels: collector state, two hit lists with their marks, merged list
+static const size_t GEN_SCRATCH = ((sizeof(GenState) + 15) / 16) * 16 + 2 * (cgw::WSCR * 4 + cgw::WSCR) + 2 * cgw::WSCR * 4;
+// shared-memory bytes of one warp: read view words (+ the fast kernels' collector state, + 64 transcript ids for bsj)
+__host__ __device__ inline int warp_smem_bytes(const PackGeom& g, bool gen, bool bsj) {
+    return (g.W2f + 1 + g.WMf + 1) * 8 + (gen ? 0 : (int)sizeof(FastState) + (bsj ? 64 * 4 : 0));
+}
+// stage the packed read of this warp into shared memory
+__device__ __forceinline__ cgw::RV warp_view(const uint64_t* __restrict__ rec, const PackGeom& g, int L, uint64_t* dst, int lane) {
+    const int W2 = g.W2f + 1;
+    __syncwarp();
+    for (int j = lane; j < g.WT; j += 32) {
+        uint64_t v = __ldg(rec + j);
+        dst[j < g.W2f ? j : W2 + (j - g.W2f)] = v;
+    }
+    if (lane == 0) { dst[g.W2f] = 0; dst[W2 + g.WMf] = ~0ULL; }
+    __syncwarp();
+    // any N below L?  (mask bits past the read's end are set by construction)
+    uint64_t m = 0;
+    if (lane < g.WMf) {
+        int lo = 64 * lane;
+        m = dst[W2 + lane];
+        if (lo >= L) m = 0; else if (L - lo < 64) m &= (1ULL << (L - lo)) - 1;
+    }
+    cgw::RV rv; rv.w = dst; rv.L = L; rv.W2 = W2; rv.anyN = __any_sync(cgw::FULL, m != 0) ? 1 : 0;
+    return rv;
+}
+// hits of both strands merged by transcript (:567-579): number of distinct transcripts
+__device__ __forceinline__ uint32_t warp_union_count(uint32_t tidF, bool aliveF, uint32_t tidR, bool aliveR) {
+    unsigned fB = __ballot_sync(cgw::FULL, aliveF), rB = __ballot_sync(cgw::FULL, aliveR);
+    uint32_t n = __popc(fB) + __popc(rB);
+    if (fB && rB) {
+        bool common = false;
+#pragma unroll 1
+        for (unsigned m = fB; m; m &= m - 1) common |= (__shfl_sync(cgw::FULL, tidF, __ffs(m) - 1) == tidR);
+        n -= __popc(__ballot_sync(cgw::FULL, aliveR && common));
+    }
+    return n;
+}
+// where the general kernels keep their per-warp state
+struct GenPtrs { GenState* st; uint32_t* scrA; uint8_t* actA; uint32_t* scrB; uint8_t* actB; uint32_t* merged; };
+__device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) {
+    unsigned char* p = base + warp * GEN_SCRATCH;
+    GenPtrs g;
+    g.st = reinterpret_cast<GenState*>(p); p += ((sizeof(GenState) + 15) / 16) * 16;
+    g.scrA = reinterpret_cast<uint32_t*>(p); p += cgw::WSCR * 4;
+    g.scrB = reinterpret_cast<uint32_t*>(p); p += cgw::WSCR * 4;
+    g.merged = reinterpret_cast<uint32_t*>(p); p += 2 * cgw::WSCR * 4;
+    g.actA = p; p += cgw::WSCR;
+    g.actB = p;
+    return g;
+}
+
+// K2-K6: one warp per mate (persistent warps, grid-stride).
+//   GEN = false: over all n mates, state in shared memory; ovf[r] = 1 hands the mate to the general kernel
+//   GEN = true : over list[0..*n_list), worst-case state in global scratch
+template <bool GEN>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
+          const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
+          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
     extern __shared__ uint64_t smem[];
-    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    int L = lens[r];
-    int pairLen = lens[r & ~1ULL];                 // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
-    ReadView rv = make_view(pk + r * (uint64_t)g.WT, g, L, smem);
-    Scratch<MAXINT, MAXKS, false> sc;
-    uint8_t fl; uint32_t nh;
-    wt_mate<MAXINT, MAXKS>(ix, rv, pairLen, lceMode, sc, fl, nh);
-    flags[r] = fl;
-    nhits[r] = nh;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, false) / 8);
+    const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_BLOCK, warp = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
+    GenPtrs gp;
+    if (GEN) gp = gen_ptrs(gscratch, warp);
+    const uint64_t n = GEN ? (uint64_t)*n_list : n_reads;
+    for (uint64_t x = warp; x < n; x += nwarps) {
+        const uint64_t r = GEN ? (uint64_t)list[x] : x;
+        int L = lens[r];
+        int pairLen = lens[r & ~1ULL];             // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+        cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
+        bool found, ok; int nF, nR;
+        const Interval* fwd; const Interval* rc;
+        if (GEN) {
+            ok = cgw::w_collect<0, cgw::GEN_FI, cgw::GEN_FK>(rv, lane, lceMode, *gp.st, found, nF, nR);
+            fwd = gp.st->fwd; rc = gp.st->rc;
+        } else {
+            FastState& st = *reinterpret_cast<FastState*>(mine + (g.W2f + 1 + g.WMf + 1));
+            ok = cgw::w_collect<0, cgw::FAST_FI, cgw::FAST_FK>(rv, lane, lceMode, st, found, nF, nR);
+            fwd = st.fwd; rc = st.rc;
+        }
+        uint8_t fl = 0; uint32_t nh = 0;
+        if (ok && found) {
+            if (nF + nR > 0) fl |= MATE_SEEDED;                                   // Circall_wt.cpp:311,486
+            bool full = false;                                                    // :318-342,493-517
+#pragma unroll 1
+            for (int i = lane; i < nF; i += 32) full |= ((int)fwd[i].len == pairLen);
+#pragma unroll 1
+            for (int i = lane; i < nR; i += 32) full |= ((int)rc[i].len == pairLen);
+            if (__any_sync(cgw::FULL, full)) fl |= MATE_FULL;
+            if (GEN) {
+                uint32_t a = cgw::w_hits_list<0>(lane, fwd, nF, gp.scrA, gp.actA);
+                uint32_t b = cgw::w_hits_list<0>(lane, rc, nR, gp.scrB, gp.actB);
+                nh = (a && b) ? cgw::w_merge(lane, gp.scrA, a, gp.scrB, b, gp.merged) : a + b;
+            } else {
+                cgw::Hits hF = cgw::w_hits_lanes<0>(lane, fwd, nF), hR = cgw::w_hits_lanes<0>(lane, rc, nR);
+                ok = hF.ok && hR.ok;
+                if (ok) nh = warp_union_count(hF.tid, hF.alive, hR.tid, hR.alive);
+            }
+        }
+        if (lane == 0) { flags[r] = ok ? fl : MATE_ERR; nhits[r] = ok ? nh : 0; if (!GEN) ovf[r] = ok ? 0 : 1; }
+    }
 }
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* sh) {
@@ -173,52 +268,139 @@ struct BsjOut {
     BatchHdr* hdr;
 };
 
-// one thread per exported record.  exp_mate == nullptr: record rec is mate 1 of pair rec (stage 2).
-// do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes
-template <int MAXINT, int MAXKS>
-__global__ void __launch_bounds__(128)
-k_bsj(IndexView ix, const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
-      const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, int lceMode, BsjOut o, int do_counts) {
+// K2-K5, K7, K8: one warp per exported record (persistent warps).  exp_mate == nullptr: record rec is mate 1 of
+// pair rec (stage 2).
+//   GEN = false: over all records (count read from the device), state in shared memory; a record that exceeds a
+//                fast capacity is flagged in ovf[] and emits nothing here
+//   GEN = true : over list[0..*n_list), worst-case state in global scratch
+// do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes.
+template <bool GEN>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
+           const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
+           int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
     extern __shared__ uint64_t smem[];
-    uint64_t rec = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint64_t nrec = exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed;
-    bool valid = rec < nrec;
-    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
-    if (valid) {
-        uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, true) / 8);
+    const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_BLOCK, warp = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
+    const IndexView& ix = cgw::c_ix[1];
+    GenPtrs gp;
+    if (GEN) gp = gen_ptrs(gscratch, warp);
+    const uint64_t n = GEN ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
+    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;          // per-warp totals (kept by every lane alike)
+    for (uint64_t x = warp; x < n; x += nwarps) {
+        const uint64_t rec = GEN ? (uint64_t)list[x] : x;
+        const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
         int L = lens[r];
-        ReadView rv = make_view(pk + r * (uint64_t)g.WT, g, L, smem);
-        Scratch<MAXINT, MAXKS, false> sc;
-        uint32_t tids[MAX_READ_OCCS];
-        JSink sink{o.junc, &o.hdr->n_junc, o.junc_cap, (uint32_t)rec};
-        uint32_t nh; bool split; uint8_t err;
-        bsj_record<MAXINT, MAXKS>(ix, rv, lceMode, sc, sink, nh, split, tids, err);
-        if (err) atomicOr(&o.hdr->status, ST_CAPACITY);
-        o.rec_nhits[rec] = nh;
-        o.rec_split[rec] = split ? 1 : 0;
-        upper = nh > 0;                                                          // Circall_bsj.cpp:383
-        uint32_t c = nh > (uint32_t)MAX_READ_OCCS ? 0 : nh;                      // :385
-        bool cand = c > 0 && split;                                              // :390
-        obs = 1; mapped = cand; hits = c;                                        // :488-491
+        cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
+        bool found, ok; int nF, nR;
+        const Interval* fwd; const Interval* rc;
+        uint32_t* tl;                                            // class key (ordered transcript list)
+        if (GEN) {
+            ok = cgw::w_collect<1, cgw::GEN_FI, cgw::GEN_FK>(rv, lane, lceMode, *gp.st, found, nF, nR);
+            fwd = gp.st->fwd; rc = gp.st->rc; tl = gp.merged;
+        } else {
+            FastState& st = *reinterpret_cast<FastState*>(mine + (g.W2f + 1 + g.WMf + 1));
+            ok = cgw::w_collect<1, cgw::FAST_FI, cgw::FAST_FK>(rv, lane, lceMode, st, found, nF, nR);
+            fwd = st.fwd; rc = st.rc; tl = reinterpret_cast<uint32_t*>(&st + 1);
+        }
+        uint32_t nh = 0;
+        if (ok && found) {
+            if (GEN) {
+                uint32_t a = cgw::w_hits_list<1>(lane, fwd, nF, gp.scrA, gp.actA);
+                uint32_t b = cgw::w_hits_list<1>(lane, rc, nR, gp.scrB, gp.actB);
+                if (a && b) nh = cgw::w_merge(lane, gp.scrA, a, gp.scrB, b, gp.merged);
+                else { nh = a + b; tl = a ? gp.scrA : gp.scrB; }
+            } else {
+                cgw::Hits hF = cgw::w_hits_lanes<1>(lane, fwd, nF), hR = cgw::w_hits_lanes<1>(lane, rc, nR);
+                ok = hF.ok && hR.ok;
+                if (ok) {
+                    nh = warp_union_count(hF.tid, hF.alive, hR.tid, hR.alive);
+                    if (nh > 0 && nh <= 64) {
+                        // gather the hit transcripts, sort and de-duplicate them on lane 0 (a handful of entries)
+                        unsigned fB = __ballot_sync(cgw::FULL, hF.alive), rB = __ballot_sync(cgw::FULL, hR.alive);
+                        __syncwarp();
+                        if (hF.alive) tl[__popc(fB & ((1u << lane) - 1))] = hF.tid;
+                        if (hR.alive) tl[__popc(fB) + __popc(rB & ((1u << lane) - 1))] = hR.tid;
+                        __syncwarp();
+                        if (lane == 0) {
+                            int nn = __popc(fB) + __popc(rB);
+                            for (int i = 1; i < nn; ++i) { uint32_t v = tl[i]; int j = i - 1; while (j >= 0 && tl[j] > v) { tl[j + 1] = tl[j]; --j; } tl[j + 1] = v; }
+                            int m = 0;
+                            for (int i = 0; i < nn; ++i) if (m == 0 || tl[m - 1] != tl[i]) tl[m++] = tl[i];
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (!ok) { if (lane == 0) ovf[rec] = 1; continue; }
+        bool split = false;
+        if (nh > 0) {                                                             // Circall_bsj.cpp:319
+#pragma unroll 1
+            for (int dir = 0; dir < 2; ++dir) {
+                const Interval* ints = dir == 0 ? fwd : rc;
+                const int ni = dir == 0 ? nF : nR;
+#pragma unroll 1
+                for (int xi = 0; xi < ni; ++xi) {
+                    const Interval it = ints[xi];
+#pragma unroll 1
+                    for (uint32_t c0 = it.begin; c0 < it.end; c0 += 32) {         // :326 / :355, 32 positions per round
+                        bool pred = false; uint32_t tid = 0; int hitPos = 0;
+                        if (c0 + lane < it.end) {
+                            uint32_t p = __ldg(&ix.sa[c0 + lane]), local;
+                            tid_of(ix, p, tid, local);
+                            uint32_t refLen = __ldg(&ix.offsets[tid + 1]) - __ldg(&ix.offsets[tid]) - 1;
+                            hitPos = (int)local;
+                            int junctPos = (int)(refLen / 2);                     // :333
+                            pred = hitPos < junctPos - 5 && hitPos + (int)it.len > junctPos + 5;   // :336 / :364
+                        }
+                        unsigned pB = __ballot_sync(cgw::FULL, pred);
+                        if (pB) {
+                            split = true;
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&o.hdr->n_junc, (unsigned long long)__popc(pB));
+                            base = cgw::shfl64(base, 0);
+                            if (pred) {
+                                unsigned long long slot = base + __popc(pB & ((1u << lane) - 1));
+                                if (slot < o.junc_cap) {
+                                    cg_junction j; j.rec = (uint32_t)rec; j.dir = (uint32_t)dir; j.query_pos = it.qpos; j.len = it.len;
+                                    j.hit_pos = hitPos; j.tid = tid;
+                                    o.junc[slot] = j;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // commit (Circall_bsj.cpp:383-491)
+        if (lane == 0) { o.rec_nhits[rec] = nh; o.rec_split[rec] = split ? 1 : 0; }
+        upper += nh > 0;                                                          // :383
+        const uint32_t c = nh > (uint32_t)MAX_READ_OCCS ? 0 : nh;                 // :385
+        const bool cand = c > 0 && split;                                         // :390
+        obs += 1; mapped += cand; hits += c;                                      // :488-491
         if (cand) {
+            // tl[0..c) = jointHits' transcripts in ascending order (the fast kernel fills it for nh <= 64; a fast
+            // record with more hits than that is impossible: <= 32 per strand)
             if (c == 1) {
-                if (do_counts & 1) atomicAdd(&o.per_bsj[tids[0]], 1ULL);         // single-transcript class (EquivalenceClassBuilder.hpp:112-130)
+                if ((do_counts & 1) && lane == 0) atomicAdd(&o.per_bsj[tl[0]], 1ULL); // single-transcript class (EquivalenceClassBuilder.hpp:112-130)
             } else if (do_counts & 2) {
-                unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL);
-                unsigned long long s = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)c);
-                if (e < o.eq_cap && s + c <= o.eq_tids_cap) {
-                    o.eq_ent[e] = make_uint4((uint32_t)rec, (uint32_t)s, c, 0u);
-                    for (uint32_t t = 0; t < c; ++t) o.eq_tids[s + t] = tids[t];
+                unsigned long long e = 0, sidx = 0;
+                if (lane == 0) { e = atomicAdd(&o.hdr->n_eq, 1ULL); sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)c); }
+                e = cgw::shfl64(e, 0); sidx = cgw::shfl64(sidx, 0);
+                if (e < o.eq_cap && sidx + c <= o.eq_tids_cap) {
+                    if (lane == 0) o.eq_ent[e] = make_uint4((uint32_t)rec, (uint32_t)sidx, c, 0u);
+                    for (uint32_t t = lane; t < c; t += 32) o.eq_tids[sidx + t] = tl[t];
                 }
             }
         }
     }
-    if (do_counts & 1) {
-        uint32_t s;
-        s = __reduce_add_sync(0xffffffffu, obs);    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)s);
-        s = __reduce_add_sync(0xffffffffu, mapped); if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)s);
-        s = __reduce_add_sync(0xffffffffu, hits);   if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)s);
-        s = __reduce_add_sync(0xffffffffu, upper);  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)s);
+    if ((do_counts & 1) && lane == 0) {
+        if (obs) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)obs);
+        if (mapped) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)mapped);
+        if (hits) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)hits);
+        if (upper) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)upper);
     }
 }
 
@@ -234,6 +416,9 @@ struct cg_session {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr, evw = nullptr, evc = nullptr;
     uint64_t launches = 0;
+    int warp_grid_wt = 0, warp_grid_bsj = 0;     // persistent grids of the warp-per-read kernels (SMs x resident blocks)
+    int gen_grid = 0;                            // grid of the general kernels (sized with the per-warp global scratch)
+    unsigned char* d_gscratch = nullptr;
     bool pending = false;
     // batch state
     uint64_t n_pairs = 0;
@@ -244,7 +429,7 @@ struct cg_session {
     const uint64_t* in_off1 = nullptr; const uint64_t* in_off2 = nullptr;
     // device buffers
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
-        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr;
+        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list;
     unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
@@ -271,25 +456,43 @@ int launch(cg_session* s, K kern, dim3 grid, dim3 block, size_t smem, A... args)
     return CG_OK;
 }
 
+// ordered compaction of the set flags of f[0..n) into out[], count into *total
+int compact_flags(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, uint32_t* total) {
+    uint32_t nb = grid_for(n, CP_TILE);
+    int rc = launch(s, k_flag_count, dim3(nb), dim3(CP_THREADS), 0, f, n, s->d_bc.as<uint32_t>());
+    if (rc) return rc;
+    rc = launch(s, k_flag_scan, dim3(1), dim3(1024), 0, s->d_bc.as<uint32_t>(), nb, total);
+    if (rc) return rc;
+    return launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, f, n, s->d_bc.as<uint32_t>(), out);
+}
+
+
 int run_bsj_stage(cg_session* s, int do_counts) {
-    const int BS = 128;
     const uint64_t n_reads = 2 * s->n_pairs;
     const bool stage2 = s->opts.stage == 2;
     const uint64_t worst = stage2 ? s->n_pairs : n_reads;
+    if (worst == 0) return CG_OK;
     BsjOut o;
     o.junc = s->d_junc.as<cg_junction>(); o.junc_cap = s->junc_cap;
     o.eq_ent = s->d_eqent.as<uint4>(); o.eq_cap = s->eq_cap;
     o.eq_tids = s->d_eqtids.as<uint32_t>(); o.eq_tids_cap = s->eq_tids_cap;
     o.rec_nhits = s->d_recnh.as<uint32_t>(); o.rec_split = s->d_recsp.as<uint8_t>();
     o.per_bsj = s->d_acc; o.ctr = s->d_acc + s->n_bsj; o.hdr = s->d_hdr.as<BatchHdr>();
-    size_t smem = (size_t)BS * s->geom.chunk() * 8;
     const uint32_t* em = stage2 ? nullptr : s->d_exp.as<uint32_t>();
     IndexView v = s->bsj->view();
-    if (s->max_len <= 160)
-        return launch(s, k_bsj<136, 544>, dim3(grid_for(worst, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(),
-                      s->geom, em, s->n_pairs, s->opts.lce_mode, o, do_counts);
-    return launch(s, k_bsj<232, 928>, dim3(grid_for(worst, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(),
-                  s->geom, em, s->n_pairs, s->opts.lce_mode, o, do_counts);
+    BatchHdr* dh = s->d_hdr.as<BatchHdr>();
+    CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, worst, s->stream));
+    CG_CUDA(cudaMemcpyToSymbolAsync(cgw::c_ix, &v, sizeof(IndexView), sizeof(IndexView), cudaMemcpyHostToDevice, s->stream));
+    const dim3 blk(WARPS_PER_BLOCK * 32);
+    int rc = launch(s, k_bsj_warp<false>, dim3(s->warp_grid_bsj), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, false, true),
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
+    if (rc) return rc;
+    rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_ovf_bsj);
+    if (rc) return rc;
+    return launch(s, k_bsj_warp<true>, dim3(s->gen_grid), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, true, true),
+                  s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(),
+                  (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch);
 }
 
 int run_batch(cg_session* s) {
@@ -304,6 +507,8 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_expflag.reserve(n_reads + 16));
     CG_CUDA(s->d_exp.reserve(n_reads * 4));
     CG_CUDA(s->d_bc.reserve((n_reads / CP_TILE + 2) * 4));
+    CG_CUDA(s->d_ovf.reserve(n_reads + 16));
+    CG_CUDA(s->d_list.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
@@ -324,29 +529,30 @@ int run_batch(cg_session* s) {
                 s->max_len, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), &s->d_hdr.as<BatchHdr>()->status);
     if (rc) return rc;
     CG_CUDA(cudaEventRecord(s->evp, s->stream));
-    if (stage != 2) {
-        const int BS = 128;
-        size_t smem = (size_t)BS * g.chunk() * 8;
+    if (stage != 2 && n_reads) {
         IndexView v = s->tx->view();
-        if (s->max_len <= 160)
-            rc = launch(s, k_wt<136, 544>, dim3(grid_for(n_reads, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g,
-                        n_reads, s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>());
-        else
-            rc = launch(s, k_wt<232, 928>, dim3(grid_for(n_reads, BS)), dim3(BS), smem, v, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g,
-                        n_reads, s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>());
+        BatchHdr* dh = s->d_hdr.as<BatchHdr>();
+        CG_CUDA(cudaMemcpyToSymbolAsync(cgw::c_ix, &v, sizeof(IndexView), 0, cudaMemcpyHostToDevice, s->stream));
+        const dim3 blk(WARPS_PER_BLOCK * 32);
+        rc = launch(s, k_wt_warp<false>, dim3(s->warp_grid_wt), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false),
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
+                    s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
+        if (rc) return rc;
+        rc = compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_ovf_wt);
+        if (rc) return rc;
+        rc = launch(s, k_wt_warp<true>, dim3(s->gen_grid), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false),
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_ovf_wt,
+                    s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch);
         if (rc) return rc;
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
         rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
                     s->d_expflag.as<uint8_t>(), s->opts.keep_mate_detail ? s->d_mflags.as<uint8_t>() : (uint8_t*)nullptr,
-                    s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_acc + s->n_bsj, s->d_hdr.as<BatchHdr>());
+                    s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_acc + s->n_bsj, dh);
         if (rc) return rc;
-        uint32_t nb = grid_for(n_reads, CP_TILE);
-        rc = launch(s, k_flag_count, dim3(nb), dim3(CP_THREADS), 0, s->d_expflag.as<uint8_t>(), n_reads, s->d_bc.as<uint32_t>());
+        rc = compact_flags(s, s->d_expflag.as<uint8_t>(), n_reads, s->d_exp.as<uint32_t>(), &dh->n_exp);
         if (rc) return rc;
-        rc = launch(s, k_flag_scan, dim3(1), dim3(1024), 0, s->d_bc.as<uint32_t>(), nb, &s->d_hdr.as<BatchHdr>()->n_exp);
-        if (rc) return rc;
-        rc = launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, s->d_expflag.as<uint8_t>(), n_reads, s->d_bc.as<uint32_t>(), s->d_exp.as<uint32_t>());
-        if (rc) return rc;
+    } else if (stage != 2) {
+        CG_CUDA(cudaEventRecord(s->evw, s->stream));
     }
     if (stage == 2) CG_CUDA(cudaEventRecord(s->evw, s->stream));
     CG_CUDA(cudaEventRecord(s->evc, s->stream));
@@ -396,6 +602,18 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_acc, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->d_acc, 0, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = s->h_hdr.reserve(sizeof(BatchHdr));
+    if (e == cudaSuccess) {
+        // persistent grids: as many blocks as stay resident (sized for the largest read geometry in common use)
+        int sms = 0, bw = 0, bb = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        PackGeom g = PackGeom::make(160);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bw, k_wt_warp<false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
+        s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
+        s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
+        s->gen_grid = sms * 2;
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_gscratch, (size_t)s->gen_grid * WARPS_PER_BLOCK * GEN_SCRATCH);
+    }
     if (e != cudaSuccess) { int rc = cgi::cuda_fail(e, "session set-up", __FILE__, __LINE__); cg_session_destroy(s); return rc; }
     *out = s;
     return CG_OK;
@@ -406,10 +624,12 @@ void cg_session_destroy(cg_session* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
-                       &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr})
+                       &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
+                       &s->d_ovf, &s->d_list})
         b->release();
     s->h_hdr.release();
     if (s->d_acc) cudaFree(s->d_acc);
+    if (s->d_gscratch) cudaFree(s->d_gscratch);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->evp) cudaEventDestroy(s->evp);
@@ -497,6 +717,8 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     out->n_export = n_exp;
     out->n_junc = hdr.n_junc;
     out->n_eq = hdr.n_eq;
+    out->n_fallback_wt = hdr.n_ovf_wt;
+    out->n_fallback_bsj = hdr.n_ovf_bsj;
     if (s->input_on_device && s->wt_read_len == 0 && s->n_pairs) {
         uint16_t l0 = 0;
         CG_CUDA(cudaMemcpy(&l0, s->d_lens.p, 2, cudaMemcpyDeviceToHost));

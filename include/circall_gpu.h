@@ -141,6 +141,7 @@ typedef struct {
     const uint32_t* rec_nhits; const uint8_t* rec_split;
     double device_ms;            /* kernels of this batch, CUDA events on the session's stream */
     double kernel_ms[4];         /* of which: read packing, wt collector, wt commit + export compaction, bsj collector + span filter */
+    uint64_t n_fallback_wt, n_fallback_bsj;   /* mates / records that needed the large-capacity general kernels */
 } cg_batch_result;
 
 /* scalar counters (ReadExperiment.hpp:265-270) for the two tools */

@@ -37,6 +37,7 @@ def _lib():
         L.emu_run_err.restype = i32
         L.emu_run_err.argtypes = [vp]
         L.emu_run_sizes.argtypes = [vp, vp]
+        L.emu_run_fallbacks.argtypes = [vp, vp]
         L.emu_run_fill.argtypes = [vp] * 12
         L.emu_stdsort.argtypes = [vp, i32]
         _LIB = L
@@ -93,6 +94,9 @@ def run(tx, bsj, r1, off1, r2, off2, lce_mode=0):
                    exp_pair=np.zeros(ne, np.uint64), exp_code=np.zeros(ne, np.uint8), junc=np.zeros((nj, 6), np.int64),
                    cand=np.zeros(nc, np.uint64), rec_nhits=np.zeros(ne, np.uint32), rec_split=np.zeros(ne, np.uint8),
                    eq_lens=np.zeros(nc, np.uint32), eq_tids=np.zeros(nt, np.uint32), ctr=np.zeros(8, np.uint64))
+        fb = np.zeros(2, np.uint64)
+        L.emu_run_fallbacks(h, fb.ctypes.data)
+        out["fallbacks"] = fb
         L.emu_run_fill(h, *[out[k].ctypes.data for k in ("mate_flags", "mate_nhits", "exp_pair", "exp_code", "junc",
                                                          "cand", "rec_nhits", "rec_split", "eq_lens", "eq_tids", "ctr")])
         return out

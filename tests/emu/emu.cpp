@@ -90,6 +90,7 @@ static bool pack_read(const char* s, int L, int W2f, int WMf, std::vector<uint64
 }
 
 static const int EMAXINT = 232, EMAXKS = 928;
+static const int EFI = 4, EFK = 16, EHC = 24;     // fast-path capacities, as in cg_session.cu
 
 // Same outputs as cg_collect.  Caller provides capacities; returns -1 on overflow, -4 on a bad base.
 int emu_collect(void* h, const char* bases, const uint64_t* off, uint64_t n_reads, int strict, int lceMode,
@@ -106,9 +107,8 @@ int emu_collect(void* h, const char* bases, const uint64_t* off, uint64_t n_read
         int W2f = (L + 31) / 32, WMf = (W2f + 1) / 2;
         if (W2f == 0) { W2f = 1; WMf = 1; }
         if (!pack_read(bases + off[r], L, W2f, WMf, pk)) { rcode = -4; break; }
-        strands.assign(2 * (W2f + 1 + WMf + 1), 0);
-        build_strands(pk.data(), 1, L, W2f, WMf, strands.data());
-        ReadView rv; rv.w = strands.data(); rv.stride = 1; rv.L = L; rv.W2 = W2f + 1; rv.WM = WMf + 1;
+        strands.assign(view_words(W2f, WMf), 0);
+        ReadView rv = build_view(pk.data(), 1, L, W2f, WMf, strands.data());
         bool f = collect_hits<EMAXINT, EMAXKS, true>(E->v, rv, strict != 0, lceMode, *sc);
         if (sc->st.err) { rcode = -6; break; }
         found[r] = f;
@@ -144,15 +144,15 @@ struct EmuRun {
     std::vector<uint32_t> recNHits; std::vector<uint8_t> recSplit;
     std::vector<uint32_t> eqLens, eqTids;     // one entry per candidate record
     uint64_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t fallbacks[2] = {0, 0};      // reads the fast path handed to the general path (wt mates, bsj records)
     int err = 0;
 };
 
 static bool view_of(const char* s, int L, std::vector<uint64_t>& pk, std::vector<uint64_t>& strands, ReadView& rv) {
     int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
     bool ok = pack_read(s, L, W2f, WMf, pk);
-    strands.assign(2 * (W2f + 1 + WMf + 1), 0);
-    build_strands(pk.data(), 1, L, W2f, WMf, strands.data());
-    rv.w = strands.data(); rv.stride = 1; rv.L = L; rv.W2 = W2f + 1; rv.WM = WMf + 1;
+    strands.assign(view_words(W2f, WMf), 0);
+    rv = build_view(pk.data(), 1, L, W2f, WMf, strands.data());
     return ok;
 }
 
@@ -162,6 +162,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
     EmuIndex* TX = (EmuIndex*)txh; EmuIndex* BS = (EmuIndex*)bsjh;
     auto* R = new EmuRun();
     auto* sc = new Scratch<EMAXINT, EMAXKS, false>();
+    auto* fs = new FastScratch<EFI, EFK, EHC>();
     std::vector<uint64_t> pk, strands;
     for (uint64_t i = 0; i < n; ++i) {
         int l1 = (int)(off1[i + 1] - off1[i]), l2 = (int)(off2[i + 1] - off2[i]);
@@ -169,7 +170,11 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
         for (int m = 0; m < 2; ++m) {
             ReadView rv;
             if (!view_of(m ? r2 + off2[i] : r1 + off1[i], m ? l2 : l1, pk, strands, rv)) R->err = -4;
-            wt_mate<EMAXINT, EMAXKS>(TX->v, rv, l1, lceMode, *sc, fl[m], nh[m]);
+            // same two-tier scheme as the kernels: small-capacity fast path, general path on overflow
+            if (!wt_mate_fast<EFI, EFK, EHC>(TX->v, rv, l1, lceMode, *fs, fl[m], nh[m])) {
+                ++R->fallbacks[0];
+                wt_mate<EMAXINT, EMAXKS>(TX->v, rv, l1, lceMode, *sc, fl[m], nh[m]);
+            }
             if (fl[m] & MATE_ERR) R->err = -6;
             R->mateFlags.push_back(fl[m] & 3);
         }
@@ -190,8 +195,13 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             ReadView rv;
             view_of(m ? r2 + off2[i] : r1 + off1[i], (int)(m ? off2[i + 1] - off2[i] : off1[i + 1] - off1[i]), pk, strands, rv);
             VecSink sink{&R->junc, rec};
-            uint32_t nh; bool split; uint8_t err;
-            bsj_record<EMAXINT, EMAXKS>(BS->v, rv, lceMode, *sc, sink, nh, split, tids, err);
+            uint32_t nh; bool split; uint8_t err = 0;
+            if (bsj_record_fast<EFI, EFK, EHC>(BS->v, rv, lceMode, *fs, sink, nh, split)) {
+                for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = fs->tid[t];
+            } else {
+                ++R->fallbacks[1];
+                bsj_record<EMAXINT, EMAXKS>(BS->v, rv, lceMode, *sc, sink, nh, split, tids, err);
+            }
             if (err) R->err = -6;
             R->recNHits.push_back(nh); R->recSplit.push_back(split);
             R->ctr[7] += nh > 0;
@@ -201,11 +211,12 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             R->ctr[5] += cand; R->ctr[6] += c; R->ctr[4] += 1;
         }
     }
-    delete sc;
+    delete sc; delete fs;
     return R;
 }
 void emu_run_free(void* r) { delete (EmuRun*)r; }
 int emu_run_err(void* r) { return ((EmuRun*)r)->err; }
+void emu_run_fallbacks(void* r, uint64_t* out) { out[0] = ((EmuRun*)r)->fallbacks[0]; out[1] = ((EmuRun*)r)->fallbacks[1]; }
 void emu_run_sizes(void* r, uint64_t* out) {
     EmuRun* R = (EmuRun*)r;
     out[0] = R->expPair.size(); out[1] = R->junc.size() / 6; out[2] = R->cand.size(); out[3] = R->eqTids.size();
@@ -224,6 +235,6 @@ void emu_run_fill(void* r, uint8_t* mateFlags, uint16_t* mateNHits, uint64_t* ex
 }
 
 // std::sort replica check: sorts packed kmerScores entries with cg::StdSort
-void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort(n); }
+void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort<true>(n); }
 
 } // extern "C"

@@ -105,6 +105,24 @@ def test_pipeline_ragged_and_edge_reads(gpu_world):
     _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, a, b)
 
 
+def test_pipeline_repeat_rich_world():
+    """Repeat families and antisense genes: SA intervals wider than a warp (and wider than maxInterval), both strands
+    surviving the vote, large hit lists (> 200 -> cleared) — the wide-interval branches of the warp kernels and the
+    hand-over to the general kernels."""
+    import circall_b200 as cg
+    import oracle
+    import synth
+    T = synth.Txome(5, 500, p_antisense=0.15, p_repeat=0.7, p_polya=0.05)
+    otx, obsj = oracle.Index.from_text(T.tx_text), oracle.Index.from_text(T.bsj_text)
+    gtx, gbsj = cg.Index.build(T.tx_text), cg.Index.build(T.bsj_text)
+    assert np.array_equal(gtx.suffix_array(), otx.sa)
+    r1, r2 = make_reads(T, 6, 30000, circ_frac=0.15)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2)
+    fl, nh = R.wt_mates()
+    assert (B.rec_nhits > 32).sum() > 50 and (B.rec_nhits > 200).sum() > 0      # wide hit lists were exercised
+    assert B.n_fallback_wt + B.n_fallback_bsj > 0                               # and so was the general path
+
+
 def test_pipeline_empty_batch(gpu_world):
     cg, T, otx, obsj, gtx, gbsj = gpu_world
     S = cg.Session(gtx, gbsj)
