@@ -89,7 +89,8 @@ struct IndexView {
     const u32x4* text;        // 2 x 16 B per 64-base block (+1 all-'$' pad block)
     const uint32_t* sa;
     const u32x4* hslots;      // {key_lo, key_hi, begin, end}; empty key = all ones
-    uint64_t hmask;           // capacity - 1
+    uint64_t hmask;           // capacity - 1 (capacity is a power of two, >= 4 x the number of k-mers)
+    int hshift;               // 64 - log2(capacity)
     const uint32_t* offsets;  // n_tx + 1 entries; offsets[n_tx] = n
     uint32_t n;               // text length (last character is '$')
     uint32_t n_tx;
@@ -306,7 +307,10 @@ CG_HD uint64_t hmix(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-CG_HD uint64_t home_slot(const IndexView& ix, uint64_t key) { return hmix(key) & ix.hmask; }
+// home slot of a k-mer: multiplicative hash (one 64-bit multiply), forced to the even slot of a 32-byte
+// sector so that the first two slots a look-up examines cost one memory sector
+CG_HD uint64_t home_of(uint64_t key, int hshift) { return ((key * 0x9E3779B97F4A7C15ULL) >> hshift) & ~1ULL; }
+CG_HD uint64_t home_slot(const IndexView& ix, uint64_t key) { return home_of(key, ix.hshift); }
 // finish a probe whose home slot `s` (at index h) has already been loaded
 CG_HD bool resolve(const IndexView& ix, uint64_t key, uint64_t h, u32x4 s, uint32_t& b, uint32_t& e) {
     for (;;) {

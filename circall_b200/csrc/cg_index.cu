@@ -126,14 +126,14 @@ __global__ void k_count_heads(const uint32_t* __restrict__ B, uint64_t nB, const
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(nk, (unsigned long long)__popc(m));
 }
 
-__global__ void k_insert(const uint32_t* __restrict__ B, uint64_t nB, const uint64_t* __restrict__ km, uint64_t n, uint4* slots, uint64_t hmask) {
+__global__ void k_insert(const uint32_t* __restrict__ B, uint64_t nB, const uint64_t* __restrict__ km, uint64_t n, uint4* slots, uint64_t hmask, int hshift) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= nB) return;
     uint32_t j = B[i];
     uint64_t key = km[j];
     if (key == ~0ULL) return;
     uint32_t e = (i + 1 < nB) ? B[i + 1] : (uint32_t)n;
-    uint64_t h = hmix(key) & hmask;
+    uint64_t h = home_of(key, hshift);
     for (;;) {
         unsigned long long* kp = (unsigned long long*)&slots[h];
         unsigned long long old = atomicCAS(kp, ~0ULL, (unsigned long long)key);
@@ -217,12 +217,14 @@ int build_khash(cg_index* idx) {
     CG_CUDA(cudaGetLastError());
     unsigned long long nk = 0;
     CG_CUDA(cudaMemcpy(&nk, cnt.p, 8, cudaMemcpyDeviceToHost));
+    // load factor <= 0.25: unsuccessful look-ups (the bulk of the mapper's probes) stop after ~1.3 slots
     uint64_t cap = 16;
-    while (cap < nk * 2 + 2) cap <<= 1;
+    int hshift = 60;
+    while (cap < nk * 4 + 2) { cap <<= 1; --hshift; }
     bnd.alloc(0); tmp.alloc(0);
     CG_CUDA(cudaMalloc((void**)&idx->d_hslots, cap * 16));
     CG_CUDA(cudaMemset(idx->d_hslots, 0xFF, cap * 16));
-    if (nB) k_insert<<<grid_for(nB, BS), BS>>>(B.as<uint32_t>(), nB, km.as<uint64_t>(), n, idx->d_hslots, cap - 1);
+    if (nB) k_insert<<<grid_for(nB, BS), BS>>>(B.as<uint32_t>(), nB, km.as<uint64_t>(), n, idx->d_hslots, cap - 1, hshift);
     CG_CUDA(cudaGetLastError());
     CG_CUDA(cudaDeviceSynchronize());
     idx->hcap = cap; idx->n_kmers = nk;

@@ -60,7 +60,7 @@ struct Hit { uint32_t b, e; bool found; };
 template <int X>
 __device__ __noinline__ Hit w_probe(uint64_t key, bool active) {
     const IndexView& ix = c_ix[X];
-    uint64_t h = hmix(key) & ix.hmask;
+    uint64_t h = home_slot(ix, key);
     Hit r; r.b = r.e = 0; r.found = false;
     bool pend = active;
     while (__any_sync(FULL, pend)) {
@@ -186,6 +186,20 @@ __device__ __noinline__ Look w_look(RV r, int lane, int s, int o, int lim, uint3
     const int sh = both ? 1 : 0;
     const int np = once ? 1 : (32 >> sh);
     Look R; R.pos = -1; R.jl = 0; R.fb = 0; R.b = R.e = 0; R.o_end = o;
+    if (once && !r.anyN && o <= lim) {
+        // the common single probe: no N anywhere in the read, so only the homopolymer rule can intervene
+        uint64_t mer = w_chunk(r, s, o) & KM;
+        if (!homopolymer(mer, k)) {
+            Hit h = w_probe<X>((both && (lane & 1)) ? revcomp(mer, k) : mer, lane < (both ? 2 : 1));
+            unsigned fb = __ballot_sync(FULL, h.found);
+            if (both && either ? (fb & 3u) : (fb & 1u)) {
+                R.jl = 0; R.pos = o; R.fb = fb; R.b = h.b; R.e = h.e;
+                return R;
+            }
+            R.o_end = o + 1;
+            return R;
+        }
+    }
     for (;;) {
         if (o > lim) { R.o_end = o; return R; }
         int j = lane >> sh;

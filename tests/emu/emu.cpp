@@ -50,7 +50,7 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
     }
     E->sa.assign(sa, sa + n);
     E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
-    E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0;
+    E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0; E->v.hshift = 0;
     // k-mer table: heads of runs of equal valid k-mers in SA order
     std::vector<uint64_t> keys; std::vector<uint32_t> begins, endsI;
     bool have = false; uint64_t prev = 0;
@@ -61,14 +61,14 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
         if (v && !same) { keys.push_back(w); begins.push_back((uint32_t)j); have = true; }
         if (v) prev = w;
     }
-    uint64_t cap = 16; while (cap < keys.size() * 2 + 2) cap <<= 1;
+    uint64_t cap = 16; int hshift = 60; while (cap < keys.size() * 4 + 2) { cap <<= 1; --hshift; }
     E->hslots.assign(cap, u32x4{0xffffffffu, 0xffffffffu, 0, 0});
     for (size_t i = 0; i < keys.size(); ++i) {
-        uint64_t h = hmix(keys[i]) & (cap - 1);
+        uint64_t h = home_of(keys[i], hshift);
         while (!(E->hslots[h].x == 0xffffffffu && E->hslots[h].y == 0xffffffffu)) h = (h + 1) & (cap - 1);
         E->hslots[h] = u32x4{(uint32_t)keys[i], (uint32_t)(keys[i] >> 32), begins[i], endsI[i]};
     }
-    E->v.hslots = E->hslots.data(); E->v.hmask = cap - 1; E->n_kmers = keys.size();
+    E->v.hslots = E->hslots.data(); E->v.hmask = cap - 1; E->v.hshift = hshift; E->n_kmers = keys.size();
     return E;
 }
 void emu_index_free(void* h) { delete (EmuIndex*)h; }
