@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcircall_gpu.so")
+LIB_PATH = os.environ.get("CG_LIB_PATH") or os.path.join(_HERE, "libcircall_gpu.so")   # CG_LIB_PATH: tuning builds
 _LIB = None
 
 CG_MAX_READ_LEN = 256

@@ -19,15 +19,18 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """tag/defines: tuning variants (libcircall_gpu<tag>.so built with -D<define>), picked up through CG_LIB_PATH"""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    SO = os.path.join(HERE, "libcircall_gpu%s.so" % tag)
+    NVCC_FLAGS = globals()["NVCC_FLAGS"] + ["-D" + d for d in defines]
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        o = os.path.join(HERE, "build", src.replace(".cu", tag + ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             log = open(o + ".log", "w")
@@ -45,4 +48,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a[6:] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs, tag=tag))
