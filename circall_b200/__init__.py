@@ -61,7 +61,8 @@ class _BatchResult(ctypes.Structure):
                 ("mate_flags", ctypes.c_void_p), ("mate_nhits", ctypes.c_void_p),
                 ("rec_nhits", ctypes.c_void_p), ("rec_split", ctypes.c_void_p),
                 ("device_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 4),
-                ("n_fallback_wt", ctypes.c_uint64), ("n_fallback_bsj", ctypes.c_uint64)]
+                ("n_fallback_wt", ctypes.c_uint64), ("n_fallback_bsj", ctypes.c_uint64),
+                ("n_tier2_wt", ctypes.c_uint64), ("n_tier2_bsj", ctypes.c_uint64)]
 
 
 class _Counters(ctypes.Structure):
@@ -274,6 +275,7 @@ class BatchResult:
         self.device_ms = r.device_ms
         self.kernel_ms = tuple(r.kernel_ms)      # pack, wt, commit+compaction, bsj
         self.n_fallback_wt, self.n_fallback_bsj = r.n_fallback_wt, r.n_fallback_bsj
+        self.n_tier2_wt, self.n_tier2_bsj = r.n_tier2_wt, r.n_tier2_bsj
         if not want_lists:
             return
         self.exp_pair = _view(r.exp_pair, np.uint32, r.n_export)

@@ -10,8 +10,10 @@
 // Nothing here falls back to the host: without a CUDA device session creation fails.
 #include "cg_kernels.cuh"
 #include "cg_warp.cuh"
+#include "cg_tsm.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 using namespace cg;
 using namespace cgk;
@@ -32,6 +34,8 @@ struct BatchHdr {
     int status;
     uint32_t n_ovf_wt;             // mates / records the fast path handed to the general kernels
     uint32_t n_ovf_bsj;
+    uint32_t n_t2_wt;              // mates / records the thread state machine handed to the warp kernels
+    uint32_t n_t2_bsj;
 };
 
 // ---- warp-per-read kernels --------------------------------------------------------------------------
@@ -93,7 +97,7 @@ __device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) 
 // K2-K6: one warp per mate (persistent warps, grid-stride).
 //   GEN = false: over all n mates, state in shared memory; ovf[r] = 1 hands the mate to the general kernel
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
-template <bool GEN>
+template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
@@ -104,9 +108,9 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_BLOCK, warp = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
     GenPtrs gp;
     if (GEN) gp = gen_ptrs(gscratch, warp);
-    const uint64_t n = GEN ? (uint64_t)*n_list : n_reads;
+    const uint64_t n = LIST ? (uint64_t)*n_list : n_reads;
     for (uint64_t x = warp; x < n; x += nwarps) {
-        const uint64_t r = GEN ? (uint64_t)list[x] : x;
+        const uint64_t r = LIST ? (uint64_t)list[x] : x;
         int L = lens[r];
         int pairLen = lens[r & ~1ULL];             // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
         cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
@@ -274,7 +278,7 @@ struct BsjOut {
 //                fast capacity is flagged in ovf[] and emits nothing here
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
 // do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes.
-template <bool GEN>
+template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
            const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
@@ -286,10 +290,10 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
     const IndexView& ix = cgw::c_ix[1];
     GenPtrs gp;
     if (GEN) gp = gen_ptrs(gscratch, warp);
-    const uint64_t n = GEN ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
+    const uint64_t n = LIST ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;          // per-warp totals (kept by every lane alike)
     for (uint64_t x = warp; x < n; x += nwarps) {
-        const uint64_t rec = GEN ? (uint64_t)list[x] : x;
+        const uint64_t rec = LIST ? (uint64_t)list[x] : x;
         const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
         int L = lens[r];
         cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
@@ -404,6 +408,121 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
     }
 }
 
+// ---- first tier: thread-per-read state machine (cg_tsm.cuh) -------------------------------------------------
+static const int TSM_THREADS = 128;
+#ifndef CG_TSM_MINB
+#define CG_TSM_MINB 4
+#endif
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// One thread per mate (BSJ = false: K2-K6 of Circall_wt) or per exported record (BSJ = true: K2-K5, K7, K8 of
+// Circall_bsj); persistent threads, grid-stride.  Every lane cycles through: fetch the packed read into its
+// scratch (cp.async, in flight for one round), run cgt::tsm_step() until the read is done or bails, commit.
+// A read that bails (or holds an N) is flagged in ovf[] and emits nothing here; the warp kernels redo it.
+template <bool BSJ>
+__global__ void __launch_bounds__(TSM_THREADS, CG_TSM_MINB)
+k_tsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_fixed,
+      const uint32_t* __restrict__ exp_mate, int lceMode,
+      uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,      // wt outputs
+      BsjOut o, int do_counts,                                       // bsj outputs
+      uint8_t* __restrict__ ovf, int zero) {
+    extern __shared__ uint32_t tsm_smem[];
+    cgt::TMem m; m.base = tsm_smem + threadIdx.x; m.stride = TSM_THREADS; m.W2 = g.W2f + 1;
+    const IndexView& ix = cgw::c_ix[BSJ ? 1 : 0];
+    const uint64_t nthreads = (uint64_t)gridDim.x * TSM_THREADS;
+    const uint64_t n = BSJ ? (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed) : n_fixed;
+    uint64_t x = (uint64_t)blockIdx.x * TSM_THREADS + threadIdx.x;
+    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
+    cgt::Ctx c; c.pc = cgt::PC_DONE; c.zero = zero;
+    JSink sink; sink.buf = nullptr; sink.cursor = nullptr; sink.cap = 0; sink.rec = 0;
+    if (BSJ) { sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; }
+    int st = 0;                                   // 0: needs a read, 1: fetch in flight, 2: running
+    uint64_t r = 0;
+    uint32_t r_next = 0;                          // BSJ: exp_mate[] of the record after this one, loaded a read ahead
+    if (BSJ && exp_mate && x < n) r_next = __ldg(exp_mate + x);
+    // every lane stays in the loop until the whole warp is out of reads: the vote at the top and the ballot before
+    // the step are meeting points of the full warp (a lane that is done idles through them)
+    bool alive = true;
+    while (__any_sync(0xffffffffu, alive)) {
+        if (alive && st == 1) {
+            cp_async_wait_all();
+            const int L = c.L;
+            bool anyN = false;                    // mask words were staged in the reverse-complement area
+            for (int j = 0; j < g.WMf; ++j) {
+                int lo = 64 * j;
+                if (lo >= L) break;
+                uint64_t mk = (uint64_t)m.ld(2 * m.W2 + 2 * j) | ((uint64_t)m.ld(2 * m.W2 + 2 * j + 1) << 32);
+                if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+                anyN |= mk != 0;
+            }
+            if (anyN || L < 1) { ovf[x] = 1; st = 0; x += nthreads; }
+            else {
+                m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
+                cgt::tsm_make_rc(m, L);
+                c.pc = cgt::PC_START; c.req = cgt::RQ_NONE; st = 2;
+            }
+        }
+        // one round of the state machine, its three phases separated by meeting points of the whole warp (top level
+        // of the loop body: every lane gets there, whatever it is doing)
+        const bool stepping = alive && st == 2;
+        bool ctl = false;
+        if (stepping) ctl = cgt::tsm_complete(c, ix, m, lceMode);
+        __syncwarp();
+        if (ctl) cgt::tsm_control<BSJ>(c, ix, m, sink);
+        __syncwarp();
+        if (stepping) {
+            cgt::tsm_issue(c, ix, m);
+            if (c.pc == cgt::PC_DONE) {
+                if (!BSJ) { flags[r] = c.flags; nhits[r] = c.nh; }
+                else {
+                    // commit (Circall_bsj.cpp:383-491)
+                    o.rec_nhits[x] = c.nh; o.rec_split[x] = c.split ? 1 : 0;
+                    upper += c.nh > 0;                                                    // :383
+                    const uint32_t cc = c.nh > (uint32_t)MAX_READ_OCCS ? 0 : c.nh;        // :385
+                    const bool cand = cc > 0 && c.split;                                  // :390
+                    obs += 1; mapped += cand; hits += cc;                                 // :488-491
+                    if (cand) {
+                        if (cc == 1) { if (do_counts & 1) atomicAdd(&o.per_bsj[m.ld(m.cb())], 1ULL); }   // EquivalenceClassBuilder.hpp:112-130
+                        else if (do_counts & 2) {
+                            unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL), sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)cc);
+                            if (e < o.eq_cap && sidx + cc <= o.eq_tids_cap) {
+                                o.eq_ent[e] = make_uint4((uint32_t)x, (uint32_t)sidx, cc, 0u);
+                                for (uint32_t t = 0; t < cc; ++t) o.eq_tids[sidx + t] = m.ld(m.cb() + t);
+                            }
+                        }
+                    }
+                }
+                st = 0; x += nthreads;
+            } else if (c.pc == cgt::PC_BAIL) { ovf[x] = 1; st = 0; x += nthreads; }
+        }
+        if (alive && st == 0) {
+            if (x >= n) { alive = false; continue; }
+            r = BSJ ? (exp_mate ? (uint64_t)r_next : 2 * x) : x;
+            if (BSJ && exp_mate && x + nthreads < n) r_next = __ldg(exp_mate + x + nthreads);
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(pk + r * (uint64_t)g.WT);
+            for (int j = 0; j < 2 * g.W2f; ++j) cp_async4(m.base + (size_t)j * TSM_THREADS, rec + j);
+            for (int j = 0; j < 2 * g.WMf; ++j) cp_async4(m.base + (size_t)(2 * m.W2 + j) * TSM_THREADS, rec + 2 * g.W2f + j);
+            cp_async_commit();
+            c.L = lens[r]; c.pairLen = BSJ ? c.L : lens[r & ~1ULL];    // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+            sink.rec = (uint32_t)x;
+            st = 1;
+        }
+    }
+    if (BSJ && (do_counts & 1)) {
+        __shared__ uint32_t sh[TSM_THREADS / 32];
+        uint32_t t;
+        t = block_sum(obs, sh);    if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)t);
+        t = block_sum(mapped, sh); if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)t);
+        t = block_sum(hits, sh);   if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)t);
+        t = block_sum(upper, sh);  if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)t);
+    }
+}
+
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 } // namespace
@@ -418,6 +537,8 @@ struct cg_session {
     uint64_t launches = 0;
     int warp_grid_wt = 0, warp_grid_bsj = 0;     // persistent grids of the warp-per-read kernels (SMs x resident blocks)
     int gen_grid = 0;                            // grid of the general kernels (sized with the per-warp global scratch)
+    int sms = 0;
+    bool use_tsm = false;                        // first tier = thread state machine (CG_TSM=1 switches it on; experimental: parity-green, not yet faster)
     unsigned char* d_gscratch = nullptr;
     bool pending = false;
     // batch state
@@ -429,7 +550,7 @@ struct cg_session {
     const uint64_t* in_off1 = nullptr; const uint64_t* in_off2 = nullptr;
     // device buffers
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
-        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list;
+        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2;
     unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
@@ -467,6 +588,18 @@ int compact_flags(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, ui
 }
 
 
+// launch the thread state machine over n_fixed mates (wt) / the exported records (bsj); persistent grid
+template <bool BSJ>
+int launch_tsm(cg_session* s, uint64_t n_fixed, const uint32_t* em, const BsjOut& o, int do_counts) {
+    const size_t smem = (size_t)cgt::TMem::words(s->geom.W2f + 1) * 4 * TSM_THREADS;
+    if (smem > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(k_tsm<BSJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tsm<BSJ>, TSM_THREADS, smem));
+    if (nb < 1) nb = 1;
+    return launch(s, k_tsm<BSJ>, dim3(s->sms * nb), dim3(TSM_THREADS), smem, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, n_fixed, em,
+                  s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), o, do_counts, s->d_ovf.as<uint8_t>(), 0);
+}
+
 int run_bsj_stage(cg_session* s, int do_counts) {
     const uint64_t n_reads = 2 * s->n_pairs;
     const bool stage2 = s->opts.stage == 2;
@@ -484,14 +617,31 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, worst, s->stream));
     CG_CUDA(cudaMemcpyToSymbolAsync(cgw::c_ix, &v, sizeof(IndexView), sizeof(IndexView), cudaMemcpyHostToDevice, s->stream));
     const dim3 blk(WARPS_PER_BLOCK * 32);
-    int rc = launch(s, k_bsj_warp<false>, dim3(s->warp_grid_bsj), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, false, true),
+    const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, false, true), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, true, true);
+    int rc;
+    const uint8_t* ovf_fast = s->d_ovf.as<uint8_t>();
+    if (s->use_tsm) {
+        // tier 1: thread state machine; tier 2: the fast warp kernel over what it handed on
+        rc = launch_tsm<true>(s, s->n_pairs, em, o, do_counts);
+        if (rc) return rc;
+        rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
+        if (rc) return rc;
+        CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, worst, s->stream));
+        rc = launch(s, k_bsj_warp<false, true>, dim3(s->warp_grid_bsj), blk, smf,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj,
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+        if (rc) return rc;
+        ovf_fast = s->d_ovf2.as<uint8_t>();
+    } else {
+        rc = launch(s, k_bsj_warp<false, false>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
                     s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
+        if (rc) return rc;
+    }
+    rc = compact_flags(s, ovf_fast, worst, s->d_list2.as<uint32_t>(), &dh->n_ovf_bsj);
     if (rc) return rc;
-    rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_ovf_bsj);
-    if (rc) return rc;
-    return launch(s, k_bsj_warp<true>, dim3(s->gen_grid), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, true, true),
-                  s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(),
+    return launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
+                  s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list2.as<uint32_t>(),
                   (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch);
 }
 
@@ -509,6 +659,8 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_bc.reserve((n_reads / CP_TILE + 2) * 4));
     CG_CUDA(s->d_ovf.reserve(n_reads + 16));
     CG_CUDA(s->d_list.reserve(n_reads * 4 + 16));
+    CG_CUDA(s->d_ovf2.reserve(n_reads + 16));
+    CG_CUDA(s->d_list2.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
@@ -534,14 +686,32 @@ int run_batch(cg_session* s) {
         BatchHdr* dh = s->d_hdr.as<BatchHdr>();
         CG_CUDA(cudaMemcpyToSymbolAsync(cgw::c_ix, &v, sizeof(IndexView), 0, cudaMemcpyHostToDevice, s->stream));
         const dim3 blk(WARPS_PER_BLOCK * 32);
-        rc = launch(s, k_wt_warp<false>, dim3(s->warp_grid_wt), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false),
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
-                    s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
+        const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false);
+        const uint8_t* ovf_fast = s->d_ovf.as<uint8_t>();
+        if (s->use_tsm) {
+            // tier 1: thread state machine; tier 2: the fast warp kernel over what it handed on
+            BsjOut none; memset(&none, 0, sizeof none);
+            CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, n_reads, s->stream));
+            rc = launch_tsm<false>(s, n_reads, (const uint32_t*)nullptr, none, 0);
+            if (rc) return rc;
+            rc = compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt);
+            if (rc) return rc;
+            CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, n_reads, s->stream));
+            rc = launch(s, k_wt_warp<false, true>, dim3(s->warp_grid_wt), blk, smf,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_wt, s->opts.lce_mode,
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+            if (rc) return rc;
+            ovf_fast = s->d_ovf2.as<uint8_t>();
+        } else {
+            rc = launch(s, k_wt_warp<false, false>, dim3(s->warp_grid_wt), blk, smf,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
+            if (rc) return rc;
+        }
+        rc = compact_flags(s, ovf_fast, n_reads, s->d_list2.as<uint32_t>(), &dh->n_ovf_wt);
         if (rc) return rc;
-        rc = compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_ovf_wt);
-        if (rc) return rc;
-        rc = launch(s, k_wt_warp<true>, dim3(s->gen_grid), blk, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false),
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_ovf_wt,
+        rc = launch(s, k_wt_warp<true, true>, dim3(s->gen_grid), blk, smg,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list2.as<uint32_t>(), (const uint32_t*)&dh->n_ovf_wt,
                     s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch);
         if (rc) return rc;
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
@@ -607,8 +777,9 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         int sms = 0, bw = 0, bb = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         PackGeom g = PackGeom::make(160);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bw, k_wt_warp<false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false));
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bw, k_wt_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
+        s->sms = sms; s->use_tsm = getenv("CG_TSM") != nullptr && atoi(getenv("CG_TSM")) != 0;
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
         s->gen_grid = sms * 2;
@@ -625,7 +796,7 @@ void cg_session_destroy(cg_session* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
-                       &s->d_ovf, &s->d_list})
+                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2})
         b->release();
     s->h_hdr.release();
     if (s->d_acc) cudaFree(s->d_acc);
@@ -719,6 +890,8 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     out->n_eq = hdr.n_eq;
     out->n_fallback_wt = hdr.n_ovf_wt;
     out->n_fallback_bsj = hdr.n_ovf_bsj;
+    out->n_tier2_wt = hdr.n_t2_wt;
+    out->n_tier2_bsj = hdr.n_t2_bsj;
     if (s->input_on_device && s->wt_read_len == 0 && s->n_pairs) {
         uint16_t l0 = 0;
         CG_CUDA(cudaMemcpy(&l0, s->d_lens.p, 2, cudaMemcpyDeviceToHost));

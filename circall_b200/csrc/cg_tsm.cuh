@@ -1,0 +1,624 @@
+// circall_b200 — thread-per-read state machine ("TSM"): the first tier of k_wt / k_bsj.
+//
+// One THREAD maps one read.  The per-read algorithm — include/SACollectorCircall.hpp:24-582 as restated by
+// cg::collect(), then the hit enumeration of :492-579 and, for Circall_bsj, the span filter of
+// src/Circall_bsj.cpp:323-374 — is split into
+//   * CONTROL: the reference's own sequential logic, written as a resumable routine (a protothread:
+//     `switch (pc)` with resume labels inside its loops).  It never touches global memory; whenever it needs the
+//     index it files a request with one of four ENGINES and suspends.
+//   * ENGINES (table look-ups, extendSearchNaive, lce, SA position -> transcript): each is a short chain of
+//     "issue loads into the context's registers" / "consume them one scheduling round later" steps.
+// One call of tsm_step() = complete what was in flight, run the control code up to its next request, issue
+// that request's loads.  The kernel's main loop calls it for the 32 lanes of a warp over and over.  All lanes
+// go through the engine code together (it is the heavy part: hashing, 2-bit comparisons) whatever control
+// state they are in, the control code in between is a few instructions, and every lane keeps its own loads in
+// flight across the call — 32+ independent HBM requests per warp instead of the one or two of the
+// warp-per-read kernels, whose 32 lanes mostly repeat scalar work.
+//
+// Scope: the common paths only.  Anything unusual makes the routine BAIL — nothing is emitted and the read is
+// redone from scratch by the warp-per-read kernels, whose results are identical:
+//   * an N in the read, a homopolymer k-mer window
+//   * both strands holding hits at the vote (the kmerScores vote, :442-490, stays with the warp kernels)
+//   * more than T_FI intervals on a strand, an open interval wider than T_WMAX in the extension,
+//     more than T_HC hit candidates, an interval wider than T_OTHER in the intersection / the span filter
+//
+// Exact shortcut used by the hit enumeration (this tier and only this tier): an interval whose query range
+// [qpos, qpos + len) lies inside the query range of a longer interval of the same strand cannot change the
+// set of hit transcripts — every occurrence p of the longer match gives the occurrence p + (qpos' - qpos) of
+// the shorter one in the same transcript, so tids(longer) is a subset of tids(shorter) and, the map being
+// injective, span(longer) <= span(shorter).  intersectSAHits computes the intersection of the tid sets of all
+// intervals, which therefore equals the intersection over the maximal ones; the others are never enumerated.
+//
+// CG_HD throughout: tests/emu steps the same code on the host against the oracle.
+#pragma once
+#include "cg_pipeline.cuh"
+
+namespace cgt {
+using namespace cg;
+
+static const int T_FI = 8;        // intervals kept per strand
+static const int T_HC = 16;       // hit candidates (positions of the narrowest maximal interval)
+static const int T_WMAX = 32;     // widest open interval the extension resolves candidate by candidate
+static const int T_OTHER = 64;    // widest interval walked by the intersection / the span filter
+
+#if defined(__CUDACC__) && !defined(CG_HOST_EMU)
+typedef uint2 u32x2;
+#else
+struct u32x2 { uint32_t x, y; };
+#endif
+
+CG_HD uint32_t fsr(uint32_t lo, uint32_t hi, int sh) {      // funnel shift right, sh in 0..31
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// Per-thread scratch of 32-bit words, word j at base[j * stride] (stride = threads per block on the device, so
+// that the lanes of a warp touching the same word index hit 32 different banks; 1 on the host).
+//   [0, 2 W2)        forward code words, 16 bases each (W2 = 64-bit words incl. one zero pad word)
+//   [2 W2, 4 W2)     reverse-complement strand, same layout
+//   [4 W2, +6 T_FI)  intervals: forward i at 3 i, reverse-complement i at 3 (T_FI + i): begin, end, len | qpos << 16
+//   then T_HC        hit candidates (transcript ids)
+struct TMem {
+    uint32_t* base; int stride; int W2;
+    CG_HD uint32_t ld(int j) const { return base[(size_t)j * stride]; }
+    CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
+    CG_HD int iv(int s, int i) const { return 4 * W2 + 3 * (s * T_FI + i); }
+    CG_HD int cb() const { return 4 * W2 + 6 * T_FI; }
+    CG_HD static int words(int W2) { return 4 * W2 + 6 * T_FI + T_HC; }
+    // 32-base window of strand s at oriented position i (i < L)
+    CG_HD uint64_t chunk(int s, int i) const {
+        int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
+        uint32_t a = ld(p), b = ld(p + 1), c = ld(p + 2);
+        return (uint64_t)fsr(a, b, sh) | ((uint64_t)fsr(b, c, sh) << 32);
+    }
+};
+
+enum { BAIL_N = 1, BAIL_HOMO, BAIL_VOTE, BAIL_NINT, BAIL_WIDE_EXT, BAIL_NCAND, BAIL_WIDE_OTHER, BAIL_NUM };
+
+// control resume points
+enum {
+    PC_START = 0, PC_DONE = -1, PC_BAIL = -2,
+    PC_A_PROBED = 1, PC_A_EXT, PC_B_LCE0, PC_B_PROBED, PC_B_RUN, PC_B_RC, PC_B_EXT, PC_B_LCE, PC_H_TID, PC_O_TID, PC_J_TID
+};
+// engine states: RQ_x = requested by the control code (loads not issued yet), RQ_x_y = loads y in flight
+enum {
+    RQ_NONE = 0,
+    RQ_PROBE, RQ_PROBE_W,                   // table look-ups
+    RQ_EXT, RQ_EXT_SA, RQ_EXT_BLK,          // extendSearchNaive, candidate by candidate
+    RQ_LCE, RQ_LCE_SA, RQ_LCE_BLK,          // SASearcher::lce
+    RQ_TID, RQ_TID_SA, RQ_TID_BLK, RQ_TID_OFF   // up to four SA positions -> transcript ids (-> transcript bounds)
+};
+// look-up patterns
+enum { PM_PAIR1 = 0,    // k-mer at pos and its reverse complement
+       PM_PAIR2,        // the same for pos and pos + 1
+       PM_RUN,          // the k-mers at pos .. pos + 3 (those that fit the read)
+       PM_RC1 };        // the reverse complement of the k-mer at pos
+
+struct Ctx {
+    int pc, req;
+    // the read
+    int L, pairLen;
+    // collector (names as in cg::collect / SACollectorCircall.hpp)
+    int pos, s, nF, nR, matched, q0, prevO;
+    uint32_t fwdHit, rcHit, lbF, ubF, pB, pE, ivB, ivE;
+    bool found, lastSearch, expectAbsent, pOther, other, hasF, hasR, a_two;
+    // look-up engine: request (strand p_s, position p_pos, pattern p_mode, limit p_lim = last position allowed);
+    // in flight: one slot per key.  The same registers carry the other engines' loads:
+    //   s0 / s1 = code halves of text blocks A / B, s2 = their '$' masks (x,y: A; z,w: B)      (extension, lce)
+    //   s0..s3  = second halves of four text blocks, then s0 / s1 = transcript bounds          (SA position -> tid)
+    int p_s, p_pos, p_mode, p_lim;
+    uint64_t key0, key1, key2, key3;
+    uint32_t h0, h1, h2, h3, pend, fnd;
+    u32x4 s0, s1, s2, s3;
+    // extension engine
+    int x_s, x_q, x_i, x_best, x_m, x_len;
+    uint32_t x_lbIn, x_ubIn, x_ci, x_w, x_first, x_last, x_sa, x_p, x_lb, x_ub, x_b0, x_b1;
+    bool x_two;
+    // lce engine
+    uint32_t l_o1, l_o2; int l_len, l_lim, l_res;
+    // SA position -> transcript engine: positions e_c .. min(e_c + 4, e_end); out: sa0..3 (text positions), tid0..3
+    uint32_t e_c, e_end, sa0, sa1, sa2, sa3, tid0, tid1, tid2, tid3;
+    bool e_off;                            // also fetch offsets[tid], offsets[tid + 1] (into s0 / s1)
+    // hit enumeration
+    uint32_t keep, alive, seen, e_n;
+    int e_x, e_mi, nc;
+    // results
+    uint32_t nh; uint8_t flags; bool split;
+    int why;                               // BAIL_* when pc == PC_BAIL
+    int zero;                              // always 0, but only known at run time (see T_REQ)
+};
+
+CG_HD uint64_t slot_key(const u32x4& s) { return (uint64_t)s.x | ((uint64_t)s.y << 32); }
+CG_HD uint32_t tid_from(const u32x4& t, uint32_t p) {
+    uint64_t mask = (uint64_t)t.x | ((uint64_t)t.y << 32);
+    uint32_t o = p & 63;
+    return t.z + (uint32_t)popc64(o ? (mask & ((1ULL << o) - 1)) : 0ULL);
+}
+CG_HD const u32x2* mask_ptr(const IndexView& ix, uint32_t b) { return reinterpret_cast<const u32x2*>(&ix.text[2 * (uint64_t)b + 1]); }
+
+// ---- engine pieces -------------------------------------------------------------------------------------------
+// text blocks for the extension: the block that holds text position p + i and, when the compared range reaches
+// into it, the next one
+CG_HD void ext_issue_blocks(Ctx& c, const IndexView& ix) {
+    uint32_t tp = c.x_p + (uint32_t)c.x_i;
+    c.x_b0 = tp >> 6;
+    c.x_two = (int)(tp & 63) + (c.x_m - c.x_i) > 64;
+    c.s0 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0]);
+    u32x2 ma = CG_LDG(mask_ptr(ix, c.x_b0));
+    c.s2.x = ma.x; c.s2.y = ma.y;
+    if (c.x_two) {
+        c.s1 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0 + 2]);
+        u32x2 mb = CG_LDG(mask_ptr(ix, c.x_b0 + 1));
+        c.s2.z = mb.x; c.s2.w = mb.y;
+    }
+}
+CG_HD uint64_t half_codes(const u32x4& b, int half) { return half ? ((uint64_t)b.z | ((uint64_t)b.w << 32)) : ((uint64_t)b.x | ((uint64_t)b.y << 32)); }
+// next candidate of the extension: its SA entry is in x_sa; fetch the following one alongside its text blocks
+CG_HD void ext_next_candidate(Ctx& c, const IndexView& ix, int k) {
+    c.x_p = c.x_sa;
+    if (c.x_ci + 1 < c.x_w) c.x_sa = CG_LDG(&ix.sa[c.x_lbIn + 2 + c.x_ci]);
+    c.x_i = k;
+    ext_issue_blocks(c, ix);
+}
+CG_HD void lce_issue_blocks(Ctx& c, const IndexView& ix) {
+    c.x_b0 = (c.l_o1 + (uint32_t)c.l_len) >> 6; c.x_b1 = (c.l_o2 + (uint32_t)c.l_len) >> 6;
+    c.s0 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0]);
+    u32x2 ma = CG_LDG(mask_ptr(ix, c.x_b0));
+    c.s2.x = ma.x; c.s2.y = ma.y;
+    if (c.x_b1 != c.x_b0) {
+        c.s1 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b1]);
+        u32x2 mb = CG_LDG(mask_ptr(ix, c.x_b1));
+        c.s2.z = mb.x; c.s2.w = mb.y;
+    }
+}
+
+// The request is filed as `constant ^ run-time zero` so that the three phases stay separate pieces of code whatever
+// the compiler inlines: the kernel puts a full-warp meeting point between them (see k_tsm), because no reconvergence
+// barrier is placed around a switch that jumps into loops, and without one every control state would run the heavy
+// engine code by itself.
+#define T_REQ(rq, label) do { c.req = (rq) ^ c.zero; c.pc = (label); return; case (label):; } while (0)
+#define T_BAIL(why_) do { c.pc = PC_BAIL; c.why = (why_); c.req = c.zero; return; } while (0)
+#define T_DONE() do { c.pc = PC_DONE; c.req = c.zero; return; } while (0)
+// extendSearchNaive(x_lbIn, x_ubIn) of strand x_s at query position x_q, startAt = k: out x_lb, x_ub, x_len
+#define T_EXT(label) do { \
+        c.x_m = L - c.x_q; c.x_w = c.x_ubIn - c.x_lbIn - 1; \
+        if (c.x_m <= k) { c.x_lb = c.x_lbIn + 1; c.x_ub = c.x_ubIn; c.x_len = k; } \
+        else if (c.x_w == 0) { c.x_lb = c.x_ubIn; c.x_ub = c.x_ubIn; c.x_len = k; }      /* empty open interval */ \
+        else { if (c.x_w > (uint32_t)T_WMAX) T_BAIL(BAIL_WIDE_EXT); T_REQ(RQ_EXT, label); } \
+    } while (0)
+// lce(SA index l_o1, SA index l_o2, startAt l_len, stopAt l_lim): out l_res
+#define T_LCE(label) do { if (c.l_lim <= c.l_len) c.l_res = c.l_len; else T_REQ(RQ_LCE, label); } while (0)
+
+// One scheduling round of a read = tsm_complete() (consume the loads that were in flight; true when the control code
+// may run), tsm_control() (the reference's logic up to its next request) and tsm_issue() (that request's loads).
+// Sink::line(dir, queryPos, len, hitPos, tid) receives the junction-table rows (BSJ only).  On PC_DONE: c.flags / c.nh
+// (wt), c.nh / c.split and, for BSJ, the hit transcripts in ascending order in the candidate words of `m`.
+CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode) {
+    const int k = ix.k;
+    // ================= complete what was in flight =================
+    bool ctl = true;                                    // false: this lane's engine needs another round
+    if (c.req == RQ_PROBE_W) {
+#define T_RESOLVE(bit, KEY, S, H) if (c.pend & (bit)) { uint64_t kk = slot_key(S); if (kk == (KEY)) { c.fnd |= (bit); c.pend &= ~(bit); } else if (kk == ~0ULL) c.pend &= ~(bit); else { H = (uint32_t)(((uint64_t)H + 1) & ix.hmask); S = CG_LDG(&ix.hslots[H]); } }
+        T_RESOLVE(1u, c.key0, c.s0, c.h0)
+        T_RESOLVE(2u, c.key1, c.s1, c.h1)
+        T_RESOLVE(4u, c.key2, c.s2, c.h2)
+        T_RESOLVE(8u, c.key3, c.s3, c.h3)
+#undef T_RESOLVE
+        if (c.pend) ctl = false;                        // linear probing: the next slots are in flight
+        else c.req = RQ_NONE;
+    } else if (c.req == RQ_EXT_SA) {
+        ext_next_candidate(c, ix, k);
+        c.req = RQ_EXT_BLK;
+        ctl = false;
+    } else if (c.req == RQ_EXT_BLK) {
+        bool stop = false;
+        while (c.x_i < c.x_m) {
+            uint32_t tp = c.x_p + (uint32_t)c.x_i;
+            uint32_t bi = (tp >> 6) - c.x_b0;
+            if (bi > (c.x_two ? 1u : 0u)) break;                             // past the loaded blocks
+            int half = (tp >> 5) & 1, o5 = tp & 31;
+            uint64_t tw = half_codes(bi ? c.s1 : c.s0, half) >> (2 * o5);
+            uint32_t tm = (bi ? (half ? c.s2.w : c.s2.z) : (half ? c.s2.y : c.s2.x)) >> o5;
+            int n = cmin(32 - o5, c.x_m - c.x_i);
+            uint64_t q = m.chunk(c.x_s, c.x_q + c.x_i);
+            uint64_t x = tw ^ q;
+            uint64_t d = (x | (x >> 1)) & EVEN;
+            int j1 = d ? (ctz64(d) >> 1) : 32;
+            int j2 = tm ? ctz32(tm) : 32;
+            int j = cmin(j1, j2);
+            if (j < n) { c.x_i += j; stop = true; break; }
+            c.x_i += n;
+        }
+        if (!stop && c.x_i < c.x_m) { ext_issue_blocks(c, ix); ctl = false; }     // the match runs on into further blocks
+        else {
+            // the suffixes sharing the longest prefix are contiguous in SA order
+            if (c.x_i > c.x_best) { c.x_best = c.x_i; c.x_first = c.x_ci; c.x_last = c.x_ci; }
+            else if (c.x_i == c.x_best) c.x_last = c.x_ci;
+            if (++c.x_ci < c.x_w) { ext_next_candidate(c, ix, k); ctl = false; }
+            else {
+                c.x_lb = c.x_lbIn + 1 + c.x_first; c.x_ub = c.x_lbIn + 1 + c.x_last + 1; c.x_len = c.x_best;
+                c.req = RQ_NONE;
+            }
+        }
+    } else if (c.req == RQ_LCE_SA) {
+        if (c.x_sa == c.x_p) c.l_o2 = c.l_o1;
+        if (lceMode == 0) { c.l_o1 += (uint32_t)c.l_len; c.l_o2 += (uint32_t)c.l_len; }
+        uint32_t mx = cmax(c.l_o1, c.l_o2);
+        int64_t room = (int64_t)ix.n - (int64_t)mx;                          // maxIndex + len < textLen
+        c.l_lim = (int)cmin<int64_t>((int64_t)c.l_lim, room);
+        if (c.l_len < c.l_lim) { lce_issue_blocks(c, ix); c.req = RQ_LCE_BLK; ctl = false; }
+        else { c.l_res = c.l_len; c.req = RQ_NONE; }
+    } else if (c.req == RQ_LCE_BLK) {
+        const bool same = c.x_b1 == c.x_b0;
+        bool stop = false;
+        while (c.l_len < c.l_lim) {
+            uint32_t a = c.l_o1 + (uint32_t)c.l_len, b = c.l_o2 + (uint32_t)c.l_len;
+            if ((a >> 6) != c.x_b0 || (b >> 6) != c.x_b1) break;
+            int ha = (a >> 5) & 1, oa = a & 31, hb = (b >> 5) & 1, ob = b & 31;
+            uint64_t wa = half_codes(c.s0, ha) >> (2 * oa);
+            uint64_t wb = half_codes(same ? c.s0 : c.s1, hb) >> (2 * ob);
+            uint32_t ma = (ha ? c.s2.y : c.s2.x) >> oa;
+            uint32_t mb = (same ? (hb ? c.s2.y : c.s2.x) : (hb ? c.s2.w : c.s2.z)) >> ob;
+            int n = cmin(cmin(32 - oa, 32 - ob), c.l_lim - c.l_len);
+            uint64_t x = wa ^ wb;
+            uint64_t d = (x | (x >> 1)) & EVEN;
+            int j1 = d ? (ctz64(d) >> 1) : 32;
+            uint32_t mm = ma | mb;
+            int j2 = mm ? ctz32(mm) : 32;
+            int j = cmin(j1, j2);
+            if (j < n) { c.l_len += j; stop = true; break; }
+            c.l_len += n;
+        }
+        if (!stop && c.l_len < c.l_lim) { lce_issue_blocks(c, ix); ctl = false; }
+        else { c.l_res = c.l_len; c.req = RQ_NONE; }
+    } else if (c.req == RQ_TID_SA) {
+        c.s0 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa0 >> 6) + 1]);
+        if (c.e_c + 1 < c.e_end) c.s1 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa1 >> 6) + 1]);
+        if (c.e_c + 2 < c.e_end) c.s2 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa2 >> 6) + 1]);
+        if (c.e_c + 3 < c.e_end) c.s3 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa3 >> 6) + 1]);
+        c.req = RQ_TID_BLK;
+        ctl = false;
+    } else if (c.req == RQ_TID_BLK) {
+        c.tid0 = tid_from(c.s0, c.sa0);
+        if (c.e_c + 1 < c.e_end) c.tid1 = tid_from(c.s1, c.sa1);
+        if (c.e_c + 2 < c.e_end) c.tid2 = tid_from(c.s2, c.sa2);
+        if (c.e_c + 3 < c.e_end) c.tid3 = tid_from(c.s3, c.sa3);
+        if (c.e_off) {
+            c.s0.x = CG_LDG(&ix.offsets[c.tid0]); c.s0.y = CG_LDG(&ix.offsets[c.tid0 + 1]);
+            if (c.e_c + 1 < c.e_end) { c.s0.z = CG_LDG(&ix.offsets[c.tid1]); c.s0.w = CG_LDG(&ix.offsets[c.tid1 + 1]); }
+            if (c.e_c + 2 < c.e_end) { c.s1.x = CG_LDG(&ix.offsets[c.tid2]); c.s1.y = CG_LDG(&ix.offsets[c.tid2 + 1]); }
+            if (c.e_c + 3 < c.e_end) { c.s1.z = CG_LDG(&ix.offsets[c.tid3]); c.s1.w = CG_LDG(&ix.offsets[c.tid3 + 1]); }
+            c.req = RQ_TID_OFF;
+            ctl = false;
+        } else c.req = RQ_NONE;
+    } else if (c.req == RQ_TID_OFF) {
+        c.req = RQ_NONE;
+    }
+
+    return ctl;
+}
+
+template <bool BSJ, class Sink>
+CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
+    const int k = ix.k, L = c.L;
+    const int skipOverlap = k - 1;
+    const uint32_t maxInterval = 1000;
+    switch (c.pc) {
+    case PC_START:
+        c.nF = c.nR = 0; c.fwdHit = c.rcHit = 0; c.found = false; c.flags = 0; c.nh = 0; c.split = false;
+        c.lbF = c.ubF = 0; c.matched = 0; c.q0 = 0;
+        // ---- Phase A (:112-200): first position whose k-mer or reverse complement is in the table, `re < read.end()`
+        c.pos = 0; c.a_two = false;                     // a_two: this round looks at two positions
+        while (c.pos + k < L) {
+            c.p_s = 0; c.p_pos = c.pos; c.p_lim = L - k - 1; c.p_mode = c.a_two ? PM_PAIR2 : PM_PAIR1;
+            T_REQ(RQ_PROBE, PC_A_PROBED);               // :131-132
+            if (!(c.fnd & 3u)) {
+                if (c.fnd & 12u) { c.pos += 1; c.fnd >>= 2; c.s0 = c.s2; }
+                else { c.pos += c.a_two ? 2 : 1; c.a_two = true; continue; }     // the walk goes on whatever the look-ups return
+            }
+            c.hasF = (c.fnd & 1u) != 0; c.hasR = (c.fnd & 2u) != 0;
+            c.a_two = true;
+            if (c.hasF) {
+                c.x_s = 0; c.x_q = c.pos; c.x_lbIn = c.s0.z > 0 ? c.s0.z - 1 : 0; c.x_ubIn = c.s0.w;   // :140
+                T_EXT(PC_A_EXT);                        // :143
+                c.lbF = c.x_lb; c.ubF = c.x_ub; c.matched = c.x_len;
+                if (c.ubF > c.lbF && c.ubF - c.lbF < maxInterval) {              // :149
+                    m.st(m.iv(0, 0), c.lbF); m.st(m.iv(0, 0) + 1, c.ubF); m.st(m.iv(0, 0) + 2, (uint32_t)c.matched | ((uint32_t)c.pos << 16));
+                    c.nF = 1; c.q0 = c.pos;
+                    ++c.fwdHit;
+                    if (c.hasR) ++c.rcHit;
+                }
+            }
+            if (c.hasR && !c.fwdHit) ++c.rcHit;                                  // :178-191
+            if (c.fwdHit + c.rcHit > 0) { c.found = true; break; }
+            ++c.pos;
+        }
+        if (!c.found) T_DONE();                                // :204
+
+        // ---- Phases B (:208-329, forward strand) and C (:332-440, reverse-complement strand)
+        for (c.s = 0; c.s < 2; ++c.s) {
+            c.lastSearch = false; c.expectAbsent = false;
+            if (c.s == 0) {
+                if (!c.fwdHit) continue;
+                c.l_o1 = c.lbF; c.l_o2 = c.ubF - 1; c.l_len = c.matched; c.l_lim = L - (c.q0 + c.matched);   // :219
+                T_LCE(PC_B_LCE0);                                                // :220
+                {
+                    int remaining = L - (c.q0 + c.matched);
+                    int fwdSkip = cmax(c.matched - skipOverlap, c.l_res - skipOverlap);
+                    c.pos = cmin(cmax(0, L - k), c.q0 + fwdSkip);                // :224-228
+                    c.expectAbsent = remaining > 0 && c.pos < L - k;
+                }
+            } else {
+                if (!(c.rcHit >= c.fwdHit)) continue;                            // :332
+                c.pos = 0;
+            }
+            c.prevO = -1; c.pB = c.pE = 0; c.pOther = false;
+            while (c.pos + k <= L) {                                             // :234 / :341-344
+                if (c.pos == c.prevO) { c.ivB = c.pB; c.ivE = c.pE; c.other = c.pOther; }   // the forced last position was just looked up
+                else {
+                    if (!c.expectAbsent) {
+                        // expected present: this k-mer and its reverse complement (:261+:268 / :372+:379)
+                        c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_PAIR1;
+                        T_REQ(RQ_PROBE, PC_B_PROBED);
+                        if (!(c.fnd & 1u)) { c.pos += 1; c.expectAbsent = true; continue; }     // :324 / :436
+                        c.other = (c.fnd & 2u) != 0;
+                        c.ivB = c.s0.z; c.ivE = c.s0.w;
+                    } else {
+                        // after a mismatch: the windows that cover it, four positions per round
+                        for (;;) {
+                            c.fnd = 0;
+                            if (c.pos + k > L) break;
+                            c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_RUN;
+                            T_REQ(RQ_PROBE, PC_B_RUN);
+                            if (c.fnd) break;
+                            c.pos += 4;
+                        }
+                        if (!c.fnd) { c.pos = L; continue; }                     // ran off the read: the loop ends
+                        if (c.fnd & 1u) { c.ivB = c.s0.z; c.ivE = c.s0.w; }
+                        else if (c.fnd & 2u) { c.pos += 1; c.ivB = c.s1.z; c.ivE = c.s1.w; }
+                        else if (c.fnd & 4u) { c.pos += 2; c.ivB = c.s2.z; c.ivE = c.s2.w; }
+                        else { c.pos += 3; c.ivB = c.s3.z; c.ivE = c.s3.w; }
+                        // the reverse complement of the k-mer that hit (:268 / :379)
+                        c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_RC1;
+                        T_REQ(RQ_PROBE, PC_B_RC);
+                        c.other = (c.fnd & 1u) != 0;
+                        c.expectAbsent = false;
+                    }
+                    c.prevO = c.pos; c.pB = c.ivB; c.pE = c.ivE; c.pOther = c.other;
+                }
+                if (c.s == 0) { ++c.fwdHit; if (c.other) ++c.rcHit; }
+                else { ++c.rcHit; if (c.other) ++c.fwdHit; }
+                c.x_s = c.s; c.x_q = c.pos; c.x_lbIn = c.ivB > 0 ? c.ivB - 1 : 0; c.x_ubIn = c.ivE;     // :279 / :392
+                T_EXT(PC_B_EXT);                                                 // :280 / :393
+                c.matched = c.x_len;
+                if (c.x_ub > c.x_lb && c.x_ub - c.x_lb < maxInterval) {          // :285 / :398
+                    int cnt = c.s == 0 ? c.nF : c.nR;
+                    if (cnt >= T_FI) T_BAIL(BAIL_NINT);
+                    int w0 = m.iv(c.s, cnt);
+                    m.st(w0, c.x_lb); m.st(w0 + 1, c.x_ub); m.st(w0 + 2, (uint32_t)c.matched | ((uint32_t)c.pos << 16));
+                    if (c.s == 0) ++c.nF; else ++c.nR;
+                }
+                if (c.lastSearch) break;                                         // :300 / :412
+                if (c.pos + c.matched < L) {
+                    c.l_o1 = c.x_lb; c.l_o2 = c.x_ub - 1; c.l_len = c.matched; c.l_lim = L - (c.pos + c.matched);
+                    T_LCE(PC_B_LCE);                                             // :304 / :416
+                    c.pos = cmax(c.pos + c.l_res - skipOverlap, c.pos + c.matched - skipOverlap);
+                    if (c.pos > L - k) { c.pos = L - k; c.lastSearch = true; }
+                    else c.expectAbsent = true;
+                } else {
+                    c.lastSearch = true; c.pos = L - k;
+                }
+            }
+        }
+
+        // ---- strand vote (:442-490): only the two clear-cut outcomes; a real vote goes to the warp kernels
+        if (c.fwdHit > 0 && c.rcHit == 0) c.nR = 0;
+        else if (c.rcHit > 0 && c.fwdHit == 0) c.nF = 0;
+        else T_BAIL(BAIL_VOTE);
+        if (c.nF + c.nR > 0) c.flags |= MATE_SEEDED;                             // Circall_wt.cpp:311,486
+        c.s = c.nF > 0 ? 0 : 1;                                                  // the strand that kept its intervals
+        c.e_n = (uint32_t)(c.nF > 0 ? c.nF : c.nR);
+        if (c.e_n == 0) T_DONE();
+
+        // ---- hits (:492-563): intersection of the transcript sets of the maximal intervals
+        {
+            // keep = maximal, first of equals; e_mi = narrowest kept interval (first on ties)
+            c.keep = 0; c.e_mi = -1;
+            uint32_t msp = 0xffffffffu;
+            for (int x = 0; x < (int)c.e_n; ++x) {
+                int wx = m.iv(c.s, x);
+                uint32_t bx = m.ld(wx), ex = m.ld(wx + 1), lq = m.ld(wx + 2);
+                int lenx = (int)(lq & 0xffffu), qx = (int)(lq >> 16);
+                if (lenx == c.pairLen) c.flags |= MATE_FULL;                     // :318-342,493-517
+                bool drop = false;
+                for (int y = 0; y < (int)c.e_n && !drop; ++y) {
+                    if (y == x) continue;
+                    int wy = m.iv(c.s, y);
+                    uint32_t lqy = m.ld(wy + 2);
+                    int leny = (int)(lqy & 0xffffu), qy = (int)(lqy >> 16);
+                    if (leny > lenx) drop = qy <= qx && qy + leny >= qx + lenx;
+                    else if (leny == lenx && y < x) drop = m.ld(wy) == bx && m.ld(wy + 1) == ex;
+                }
+                if (!drop) {
+                    c.keep |= 1u << x;
+                    if (ex - bx < msp) { msp = ex - bx; c.e_mi = x; }
+                }
+            }
+            if (msp > (uint32_t)T_HC) T_BAIL(BAIL_NCAND);
+            c.e_c = m.ld(m.iv(c.s, c.e_mi)); c.e_end = m.ld(m.iv(c.s, c.e_mi) + 1);
+        }
+        // candidates: transcript of every position of the narrowest interval, four positions per round
+        c.nc = 0; c.alive = 0; c.e_off = false;
+        while (c.e_c < c.e_end) {
+            T_REQ(RQ_TID, PC_H_TID);
+            for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
+                uint32_t t = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
+                bool fresh = true;                       // one candidate per distinct transcript
+                for (int y = 0; y < c.nc; ++y) if (m.ld(m.cb() + y) == t) { fresh = false; break; }
+                if (fresh) { m.st(m.cb() + c.nc, t); c.alive |= 1u << c.nc; ++c.nc; }
+            }
+        }
+        // a candidate stays alive iff its transcript occurs among the positions of every other maximal interval
+        for (c.e_x = 0; c.e_x < (int)c.e_n && c.alive; ++c.e_x) {
+            if (c.e_x == c.e_mi || !((c.keep >> c.e_x) & 1u)) continue;
+            c.e_c = m.ld(m.iv(c.s, c.e_x)); c.e_end = m.ld(m.iv(c.s, c.e_x) + 1);
+            if (c.e_end - c.e_c > (uint32_t)T_OTHER) T_BAIL(BAIL_WIDE_OTHER);
+            c.seen = 0;
+            while (c.e_c < c.e_end) {
+                T_REQ(RQ_TID, PC_O_TID);
+                for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
+                    uint32_t t = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
+                    for (int y = 0; y < c.nc; ++y) if (m.ld(m.cb() + y) == t) c.seen |= 1u << y;
+                }
+            }
+            c.alive &= c.seen;
+        }
+        c.nh = (uint32_t)popc64(c.alive);
+        if (!BSJ) T_DONE();
+
+        // ---- Circall_bsj: ordered transcript list, then the junction-span filter over every position of every
+        //      interval (src/Circall_bsj.cpp:319-374), four positions per round
+        {
+            int n = 0;                                   // compact the live candidates, then insertion sort
+            for (int y = 0; y < c.nc; ++y) if ((c.alive >> y) & 1u) { m.st(m.cb() + n, m.ld(m.cb() + y)); ++n; }
+            for (int i = 1; i < n; ++i) {
+                uint32_t v = m.ld(m.cb() + i); int j = i - 1;
+                while (j >= 0 && m.ld(m.cb() + j) > v) { m.st(m.cb() + j + 1, m.ld(m.cb() + j)); --j; }
+                m.st(m.cb() + j + 1, v);
+            }
+        }
+        if (c.nh == 0) T_DONE();                               // :319
+        for (int x = 0; x < (int)c.e_n; ++x)             // bail before the first row of this record is emitted, or not at all
+            if (m.ld(m.iv(c.s, x) + 1) - m.ld(m.iv(c.s, x)) > (uint32_t)T_OTHER) T_BAIL(BAIL_WIDE_OTHER);
+        c.e_off = true;
+        for (c.e_x = 0; c.e_x < (int)c.e_n; ++c.e_x) {
+            c.e_c = m.ld(m.iv(c.s, c.e_x)); c.e_end = m.ld(m.iv(c.s, c.e_x) + 1);
+            while (c.e_c < c.e_end) {
+                T_REQ(RQ_TID, PC_J_TID);
+                {
+                    uint32_t lq = m.ld(m.iv(c.s, c.e_x) + 2);
+                    int len = (int)(lq & 0xffffu), qp = (int)(lq >> 16);
+                    for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
+                        uint32_t p = z == 0 ? c.sa0 : z == 1 ? c.sa1 : z == 2 ? c.sa2 : c.sa3;
+                        uint32_t tid = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
+                        uint32_t st0 = z == 0 ? c.s0.x : z == 1 ? c.s0.z : z == 2 ? c.s1.x : c.s1.z;
+                        uint32_t st1 = z == 0 ? c.s0.y : z == 1 ? c.s0.w : z == 2 ? c.s1.y : c.s1.w;
+                        int hitPos = (int)(p - st0);
+                        int junctPos = (int)((st1 - st0 - 1) / 2);                // :333
+                        if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {   // :336 / :364
+                            sink.line((uint32_t)c.s, (uint32_t)qp, (uint32_t)len, hitPos, tid);
+                            c.split = true;
+                        }
+                    }
+                }
+            }
+        }
+        T_DONE();
+
+    default:
+        break;
+    }
+}
+
+CG_HD void tsm_issue(Ctx& c, const IndexView& ix, const TMem& m) {
+    const int k = ix.k;
+    const uint64_t KM = kmask(k);
+    if (c.req == RQ_PROBE) {
+        // keys of the pattern, then their home slots
+        const int p = c.p_pos;
+        bool homo = false;
+        c.pend = 0; c.fnd = 0;
+        if (c.p_mode == PM_RUN) {
+            if (p <= c.p_lim) { c.key0 = m.chunk(c.p_s, p) & KM; c.pend |= 1u; homo |= homopolymer(c.key0, k); }
+            if (p + 1 <= c.p_lim) { c.key1 = m.chunk(c.p_s, p + 1) & KM; c.pend |= 2u; homo |= homopolymer(c.key1, k); }
+            if (p + 2 <= c.p_lim) { c.key2 = m.chunk(c.p_s, p + 2) & KM; c.pend |= 4u; homo |= homopolymer(c.key2, k); }
+            if (p + 3 <= c.p_lim) { c.key3 = m.chunk(c.p_s, p + 3) & KM; c.pend |= 8u; homo |= homopolymer(c.key3, k); }
+        } else {
+            c.key0 = m.chunk(c.p_s, p) & KM;
+            homo |= homopolymer(c.key0, k);
+            c.key1 = revcomp(c.key0, k);
+            c.pend = 3u;
+            if (c.p_mode == PM_RC1) { c.key0 = c.key1; c.pend = 1u; }
+            else if (c.p_mode == PM_PAIR2 && p + 1 <= c.p_lim) {
+                c.key2 = m.chunk(c.p_s, p + 1) & KM;
+                homo |= homopolymer(c.key2, k);
+                c.key3 = revcomp(c.key2, k);
+                c.pend = 15u;
+            }
+        }
+        if (homo) { c.pc = PC_BAIL; c.why = BAIL_HOMO; c.req = RQ_NONE; }      // (no jump back to `issue`: the warp meets there once per step)
+        else {
+            if (c.pend & 1u) { c.h0 = (uint32_t)home_slot(ix, c.key0); c.s0 = CG_LDG(&ix.hslots[c.h0]); }
+            if (c.pend & 2u) { c.h1 = (uint32_t)home_slot(ix, c.key1); c.s1 = CG_LDG(&ix.hslots[c.h1]); }
+            if (c.pend & 4u) { c.h2 = (uint32_t)home_slot(ix, c.key2); c.s2 = CG_LDG(&ix.hslots[c.h2]); }
+            if (c.pend & 8u) { c.h3 = (uint32_t)home_slot(ix, c.key3); c.s3 = CG_LDG(&ix.hslots[c.h3]); }
+            c.req = RQ_PROBE_W;
+        }
+    } else if (c.req == RQ_EXT) {
+        c.x_best = -1; c.x_first = c.x_last = 0; c.x_ci = 0;
+        c.x_sa = CG_LDG(&ix.sa[c.x_lbIn + 1]);
+        c.req = RQ_EXT_SA;
+    } else if (c.req == RQ_LCE) {
+        c.x_p = c.l_o1; c.x_sa = c.l_o2;                 // the two SA indices
+        c.l_o1 = CG_LDG(&ix.sa[c.x_p]);
+        if (c.x_sa != c.x_p) c.l_o2 = CG_LDG(&ix.sa[c.x_sa]);
+        c.req = RQ_LCE_SA;
+    } else if (c.req == RQ_TID) {
+        c.sa0 = CG_LDG(&ix.sa[c.e_c]);
+        if (c.e_c + 1 < c.e_end) c.sa1 = CG_LDG(&ix.sa[c.e_c + 1]);
+        if (c.e_c + 2 < c.e_end) c.sa2 = CG_LDG(&ix.sa[c.e_c + 2]);
+        if (c.e_c + 3 < c.e_end) c.sa3 = CG_LDG(&ix.sa[c.e_c + 3]);
+        c.req = RQ_TID_SA;
+    }
+}
+
+// the three phases back to back (host emulation; the kernel interleaves them with warp meeting points)
+template <bool BSJ, class Sink>
+CG_HD void tsm_step(Ctx& c, const IndexView& ix, const TMem& m, int lceMode, Sink& sink) {
+    if (tsm_complete(c, ix, m, lceMode)) tsm_control<BSJ>(c, ix, m, sink);
+    tsm_issue(c, ix, m);
+}
+
+#undef T_REQ
+#undef T_EXT
+#undef T_LCE
+#undef T_BAIL
+#undef T_DONE
+
+struct NoSink { CG_HD void line(uint32_t, uint32_t, uint32_t, int, uint32_t) const {} };
+
+// reverse-complement strand from the forward words: word j = 32 bases from oriented position 32 j (ReadView::chunk(1, .))
+CG_HD void tsm_make_rc(const TMem& m, int L) {
+    for (int j = 0; j < m.W2; ++j) {
+        int a = L - 32 - 32 * j;
+        uint64_t v = 0;
+        if (a >= 0) v = rc64(m.chunk(0, a));
+        else if (32 + a > 0) v = rc64(m.chunk(0, 0)) >> (2 * (-a));
+        m.st(2 * m.W2 + 2 * j, (uint32_t)v); m.st(2 * m.W2 + 2 * j + 1, (uint32_t)(v >> 32));
+    }
+}
+
+// Stage a packed read (cgk::k_pack record: W2f code words then the N-mask words) into the thread's scratch and
+// initialise the context (host side; the kernel stages the words with cp.async and does the rest itself).
+// Returns false when the read must go to the warp kernels straight away (an N below L).
+CG_HD bool tsm_begin(Ctx& c, const TMem& m, const uint64_t* rec, int W2f, int WMf, int L, int pairLen) {
+    bool anyN = false;
+    for (int j = 0; j < WMf; ++j) {
+        int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = CG_LDG(rec + W2f + j);
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        anyN |= mk != 0;
+    }
+    c.L = L; c.pairLen = pairLen; c.pc = PC_START; c.req = RQ_NONE; c.why = 0; c.zero = 0;
+    if (anyN || L < 1) { c.why = BAIL_N; return false; }
+    for (int j = 0; j < W2f; ++j) { uint64_t v = CG_LDG(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
+    m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
+    tsm_make_rc(m, L);
+    return true;
+}
+
+} // namespace cgt

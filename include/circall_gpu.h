@@ -142,6 +142,7 @@ typedef struct {
     double device_ms;            /* kernels of this batch, CUDA events on the session's stream */
     double kernel_ms[4];         /* of which: read packing, wt collector, wt commit + export compaction, bsj collector + span filter */
     uint64_t n_fallback_wt, n_fallback_bsj;   /* mates / records that needed the large-capacity general kernels */
+    uint64_t n_tier2_wt, n_tier2_bsj;         /* mates / records the thread-per-read first tier handed to the warp-per-read kernels */
 } cg_batch_result;
 
 /* scalar counters (ReadExperiment.hpp:265-270) for the two tools */

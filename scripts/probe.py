@@ -34,15 +34,15 @@ for stage in (1, 0):
     S = cg.Session(gtx, gbsj if stage == 0 else None, stage=stage)
     for it in range(a.iters):
         cg.flush_l2()
-        tot = 0.0; nexp = 0; njunc = 0; fb = [0, 0]; km = [0.0] * 4
+        tot = 0.0; nexp = 0; njunc = 0; fb = [0, 0]; t2 = [0, 0]; km = [0.0] * 4
         w = time.time()
         for b0 in range(0, n, a.batch):
             nb = min(a.batch, n - b0)
             S.submit_device(d1.ptr + b0 * L, doff.ptr, d2.ptr + b0 * L, doff.ptr, nb, L)
             B = S.fetch(want_lists=False)
-            tot += B.device_ms; nexp += B.n_export; njunc += B.n_junc; fb[0] += B.n_fallback_wt; fb[1] += B.n_fallback_bsj; km = [a + b for a, b in zip(km, B.kernel_ms)]
+            tot += B.device_ms; nexp += B.n_export; njunc += B.n_junc; fb[0] += B.n_fallback_wt; fb[1] += B.n_fallback_bsj; t2[0] += B.n_tier2_wt; t2[1] += B.n_tier2_bsj; km = [a + b for a, b in zip(km, B.kernel_ms)]
         w = time.time() - w
-        print("stage %d iter %d: device %.2f ms wall %.2f ms  -> %.2f M pairs/s (device)  export=%d junc=%d fallback wt/bsj=%d/%d kernel ms pack/wt/commit/bsj=%s" % (stage, it, tot, w * 1e3, n / tot / 1e3, nexp, njunc, fb[0], fb[1], ["%.1f" % x for x in km]), flush=True)
+        print("stage %d iter %d: device %.2f ms wall %.2f ms  -> %.2f M pairs/s (device)  export=%d junc=%d fallback wt/bsj=%d/%d tier2 wt/bsj=%d/%d kernel ms pack/wt/commit/bsj=%s" % (stage, it, tot, w * 1e3, n / tot / 1e3, nexp, njunc, fb[0], fb[1], t2[0], t2[1], ["%.1f" % x for x in km]), flush=True)
     print(S.counters(per_bsj=False), "launches", S.launches)
     S.close()
 if a.gather:
