@@ -13,6 +13,7 @@
 #include "cg_tsm.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstddef>
 #include <cstdlib>
 
 using namespace cg;
@@ -408,80 +409,170 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
     }
 }
 
-// ---- first tier: thread-per-read state machine (cg_tsm.cuh) -------------------------------------------------
-static const int TSM_THREADS = 128;
-#ifndef CG_TSM_MINB
-#define CG_TSM_MINB 4
+// ---- first tier: block-sorted state machine (cg_tsm.cuh) ------------------------------------------------------
+// A block owns BSM_NC read contexts in shared memory (collector state, packed read, interval list, the landing
+// zone of its loads).  Every round: wait for the loads of the previous round (cp.async), SORT the contexts by state,
+// and let thread t advance the t-th context of that order by one step of cgt::tsm_complete / control / issue.  A warp
+// therefore runs 32 reads that are at the same place of the algorithm — the instruction stream is shared by all
+// 32 lanes instead of the 3 or 4 that happen to agree when every thread keeps its own read — and each context has
+// its next loads in flight while the block goes on to other contexts.  A read that bails (or holds an N) is flagged
+// in ovf[] and emits nothing here; the warp kernels redo it.
+#ifndef CG_BSM_NC
+#define CG_BSM_NC 256
 #endif
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc) {
+static const int BSM_NC = CG_BSM_NC;
+#ifndef CG_BSM_MINB
+#define CG_BSM_MINB 1
+#endif
+static const int BSM_NCW = (int)(offsetof(cgt::Ctx, d) / 4);       // saved context words
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gsrc));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
-// One thread per mate (BSJ = false: K2-K6 of Circall_wt) or per exported record (BSJ = true: K2-K5, K7, K8 of
-// Circall_bsj); persistent threads, grid-stride.  Every lane cycles through: fetch the packed read into its
-// scratch (cp.async, in flight for one round), run cgt::tsm_step() until the read is done or bails, commit.
-// A read that bails (or holds an N) is flagged in ovf[] and emits nothing here; the warp kernels redo it.
+// scratch + landing zone of one context; the engines' loads become asynchronous copies into the landing zone
+struct BMem : cgt::TMem {
+    uint4* land;          // land[slot * BSM_NC]: 16-byte landing slots of this context
+    uint32_t* sal;        // sal[slot * BSM_NC]: its suffix-array entries
+    __device__ __forceinline__ void ld16(u32x4&, int slot, const u32x4* p) const { cp_async16(land + slot * BSM_NC, p); }
+    __device__ __forceinline__ void ld8(uint32_t&, uint32_t&, int slot, int half, const cgt::u32x2* p) const { cp_async8(reinterpret_cast<char*>(land + slot * BSM_NC) + 8 * half, p); }
+    __device__ __forceinline__ void ld4(uint32_t&, int slot, const uint32_t* p) const { cp_async4(sal + slot * BSM_NC, p); }
+    __device__ __forceinline__ void ld4w(uint32_t&, int slot, int word, const uint32_t* p) const { cp_async4(reinterpret_cast<uint32_t*>(land + slot * BSM_NC) + word, p); }
+};
+__host__ __device__ inline size_t bsm_smem_bytes(const PackGeom& g) {
+    return (size_t)BSM_NC * (4 * 16 + BSM_NCW * 4 + cgt::TMem::words(g.W2f + 1) * 4 + 4 * 4 + 4) + 2 * 32 * 4;
+}
+
 template <bool BSJ>
-__global__ void __launch_bounds__(TSM_THREADS, CG_TSM_MINB)
-k_tsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_fixed,
+__global__ void __launch_bounds__(BSM_NC, CG_BSM_MINB)
+k_bsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_fixed,
       const uint32_t* __restrict__ exp_mate, int lceMode,
       uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,      // wt outputs
       BsjOut o, int do_counts,                                       // bsj outputs
       uint8_t* __restrict__ ovf, int zero) {
-    extern __shared__ uint32_t tsm_smem[];
-    cgt::TMem m; m.base = tsm_smem + threadIdx.x; m.stride = TSM_THREADS; m.W2 = g.W2f + 1;
+    extern __shared__ uint4 bsm_smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W2 = g.W2f + 1, SW = cgt::TMem::words(W2);
+    uint4* land = bsm_smem;                                                    // [4][NC]
+    uint32_t* cxw = reinterpret_cast<uint32_t*>(land + 4 * BSM_NC);            // [NCW][NC]
+    uint32_t* scr = cxw + BSM_NCW * BSM_NC;                                    // [SW][NC]
+    uint32_t* sal = scr + SW * BSM_NC;                                         // [4][NC]
+    uint32_t* order = sal + 4 * BSM_NC;                                        // [NC]
+    uint32_t* hist = order + BSM_NC;                                           // [32]
+    uint32_t* start = hist + 32;                                               // [32]
     const IndexView& ix = cgw::c_ix[BSJ ? 1 : 0];
-    const uint64_t nthreads = (uint64_t)gridDim.x * TSM_THREADS;
-    const uint64_t n = BSJ ? (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed) : n_fixed;
-    uint64_t x = (uint64_t)blockIdx.x * TSM_THREADS + threadIdx.x;
+    const uint32_t n = (uint32_t)(BSJ ? (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed) : n_fixed);
+    const uint32_t stride = gridDim.x * BSM_NC;
     uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
-    cgt::Ctx c; c.pc = cgt::PC_DONE; c.zero = zero;
     JSink sink; sink.buf = nullptr; sink.cursor = nullptr; sink.cap = 0; sink.rec = 0;
     if (BSJ) { sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; }
-    int st = 0;                                   // 0: needs a read, 1: fetch in flight, 2: running
-    uint64_t r = 0;
-    uint32_t r_next = 0;                          // BSJ: exp_mate[] of the record after this one, loaded a read ahead
-    if (BSJ && exp_mate && x < n) r_next = __ldg(exp_mate + x);
-    // every lane stays in the loop until the whole warp is out of reads: the vote at the top and the ballot before
-    // the step are meeting points of the full warp (a lane that is done idles through them)
-    bool alive = true;
-    while (__any_sync(0xffffffffu, alive)) {
-        if (alive && st == 1) {
-            cp_async_wait_all();
-            const int L = c.L;
-            bool anyN = false;                    // mask words were staged in the reverse-complement area
+
+    auto accessor = [&](int i) {
+        BMem m; m.base = scr + i; m.stride = BSM_NC; m.W2 = W2; m.land = land + i; m.sal = sal + i;
+        return m;
+    };
+    // the packed words of mate c.r -> forward strand area (codes) and reverse-complement area (N masks, checked and
+    // then overwritten); both mates' lengths -> sa1
+    auto issue_record = [&](cgt::Ctx& c, const BMem& m) {
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(pk + (uint64_t)c.r * g.WT);
+        for (int j = 0; j < 2 * g.W2f; ++j) cp_async4(m.base + (size_t)j * BSM_NC, rec + j);
+        for (int j = 0; j < 2 * g.WMf; ++j) cp_async4(m.base + (size_t)(2 * W2 + j) * BSM_NC, rec + 2 * g.W2f + j);
+        cp_async4(m.sal + 1 * BSM_NC, reinterpret_cast<const uint32_t*>(lens + (c.r & ~1u)));
+        c.req = cgt::RQ_FETCH_W;
+    };
+    auto start_read = [&](cgt::Ctx& c, const BMem& m) {
+        if (c.x >= n) { c.req = cgt::RQ_DEAD; return; }
+        if (BSJ && exp_mate) { cp_async4(m.sal, exp_mate + c.x); c.req = cgt::RQ_FETCH_R; }
+        else { c.r = BSJ ? 2 * c.x : c.x; issue_record(c, m); }
+    };
+    auto save = [&](const cgt::Ctx& c, int i) {
+#pragma unroll
+        for (int w = 0; w < BSM_NCW; ++w) { uint32_t v; memcpy(&v, reinterpret_cast<const char*>(&c) + 4 * w, 4); cxw[w * BSM_NC + i] = v; }
+    };
+
+    {   // context tid starts on work item blockIdx.x * NC + tid
+        cgt::Ctx c;
+        memset(&c, 0, sizeof c);
+        c.zero = zero; c.pc = cgt::PC_START; c.x = blockIdx.x * BSM_NC + tid;
+        start_read(c, accessor(tid));
+        save(c, tid);
+    }
+    for (;;) {
+        cp_async_wait_all();
+        if (tid < 32) hist[tid] = 0;
+        __syncthreads();
+        // ---- sort the contexts by state: table look-up state, else the control resume point
+        {
+            const int req = (int)cxw[(offsetof(cgt::Ctx, req) / 4) * BSM_NC + tid], pc = (int)cxw[(offsetof(cgt::Ctx, pc) / 4) * BSM_NC + tid];
+            const int key = req ? req : 16 + pc;
+            const unsigned mm = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(mm) - 1;
+            uint32_t wb = 0;
+            if (lane == leader) wb = atomicAdd(&hist[key], (uint32_t)__popc(mm));
+            wb = __shfl_sync(0xffffffffu, wb, leader);
+            __syncthreads();
+            if (tid < 32) {
+                uint32_t v = hist[tid], xs = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, xs, d); if (lane >= d) xs += y; }
+                start[tid] = xs - v;
+            }
+            __syncthreads();
+            order[start[key] + wb + __popc(mm & ((1u << lane) - 1))] = tid;
+        }
+        __syncthreads();
+        if (hist[cgt::RQ_DEAD] == BSM_NC) break;
+        const int i = (int)order[tid];
+        const BMem m = accessor(i);
+        cgt::Ctx c;
+#pragma unroll
+        for (int w = 0; w < BSM_NCW; ++w) { uint32_t v = cxw[w * BSM_NC + i]; memcpy(reinterpret_cast<char*>(&c) + 4 * w, &v, 4); }
+        c.d.s0 = land[0 * BSM_NC + i]; c.d.s1 = land[1 * BSM_NC + i]; c.d.s2 = land[2 * BSM_NC + i]; c.d.s3 = land[3 * BSM_NC + i];
+        c.d.sa0 = sal[0 * BSM_NC + i]; c.d.sa1 = sal[1 * BSM_NC + i]; c.d.sa2 = sal[2 * BSM_NC + i]; c.d.sa3 = sal[3 * BSM_NC + i];
+
+        if (c.req == cgt::RQ_FETCH_R) { c.r = c.d.sa0; issue_record(c, m); }
+        else if (c.req == cgt::RQ_FETCH_W) {
+            const uint32_t lw = c.d.sa1;
+            const int L = (int)((c.r & 1u) ? lw >> 16 : lw & 0xffffu);
+            bool anyN = false;                    // the mask words were staged in the reverse-complement area
             for (int j = 0; j < g.WMf; ++j) {
                 int lo = 64 * j;
                 if (lo >= L) break;
-                uint64_t mk = (uint64_t)m.ld(2 * m.W2 + 2 * j) | ((uint64_t)m.ld(2 * m.W2 + 2 * j + 1) << 32);
+                uint64_t mk = (uint64_t)m.ld(2 * W2 + 2 * j) | ((uint64_t)m.ld(2 * W2 + 2 * j + 1) << 32);
                 if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
                 anyN |= mk != 0;
             }
-            if (anyN || L < 1) { ovf[x] = 1; st = 0; x += nthreads; }
+            if (anyN || L < 1) { ovf[c.x] = 1; c.x += stride; start_read(c, m); }
             else {
                 m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
                 cgt::tsm_make_rc(m, L);
-                c.pc = cgt::PC_START; c.req = cgt::RQ_NONE; st = 2;
+                c.L = L; c.pairLen = BSJ ? L : (int)(lw & 0xffffu);        // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+                c.pc = cgt::PC_START; c.req = cgt::RQ_NONE;
             }
         }
-        // one round of the state machine, its three phases separated by meeting points of the whole warp (top level
-        // of the loop body: every lane gets there, whatever it is doing)
-        const bool stepping = alive && st == 2;
+        // one step of the state machine; its three phases are separated by meeting points of the warp
+        const bool stepping = c.req < cgt::RQ_FETCH_R;
         bool ctl = false;
         if (stepping) ctl = cgt::tsm_complete(c, ix, m, lceMode);
         __syncwarp();
-        if (ctl) cgt::tsm_control<BSJ>(c, ix, m, sink);
+        if (ctl) { sink.rec = c.x; cgt::tsm_control<BSJ>(c, ix, m, sink); }
         __syncwarp();
         if (stepping) {
             cgt::tsm_issue(c, ix, m);
             if (c.pc == cgt::PC_DONE) {
-                if (!BSJ) { flags[r] = c.flags; nhits[r] = c.nh; }
+                if (!BSJ) { flags[c.r] = c.flags; nhits[c.r] = c.nh; }
                 else {
                     // commit (Circall_bsj.cpp:383-491)
-                    o.rec_nhits[x] = c.nh; o.rec_split[x] = c.split ? 1 : 0;
+                    o.rec_nhits[c.x] = c.nh; o.rec_split[c.x] = c.split ? 1 : 0;
                     upper += c.nh > 0;                                                    // :383
                     const uint32_t cc = c.nh > (uint32_t)MAX_READ_OCCS ? 0 : c.nh;        // :385
                     const bool cand = cc > 0 && c.split;                                  // :390
@@ -491,30 +582,19 @@ k_tsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGe
                         else if (do_counts & 2) {
                             unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL), sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)cc);
                             if (e < o.eq_cap && sidx + cc <= o.eq_tids_cap) {
-                                o.eq_ent[e] = make_uint4((uint32_t)x, (uint32_t)sidx, cc, 0u);
+                                o.eq_ent[e] = make_uint4(c.x, (uint32_t)sidx, cc, 0u);
                                 for (uint32_t t = 0; t < cc; ++t) o.eq_tids[sidx + t] = m.ld(m.cb() + t);
                             }
                         }
                     }
                 }
-                st = 0; x += nthreads;
-            } else if (c.pc == cgt::PC_BAIL) { ovf[x] = 1; st = 0; x += nthreads; }
+                c.pc = cgt::PC_START; c.x += stride; start_read(c, m);
+            } else if (c.pc == cgt::PC_BAIL) { ovf[c.x] = 1; c.pc = cgt::PC_START; c.x += stride; start_read(c, m); }
         }
-        if (alive && st == 0) {
-            if (x >= n) { alive = false; continue; }
-            r = BSJ ? (exp_mate ? (uint64_t)r_next : 2 * x) : x;
-            if (BSJ && exp_mate && x + nthreads < n) r_next = __ldg(exp_mate + x + nthreads);
-            const uint32_t* rec = reinterpret_cast<const uint32_t*>(pk + r * (uint64_t)g.WT);
-            for (int j = 0; j < 2 * g.W2f; ++j) cp_async4(m.base + (size_t)j * TSM_THREADS, rec + j);
-            for (int j = 0; j < 2 * g.WMf; ++j) cp_async4(m.base + (size_t)(2 * m.W2 + j) * TSM_THREADS, rec + 2 * g.W2f + j);
-            cp_async_commit();
-            c.L = lens[r]; c.pairLen = BSJ ? c.L : lens[r & ~1ULL];    // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
-            sink.rec = (uint32_t)x;
-            st = 1;
-        }
+        save(c, i);
     }
     if (BSJ && (do_counts & 1)) {
-        __shared__ uint32_t sh[TSM_THREADS / 32];
+        __shared__ uint32_t sh[BSM_NC / 32];
         uint32_t t;
         t = block_sum(obs, sh);    if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)t);
         t = block_sum(mapped, sh); if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)t);
@@ -588,15 +668,15 @@ int compact_flags(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, ui
 }
 
 
-// launch the thread state machine over n_fixed mates (wt) / the exported records (bsj); persistent grid
+// launch the block-sorted state machine over n_fixed mates (wt) / the exported records (bsj); persistent grid
 template <bool BSJ>
 int launch_tsm(cg_session* s, uint64_t n_fixed, const uint32_t* em, const BsjOut& o, int do_counts) {
-    const size_t smem = (size_t)cgt::TMem::words(s->geom.W2f + 1) * 4 * TSM_THREADS;
-    if (smem > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(k_tsm<BSJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = bsm_smem_bytes(s->geom);
+    if (smem > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(k_bsm<BSJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tsm<BSJ>, TSM_THREADS, smem));
+    CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bsm<BSJ>, BSM_NC, smem));
     if (nb < 1) nb = 1;
-    return launch(s, k_tsm<BSJ>, dim3(s->sms * nb), dim3(TSM_THREADS), smem, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, n_fixed, em,
+    return launch(s, k_bsm<BSJ>, dim3(s->sms * nb), dim3(BSM_NC), smem, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, n_fixed, em,
                   s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), o, do_counts, s->d_ovf.as<uint8_t>(), 0);
 }
 

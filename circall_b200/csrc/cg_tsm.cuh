@@ -63,11 +63,17 @@ CG_HD uint32_t fsr(uint32_t lo, uint32_t hi, int sh) {      // funnel shift righ
 //   then T_HC        hit candidates (transcript ids)
 struct TMem {
     uint32_t* base; int stride; int W2;
+    static const bool kAsync = false;
     CG_HD uint32_t ld(int j) const { return base[(size_t)j * stride]; }
     CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
     CG_HD int iv(int s, int i) const { return 4 * W2 + 3 * (s * T_FI + i); }
     CG_HD int cb() const { return 4 * W2 + 6 * T_FI; }
     CG_HD static int words(int W2) { return 4 * W2 + 6 * T_FI + T_HC; }
+    // loads of the engines: value at p -> landing field (here: straight into the context's registers)
+    CG_HD void ld16(u32x4& dst, int /*slot*/, const u32x4* p) const { dst = CG_LDG(p); }
+    CG_HD void ld8(uint32_t& lo, uint32_t& hi, int /*slot*/, int /*half*/, const u32x2* p) const { u32x2 v = CG_LDG(p); lo = v.x; hi = v.y; }
+    CG_HD void ld4(uint32_t& dst, int /*slot*/, const uint32_t* p) const { dst = CG_LDG(p); }
+    CG_HD void ld4w(uint32_t& dst, int /*slot*/, int /*word*/, const uint32_t* p) const { dst = CG_LDG(p); }
     // 32-base window of strand s at oriented position i (i < L)
     CG_HD uint64_t chunk(int s, int i) const {
         int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
@@ -89,13 +95,25 @@ enum {
     RQ_PROBE, RQ_PROBE_W,                   // table look-ups
     RQ_EXT, RQ_EXT_SA, RQ_EXT_BLK,          // extendSearchNaive, candidate by candidate
     RQ_LCE, RQ_LCE_SA, RQ_LCE_BLK,          // SASearcher::lce
-    RQ_TID, RQ_TID_SA, RQ_TID_BLK, RQ_TID_OFF   // up to four SA positions -> transcript ids (-> transcript bounds)
+    RQ_TID, RQ_TID_SA, RQ_TID_BLK, RQ_TID_OFF,  // up to four SA positions -> transcript ids (-> transcript bounds)
+    RQ_FETCH_R, RQ_FETCH_W, RQ_DEAD             // owned by the kernel: record index / packed read in flight; out of reads
 };
 // look-up patterns
 enum { PM_PAIR1 = 0,    // k-mer at pos and its reverse complement
        PM_PAIR2,        // the same for pos and pos + 1
        PM_RUN,          // the k-mers at pos .. pos + 3 (those that fit the read)
        PM_RC1 };        // the reverse complement of the k-mer at pos
+
+// Load targets.  Every global load of the engines lands in one of these; nothing else in the context is written by a
+// load, and the engines never keep a value here across rounds except through a load.  On the host (and in a
+// thread-resident kernel) they are plain fields; in the block-sorted kernel they are the cp.async landing zone of the
+// context in shared memory, re-read at the start of every round and never written back.
+struct Land {
+    u32x4 s0, s1, s2, s3;                  // table slots | code halves of text blocks A / B (s0 / s1) and their '$' masks
+                                           // (s2: x,y = A; z,w = B) | second halves of four text blocks | transcript bounds
+    uint32_t sa0, sa1, sa2, sa3;           // suffix-array entries
+};
+enum { LD_S0 = 0, LD_S1, LD_S2, LD_S3 };   // 16-byte landing slots; LD_S2 also takes two 8-byte halves (ld8 lo / hi)
 
 struct Ctx {
     int pc, req;
@@ -105,23 +123,19 @@ struct Ctx {
     int pos, s, nF, nR, matched, q0, prevO;
     uint32_t fwdHit, rcHit, lbF, ubF, pB, pE, ivB, ivE;
     bool found, lastSearch, expectAbsent, pOther, other, hasF, hasR, a_two;
-    // look-up engine: request (strand p_s, position p_pos, pattern p_mode, limit p_lim = last position allowed);
-    // in flight: one slot per key.  The same registers carry the other engines' loads:
-    //   s0 / s1 = code halves of text blocks A / B, s2 = their '$' masks (x,y: A; z,w: B)      (extension, lce)
-    //   s0..s3  = second halves of four text blocks, then s0 / s1 = transcript bounds          (SA position -> tid)
+    // look-up engine: request (strand p_s, position p_pos, pattern p_mode, limit p_lim = last position allowed)
     int p_s, p_pos, p_mode, p_lim;
     uint64_t key0, key1, key2, key3;
     uint32_t h0, h1, h2, h3, pend, fnd;
-    u32x4 s0, s1, s2, s3;
     // extension engine
     int x_s, x_q, x_i, x_best, x_m, x_len;
-    uint32_t x_lbIn, x_ubIn, x_ci, x_w, x_first, x_last, x_sa, x_p, x_lb, x_ub, x_b0, x_b1;
+    uint32_t x_lbIn, x_ubIn, x_ci, x_w, x_first, x_last, x_p, x_lb, x_ub, x_b0, x_b1;
     bool x_two;
     // lce engine
-    uint32_t l_o1, l_o2; int l_len, l_lim, l_res;
-    // SA position -> transcript engine: positions e_c .. min(e_c + 4, e_end); out: sa0..3 (text positions), tid0..3
-    uint32_t e_c, e_end, sa0, sa1, sa2, sa3, tid0, tid1, tid2, tid3;
-    bool e_off;                            // also fetch offsets[tid], offsets[tid + 1] (into s0 / s1)
+    uint32_t l_i1, l_i2, l_o1, l_o2; int l_len, l_lim, l_res;
+    // SA position -> transcript engine: positions e_c .. min(e_c + 4, e_end); out: d.sa0..3 (text positions), tid0..3
+    uint32_t e_c, e_end, tid0, tid1, tid2, tid3;
+    bool e_off;                            // also fetch offsets[tid], offsets[tid + 1] (into d.s0 / d.s1)
     // hit enumeration
     uint32_t keep, alive, seen, e_n;
     int e_x, e_mi, nc;
@@ -129,6 +143,8 @@ struct Ctx {
     uint32_t nh; uint8_t flags; bool split;
     int why;                               // BAIL_* when pc == PC_BAIL
     int zero;                              // always 0, but only known at run time (see T_REQ)
+    uint32_t x, r;                         // owned by the kernel: work item (mate / export record) and the mate it maps
+    Land d;                                // last: everything before it is the part of the context that is saved
 };
 
 CG_HD uint64_t slot_key(const u32x4& s) { return (uint64_t)s.x | ((uint64_t)s.y << 32); }
@@ -142,36 +158,35 @@ CG_HD const u32x2* mask_ptr(const IndexView& ix, uint32_t b) { return reinterpre
 // ---- engine pieces -------------------------------------------------------------------------------------------
 // text blocks for the extension: the block that holds text position p + i and, when the compared range reaches
 // into it, the next one
-CG_HD void ext_issue_blocks(Ctx& c, const IndexView& ix) {
+template <class M>
+CG_HD void ext_issue_blocks(Ctx& c, const IndexView& ix, const M& m) {
     uint32_t tp = c.x_p + (uint32_t)c.x_i;
     c.x_b0 = tp >> 6;
     c.x_two = (int)(tp & 63) + (c.x_m - c.x_i) > 64;
-    c.s0 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0]);
-    u32x2 ma = CG_LDG(mask_ptr(ix, c.x_b0));
-    c.s2.x = ma.x; c.s2.y = ma.y;
+    m.ld16(c.d.s0, LD_S0, &ix.text[2 * (uint64_t)c.x_b0]);
+    m.ld8(c.d.s2.x, c.d.s2.y, LD_S2, 0, mask_ptr(ix, c.x_b0));
     if (c.x_two) {
-        c.s1 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0 + 2]);
-        u32x2 mb = CG_LDG(mask_ptr(ix, c.x_b0 + 1));
-        c.s2.z = mb.x; c.s2.w = mb.y;
+        m.ld16(c.d.s1, LD_S1, &ix.text[2 * (uint64_t)c.x_b0 + 2]);
+        m.ld8(c.d.s2.z, c.d.s2.w, LD_S2, 1, mask_ptr(ix, c.x_b0 + 1));
     }
 }
 CG_HD uint64_t half_codes(const u32x4& b, int half) { return half ? ((uint64_t)b.z | ((uint64_t)b.w << 32)) : ((uint64_t)b.x | ((uint64_t)b.y << 32)); }
-// next candidate of the extension: its SA entry is in x_sa; fetch the following one alongside its text blocks
-CG_HD void ext_next_candidate(Ctx& c, const IndexView& ix, int k) {
-    c.x_p = c.x_sa;
-    if (c.x_ci + 1 < c.x_w) c.x_sa = CG_LDG(&ix.sa[c.x_lbIn + 2 + c.x_ci]);
+// next candidate of the extension: its SA entry has landed in sa0; fetch the following one alongside its text blocks
+template <class M>
+CG_HD void ext_next_candidate(Ctx& c, const IndexView& ix, const M& m, int k) {
+    c.x_p = c.d.sa0;
+    if (c.x_ci + 1 < c.x_w) m.ld4(c.d.sa0, 0, &ix.sa[c.x_lbIn + 2 + c.x_ci]);
     c.x_i = k;
-    ext_issue_blocks(c, ix);
+    ext_issue_blocks(c, ix, m);
 }
-CG_HD void lce_issue_blocks(Ctx& c, const IndexView& ix) {
+template <class M>
+CG_HD void lce_issue_blocks(Ctx& c, const IndexView& ix, const M& m) {
     c.x_b0 = (c.l_o1 + (uint32_t)c.l_len) >> 6; c.x_b1 = (c.l_o2 + (uint32_t)c.l_len) >> 6;
-    c.s0 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b0]);
-    u32x2 ma = CG_LDG(mask_ptr(ix, c.x_b0));
-    c.s2.x = ma.x; c.s2.y = ma.y;
+    m.ld16(c.d.s0, LD_S0, &ix.text[2 * (uint64_t)c.x_b0]);
+    m.ld8(c.d.s2.x, c.d.s2.y, LD_S2, 0, mask_ptr(ix, c.x_b0));
     if (c.x_b1 != c.x_b0) {
-        c.s1 = CG_LDG(&ix.text[2 * (uint64_t)c.x_b1]);
-        u32x2 mb = CG_LDG(mask_ptr(ix, c.x_b1));
-        c.s2.z = mb.x; c.s2.w = mb.y;
+        m.ld16(c.d.s1, LD_S1, &ix.text[2 * (uint64_t)c.x_b1]);
+        m.ld8(c.d.s2.z, c.d.s2.w, LD_S2, 1, mask_ptr(ix, c.x_b1));
     }
 }
 
@@ -196,21 +211,22 @@ CG_HD void lce_issue_blocks(Ctx& c, const IndexView& ix) {
 // may run), tsm_control() (the reference's logic up to its next request) and tsm_issue() (that request's loads).
 // Sink::line(dir, queryPos, len, hitPos, tid) receives the junction-table rows (BSJ only).  On PC_DONE: c.flags / c.nh
 // (wt), c.nh / c.split and, for BSJ, the hit transcripts in ascending order in the candidate words of `m`.
-CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode) {
+template <class M>
+CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const M& m, int lceMode) {
     const int k = ix.k;
     // ================= complete what was in flight =================
     bool ctl = true;                                    // false: this lane's engine needs another round
     if (c.req == RQ_PROBE_W) {
-#define T_RESOLVE(bit, KEY, S, H) if (c.pend & (bit)) { uint64_t kk = slot_key(S); if (kk == (KEY)) { c.fnd |= (bit); c.pend &= ~(bit); } else if (kk == ~0ULL) c.pend &= ~(bit); else { H = (uint32_t)(((uint64_t)H + 1) & ix.hmask); S = CG_LDG(&ix.hslots[H]); } }
-        T_RESOLVE(1u, c.key0, c.s0, c.h0)
-        T_RESOLVE(2u, c.key1, c.s1, c.h1)
-        T_RESOLVE(4u, c.key2, c.s2, c.h2)
-        T_RESOLVE(8u, c.key3, c.s3, c.h3)
+#define T_RESOLVE(bit, KEY, S, SLOT, H) if (c.pend & (bit)) { uint64_t kk = slot_key(S); if (kk == (KEY)) { c.fnd |= (bit); c.pend &= ~(bit); } else if (kk == ~0ULL) c.pend &= ~(bit); else { H = (uint32_t)(((uint64_t)H + 1) & ix.hmask); m.ld16(S, SLOT, &ix.hslots[H]); } }
+        T_RESOLVE(1u, c.key0, c.d.s0, LD_S0, c.h0)
+        T_RESOLVE(2u, c.key1, c.d.s1, LD_S1, c.h1)
+        T_RESOLVE(4u, c.key2, c.d.s2, LD_S2, c.h2)
+        T_RESOLVE(8u, c.key3, c.d.s3, LD_S3, c.h3)
 #undef T_RESOLVE
         if (c.pend) ctl = false;                        // linear probing: the next slots are in flight
         else c.req = RQ_NONE;
     } else if (c.req == RQ_EXT_SA) {
-        ext_next_candidate(c, ix, k);
+        ext_next_candidate(c, ix, m, k);
         c.req = RQ_EXT_BLK;
         ctl = false;
     } else if (c.req == RQ_EXT_BLK) {
@@ -220,8 +236,8 @@ CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode)
             uint32_t bi = (tp >> 6) - c.x_b0;
             if (bi > (c.x_two ? 1u : 0u)) break;                             // past the loaded blocks
             int half = (tp >> 5) & 1, o5 = tp & 31;
-            uint64_t tw = half_codes(bi ? c.s1 : c.s0, half) >> (2 * o5);
-            uint32_t tm = (bi ? (half ? c.s2.w : c.s2.z) : (half ? c.s2.y : c.s2.x)) >> o5;
+            uint64_t tw = half_codes(bi ? c.d.s1 : c.d.s0, half) >> (2 * o5);
+            uint32_t tm = (bi ? (half ? c.d.s2.w : c.d.s2.z) : (half ? c.d.s2.y : c.d.s2.x)) >> o5;
             int n = cmin(32 - o5, c.x_m - c.x_i);
             uint64_t q = m.chunk(c.x_s, c.x_q + c.x_i);
             uint64_t x = tw ^ q;
@@ -232,24 +248,24 @@ CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode)
             if (j < n) { c.x_i += j; stop = true; break; }
             c.x_i += n;
         }
-        if (!stop && c.x_i < c.x_m) { ext_issue_blocks(c, ix); ctl = false; }     // the match runs on into further blocks
+        if (!stop && c.x_i < c.x_m) { ext_issue_blocks(c, ix, m); ctl = false; }     // the match runs on into further blocks
         else {
             // the suffixes sharing the longest prefix are contiguous in SA order
             if (c.x_i > c.x_best) { c.x_best = c.x_i; c.x_first = c.x_ci; c.x_last = c.x_ci; }
             else if (c.x_i == c.x_best) c.x_last = c.x_ci;
-            if (++c.x_ci < c.x_w) { ext_next_candidate(c, ix, k); ctl = false; }
+            if (++c.x_ci < c.x_w) { ext_next_candidate(c, ix, m, k); ctl = false; }
             else {
                 c.x_lb = c.x_lbIn + 1 + c.x_first; c.x_ub = c.x_lbIn + 1 + c.x_last + 1; c.x_len = c.x_best;
                 c.req = RQ_NONE;
             }
         }
     } else if (c.req == RQ_LCE_SA) {
-        if (c.x_sa == c.x_p) c.l_o2 = c.l_o1;
+        c.l_o1 = c.d.sa0; c.l_o2 = (c.l_i2 == c.l_i1) ? c.d.sa0 : c.d.sa1;
         if (lceMode == 0) { c.l_o1 += (uint32_t)c.l_len; c.l_o2 += (uint32_t)c.l_len; }
         uint32_t mx = cmax(c.l_o1, c.l_o2);
         int64_t room = (int64_t)ix.n - (int64_t)mx;                          // maxIndex + len < textLen
         c.l_lim = (int)cmin<int64_t>((int64_t)c.l_lim, room);
-        if (c.l_len < c.l_lim) { lce_issue_blocks(c, ix); c.req = RQ_LCE_BLK; ctl = false; }
+        if (c.l_len < c.l_lim) { lce_issue_blocks(c, ix, m); c.req = RQ_LCE_BLK; ctl = false; }
         else { c.l_res = c.l_len; c.req = RQ_NONE; }
     } else if (c.req == RQ_LCE_BLK) {
         const bool same = c.x_b1 == c.x_b0;
@@ -258,10 +274,10 @@ CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode)
             uint32_t a = c.l_o1 + (uint32_t)c.l_len, b = c.l_o2 + (uint32_t)c.l_len;
             if ((a >> 6) != c.x_b0 || (b >> 6) != c.x_b1) break;
             int ha = (a >> 5) & 1, oa = a & 31, hb = (b >> 5) & 1, ob = b & 31;
-            uint64_t wa = half_codes(c.s0, ha) >> (2 * oa);
-            uint64_t wb = half_codes(same ? c.s0 : c.s1, hb) >> (2 * ob);
-            uint32_t ma = (ha ? c.s2.y : c.s2.x) >> oa;
-            uint32_t mb = (same ? (hb ? c.s2.y : c.s2.x) : (hb ? c.s2.w : c.s2.z)) >> ob;
+            uint64_t wa = half_codes(c.d.s0, ha) >> (2 * oa);
+            uint64_t wb = half_codes(same ? c.d.s0 : c.d.s1, hb) >> (2 * ob);
+            uint32_t ma = (ha ? c.d.s2.y : c.d.s2.x) >> oa;
+            uint32_t mb = (same ? (hb ? c.d.s2.y : c.d.s2.x) : (hb ? c.d.s2.w : c.d.s2.z)) >> ob;
             int n = cmin(cmin(32 - oa, 32 - ob), c.l_lim - c.l_len);
             uint64_t x = wa ^ wb;
             uint64_t d = (x | (x >> 1)) & EVEN;
@@ -272,25 +288,25 @@ CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode)
             if (j < n) { c.l_len += j; stop = true; break; }
             c.l_len += n;
         }
-        if (!stop && c.l_len < c.l_lim) { lce_issue_blocks(c, ix); ctl = false; }
+        if (!stop && c.l_len < c.l_lim) { lce_issue_blocks(c, ix, m); ctl = false; }
         else { c.l_res = c.l_len; c.req = RQ_NONE; }
     } else if (c.req == RQ_TID_SA) {
-        c.s0 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa0 >> 6) + 1]);
-        if (c.e_c + 1 < c.e_end) c.s1 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa1 >> 6) + 1]);
-        if (c.e_c + 2 < c.e_end) c.s2 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa2 >> 6) + 1]);
-        if (c.e_c + 3 < c.e_end) c.s3 = CG_LDG(&ix.text[2 * (uint64_t)(c.sa3 >> 6) + 1]);
+        m.ld16(c.d.s0, LD_S0, &ix.text[2 * (uint64_t)(c.d.sa0 >> 6) + 1]);
+        if (c.e_c + 1 < c.e_end) m.ld16(c.d.s1, LD_S1, &ix.text[2 * (uint64_t)(c.d.sa1 >> 6) + 1]);
+        if (c.e_c + 2 < c.e_end) m.ld16(c.d.s2, LD_S2, &ix.text[2 * (uint64_t)(c.d.sa2 >> 6) + 1]);
+        if (c.e_c + 3 < c.e_end) m.ld16(c.d.s3, LD_S3, &ix.text[2 * (uint64_t)(c.d.sa3 >> 6) + 1]);
         c.req = RQ_TID_BLK;
         ctl = false;
     } else if (c.req == RQ_TID_BLK) {
-        c.tid0 = tid_from(c.s0, c.sa0);
-        if (c.e_c + 1 < c.e_end) c.tid1 = tid_from(c.s1, c.sa1);
-        if (c.e_c + 2 < c.e_end) c.tid2 = tid_from(c.s2, c.sa2);
-        if (c.e_c + 3 < c.e_end) c.tid3 = tid_from(c.s3, c.sa3);
+        c.tid0 = tid_from(c.d.s0, c.d.sa0);
+        if (c.e_c + 1 < c.e_end) c.tid1 = tid_from(c.d.s1, c.d.sa1);
+        if (c.e_c + 2 < c.e_end) c.tid2 = tid_from(c.d.s2, c.d.sa2);
+        if (c.e_c + 3 < c.e_end) c.tid3 = tid_from(c.d.s3, c.d.sa3);
         if (c.e_off) {
-            c.s0.x = CG_LDG(&ix.offsets[c.tid0]); c.s0.y = CG_LDG(&ix.offsets[c.tid0 + 1]);
-            if (c.e_c + 1 < c.e_end) { c.s0.z = CG_LDG(&ix.offsets[c.tid1]); c.s0.w = CG_LDG(&ix.offsets[c.tid1 + 1]); }
-            if (c.e_c + 2 < c.e_end) { c.s1.x = CG_LDG(&ix.offsets[c.tid2]); c.s1.y = CG_LDG(&ix.offsets[c.tid2 + 1]); }
-            if (c.e_c + 3 < c.e_end) { c.s1.z = CG_LDG(&ix.offsets[c.tid3]); c.s1.w = CG_LDG(&ix.offsets[c.tid3 + 1]); }
+            m.ld4w(c.d.s0.x, LD_S0, 0, &ix.offsets[c.tid0]); m.ld4w(c.d.s0.y, LD_S0, 1, &ix.offsets[c.tid0 + 1]);
+            if (c.e_c + 1 < c.e_end) { m.ld4w(c.d.s0.z, LD_S0, 2, &ix.offsets[c.tid1]); m.ld4w(c.d.s0.w, LD_S0, 3, &ix.offsets[c.tid1 + 1]); }
+            if (c.e_c + 2 < c.e_end) { m.ld4w(c.d.s1.x, LD_S1, 0, &ix.offsets[c.tid2]); m.ld4w(c.d.s1.y, LD_S1, 1, &ix.offsets[c.tid2 + 1]); }
+            if (c.e_c + 3 < c.e_end) { m.ld4w(c.d.s1.z, LD_S1, 2, &ix.offsets[c.tid3]); m.ld4w(c.d.s1.w, LD_S1, 3, &ix.offsets[c.tid3 + 1]); }
             c.req = RQ_TID_OFF;
             ctl = false;
         } else c.req = RQ_NONE;
@@ -301,8 +317,8 @@ CG_HD bool tsm_complete(Ctx& c, const IndexView& ix, const TMem& m, int lceMode)
     return ctl;
 }
 
-template <bool BSJ, class Sink>
-CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
+template <bool BSJ, class M, class Sink>
+CG_HD void tsm_control(Ctx& c, const IndexView& ix, const M& m, Sink& sink) {
     const int k = ix.k, L = c.L;
     const int skipOverlap = k - 1;
     const uint32_t maxInterval = 1000;
@@ -316,13 +332,13 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
             c.p_s = 0; c.p_pos = c.pos; c.p_lim = L - k - 1; c.p_mode = c.a_two ? PM_PAIR2 : PM_PAIR1;
             T_REQ(RQ_PROBE, PC_A_PROBED);               // :131-132
             if (!(c.fnd & 3u)) {
-                if (c.fnd & 12u) { c.pos += 1; c.fnd >>= 2; c.s0 = c.s2; }
+                if (c.fnd & 12u) { c.pos += 1; c.fnd >>= 2; c.d.s0 = c.d.s2; }
                 else { c.pos += c.a_two ? 2 : 1; c.a_two = true; continue; }     // the walk goes on whatever the look-ups return
             }
             c.hasF = (c.fnd & 1u) != 0; c.hasR = (c.fnd & 2u) != 0;
             c.a_two = true;
             if (c.hasF) {
-                c.x_s = 0; c.x_q = c.pos; c.x_lbIn = c.s0.z > 0 ? c.s0.z - 1 : 0; c.x_ubIn = c.s0.w;   // :140
+                c.x_s = 0; c.x_q = c.pos; c.x_lbIn = c.d.s0.z > 0 ? c.d.s0.z - 1 : 0; c.x_ubIn = c.d.s0.w;   // :140
                 T_EXT(PC_A_EXT);                        // :143
                 c.lbF = c.x_lb; c.ubF = c.x_ub; c.matched = c.x_len;
                 if (c.ubF > c.lbF && c.ubF - c.lbF < maxInterval) {              // :149
@@ -343,7 +359,7 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
             c.lastSearch = false; c.expectAbsent = false;
             if (c.s == 0) {
                 if (!c.fwdHit) continue;
-                c.l_o1 = c.lbF; c.l_o2 = c.ubF - 1; c.l_len = c.matched; c.l_lim = L - (c.q0 + c.matched);   // :219
+                c.l_i1 = c.lbF; c.l_i2 = c.ubF - 1; c.l_len = c.matched; c.l_lim = L - (c.q0 + c.matched);   // :219
                 T_LCE(PC_B_LCE0);                                                // :220
                 {
                     int remaining = L - (c.q0 + c.matched);
@@ -365,7 +381,7 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
                         T_REQ(RQ_PROBE, PC_B_PROBED);
                         if (!(c.fnd & 1u)) { c.pos += 1; c.expectAbsent = true; continue; }     // :324 / :436
                         c.other = (c.fnd & 2u) != 0;
-                        c.ivB = c.s0.z; c.ivE = c.s0.w;
+                        c.ivB = c.d.s0.z; c.ivE = c.d.s0.w;
                     } else {
                         // after a mismatch: the windows that cover it, four positions per round
                         for (;;) {
@@ -377,10 +393,10 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
                             c.pos += 4;
                         }
                         if (!c.fnd) { c.pos = L; continue; }                     // ran off the read: the loop ends
-                        if (c.fnd & 1u) { c.ivB = c.s0.z; c.ivE = c.s0.w; }
-                        else if (c.fnd & 2u) { c.pos += 1; c.ivB = c.s1.z; c.ivE = c.s1.w; }
-                        else if (c.fnd & 4u) { c.pos += 2; c.ivB = c.s2.z; c.ivE = c.s2.w; }
-                        else { c.pos += 3; c.ivB = c.s3.z; c.ivE = c.s3.w; }
+                        if (c.fnd & 1u) { c.ivB = c.d.s0.z; c.ivE = c.d.s0.w; }
+                        else if (c.fnd & 2u) { c.pos += 1; c.ivB = c.d.s1.z; c.ivE = c.d.s1.w; }
+                        else if (c.fnd & 4u) { c.pos += 2; c.ivB = c.d.s2.z; c.ivE = c.d.s2.w; }
+                        else { c.pos += 3; c.ivB = c.d.s3.z; c.ivE = c.d.s3.w; }
                         // the reverse complement of the k-mer that hit (:268 / :379)
                         c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_RC1;
                         T_REQ(RQ_PROBE, PC_B_RC);
@@ -403,7 +419,7 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
                 }
                 if (c.lastSearch) break;                                         // :300 / :412
                 if (c.pos + c.matched < L) {
-                    c.l_o1 = c.x_lb; c.l_o2 = c.x_ub - 1; c.l_len = c.matched; c.l_lim = L - (c.pos + c.matched);
+                    c.l_i1 = c.x_lb; c.l_i2 = c.x_ub - 1; c.l_len = c.matched; c.l_lim = L - (c.pos + c.matched);
                     T_LCE(PC_B_LCE);                                             // :304 / :416
                     c.pos = cmax(c.pos + c.l_res - skipOverlap, c.pos + c.matched - skipOverlap);
                     if (c.pos > L - k) { c.pos = L - k; c.lastSearch = true; }
@@ -502,10 +518,10 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
                     uint32_t lq = m.ld(m.iv(c.s, c.e_x) + 2);
                     int len = (int)(lq & 0xffffu), qp = (int)(lq >> 16);
                     for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
-                        uint32_t p = z == 0 ? c.sa0 : z == 1 ? c.sa1 : z == 2 ? c.sa2 : c.sa3;
+                        uint32_t p = z == 0 ? c.d.sa0 : z == 1 ? c.d.sa1 : z == 2 ? c.d.sa2 : c.d.sa3;
                         uint32_t tid = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
-                        uint32_t st0 = z == 0 ? c.s0.x : z == 1 ? c.s0.z : z == 2 ? c.s1.x : c.s1.z;
-                        uint32_t st1 = z == 0 ? c.s0.y : z == 1 ? c.s0.w : z == 2 ? c.s1.y : c.s1.w;
+                        uint32_t st0 = z == 0 ? c.d.s0.x : z == 1 ? c.d.s0.z : z == 2 ? c.d.s1.x : c.d.s1.z;
+                        uint32_t st1 = z == 0 ? c.d.s0.y : z == 1 ? c.d.s0.w : z == 2 ? c.d.s1.y : c.d.s1.w;
                         int hitPos = (int)(p - st0);
                         int junctPos = (int)((st1 - st0 - 1) / 2);                // :333
                         if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {   // :336 / :364
@@ -523,7 +539,8 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const TMem& m, Sink& sink) {
     }
 }
 
-CG_HD void tsm_issue(Ctx& c, const IndexView& ix, const TMem& m) {
+template <class M>
+CG_HD void tsm_issue(Ctx& c, const IndexView& ix, const M& m) {
     const int k = ix.k;
     const uint64_t KM = kmask(k);
     if (c.req == RQ_PROBE) {
@@ -551,33 +568,32 @@ CG_HD void tsm_issue(Ctx& c, const IndexView& ix, const TMem& m) {
         }
         if (homo) { c.pc = PC_BAIL; c.why = BAIL_HOMO; c.req = RQ_NONE; }      // (no jump back to `issue`: the warp meets there once per step)
         else {
-            if (c.pend & 1u) { c.h0 = (uint32_t)home_slot(ix, c.key0); c.s0 = CG_LDG(&ix.hslots[c.h0]); }
-            if (c.pend & 2u) { c.h1 = (uint32_t)home_slot(ix, c.key1); c.s1 = CG_LDG(&ix.hslots[c.h1]); }
-            if (c.pend & 4u) { c.h2 = (uint32_t)home_slot(ix, c.key2); c.s2 = CG_LDG(&ix.hslots[c.h2]); }
-            if (c.pend & 8u) { c.h3 = (uint32_t)home_slot(ix, c.key3); c.s3 = CG_LDG(&ix.hslots[c.h3]); }
+            if (c.pend & 1u) { c.h0 = (uint32_t)home_slot(ix, c.key0); m.ld16(c.d.s0, LD_S0, &ix.hslots[c.h0]); }
+            if (c.pend & 2u) { c.h1 = (uint32_t)home_slot(ix, c.key1); m.ld16(c.d.s1, LD_S1, &ix.hslots[c.h1]); }
+            if (c.pend & 4u) { c.h2 = (uint32_t)home_slot(ix, c.key2); m.ld16(c.d.s2, LD_S2, &ix.hslots[c.h2]); }
+            if (c.pend & 8u) { c.h3 = (uint32_t)home_slot(ix, c.key3); m.ld16(c.d.s3, LD_S3, &ix.hslots[c.h3]); }
             c.req = RQ_PROBE_W;
         }
     } else if (c.req == RQ_EXT) {
         c.x_best = -1; c.x_first = c.x_last = 0; c.x_ci = 0;
-        c.x_sa = CG_LDG(&ix.sa[c.x_lbIn + 1]);
+        m.ld4(c.d.sa0, 0, &ix.sa[c.x_lbIn + 1]);
         c.req = RQ_EXT_SA;
     } else if (c.req == RQ_LCE) {
-        c.x_p = c.l_o1; c.x_sa = c.l_o2;                 // the two SA indices
-        c.l_o1 = CG_LDG(&ix.sa[c.x_p]);
-        if (c.x_sa != c.x_p) c.l_o2 = CG_LDG(&ix.sa[c.x_sa]);
+        m.ld4(c.d.sa0, 0, &ix.sa[c.l_i1]);
+        if (c.l_i2 != c.l_i1) m.ld4(c.d.sa1, 1, &ix.sa[c.l_i2]);
         c.req = RQ_LCE_SA;
     } else if (c.req == RQ_TID) {
-        c.sa0 = CG_LDG(&ix.sa[c.e_c]);
-        if (c.e_c + 1 < c.e_end) c.sa1 = CG_LDG(&ix.sa[c.e_c + 1]);
-        if (c.e_c + 2 < c.e_end) c.sa2 = CG_LDG(&ix.sa[c.e_c + 2]);
-        if (c.e_c + 3 < c.e_end) c.sa3 = CG_LDG(&ix.sa[c.e_c + 3]);
+        m.ld4(c.d.sa0, 0, &ix.sa[c.e_c]);
+        if (c.e_c + 1 < c.e_end) m.ld4(c.d.sa1, 1, &ix.sa[c.e_c + 1]);
+        if (c.e_c + 2 < c.e_end) m.ld4(c.d.sa2, 2, &ix.sa[c.e_c + 2]);
+        if (c.e_c + 3 < c.e_end) m.ld4(c.d.sa3, 3, &ix.sa[c.e_c + 3]);
         c.req = RQ_TID_SA;
     }
 }
 
 // the three phases back to back (host emulation; the kernel interleaves them with warp meeting points)
-template <bool BSJ, class Sink>
-CG_HD void tsm_step(Ctx& c, const IndexView& ix, const TMem& m, int lceMode, Sink& sink) {
+template <bool BSJ, class M, class Sink>
+CG_HD void tsm_step(Ctx& c, const IndexView& ix, const M& m, int lceMode, Sink& sink) {
     if (tsm_complete(c, ix, m, lceMode)) tsm_control<BSJ>(c, ix, m, sink);
     tsm_issue(c, ix, m);
 }
@@ -591,7 +607,8 @@ CG_HD void tsm_step(Ctx& c, const IndexView& ix, const TMem& m, int lceMode, Sin
 struct NoSink { CG_HD void line(uint32_t, uint32_t, uint32_t, int, uint32_t) const {} };
 
 // reverse-complement strand from the forward words: word j = 32 bases from oriented position 32 j (ReadView::chunk(1, .))
-CG_HD void tsm_make_rc(const TMem& m, int L) {
+template <class M>
+CG_HD void tsm_make_rc(const M& m, int L) {
     for (int j = 0; j < m.W2; ++j) {
         int a = L - 32 - 32 * j;
         uint64_t v = 0;

@@ -414,11 +414,26 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
     const IndexView& ix = c_ix[X];
     Hits H; H.alive = false; H.tid = 0xffffffffu; H.ok = true; H.count = 0;
     if (n == 0) return H;
-    int mi = 0;
-    uint32_t msp = ints[0].end - ints[0].begin;
-    bool wide = msp > 32;
+    // An interval whose query range lies inside that of a longer interval of the same strand cannot change the hit
+    // set: every occurrence p of the longer match gives the occurrence p + (qpos' - qpos) of the shorter one in the
+    // same transcript, so tids(longer) is a subset of tids(shorter) and span(longer) <= span(shorter); the
+    // intersection over all intervals (intersectSAHits) equals the one over the maximal intervals.  Skip the rest.
+    bool drop = false;
+    if (lane < n) {
+        const int ql = ints[lane].qpos, ll = ints[lane].len;
 #pragma unroll 1
-    for (int i = 1; i < n; ++i) {
+        for (int y = 0; y < n; ++y) {
+            const int qy = ints[y].qpos, ly = ints[y].len;
+            drop |= (ly > ll && qy <= ql && qy + ly >= ql + ll);
+        }
+    }
+    const unsigned skipB = __ballot_sync(FULL, drop);
+    int mi = -1;
+    uint32_t msp = 0xffffffffu;
+    bool wide = false;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        if ((skipB >> i) & 1) continue;
         uint32_t sp = ints[i].end - ints[i].begin;
         if (sp > 32) wide = true;
         if (sp < msp) { msp = sp; mi = i; }
@@ -432,7 +447,7 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
     H.alive = have && (__ffs(same) - 1 == lane);
 #pragma unroll 1
     for (int x = 0; x < n; ++x) {
-        if (x == mi) continue;
+        if (x == mi || ((skipB >> x) & 1)) continue;
         const uint32_t ib = ints[x].begin, ie = ints[x].end;
         bool dup = (ib == mb && ie == me);                           // same positions: cannot drop a transcript
 #pragma unroll 1
