@@ -98,8 +98,11 @@ __device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) 
 // K2-K6: one warp per mate (persistent warps, grid-stride).
 //   GEN = false: over all n mates, state in shared memory; ovf[r] = 1 hands the mate to the general kernel
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
+#ifndef CG_WARP_MINB
+#define CG_WARP_MINB 4     // resident blocks per SM asked of the fast warp kernels: 64 registers, 32 warps per SM (the kernels are latency-bound)
+#endif
 template <bool GEN, bool LIST>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? 1 : CG_WARP_MINB)
 k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
           uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
@@ -114,6 +117,7 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
         const uint64_t r = LIST ? (uint64_t)list[x] : x;
         int L = lens[r];
         int pairLen = lens[r & ~1ULL];             // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+        if ((CG_OPT_PF & 4) && !LIST && x + nwarps < n && lane * 4 < g.WT) cgw::prefetch_l2(pk + (x + nwarps) * (uint64_t)g.WT + lane * 4);   // this warp's next read
         cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
         bool found, ok; int nF, nR;
         const Interval* fwd; const Interval* rc;
@@ -280,7 +284,7 @@ struct BsjOut {
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
 // do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes.
 template <bool GEN, bool LIST>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? 1 : CG_WARP_MINB)
 k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
            const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
            int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch) {

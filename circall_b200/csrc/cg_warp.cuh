@@ -22,6 +22,13 @@
 #pragma once
 #include "cg_core.cuh"
 
+#ifndef CG_OPT_TWOBLOCK
+#define CG_OPT_TWOBLOCK 0     // load the next text block together with the current one in w_match: measured slower (registers)
+#endif
+#ifndef CG_OPT_PF
+#define CG_OPT_PF 1           // bit0: transcript-id half of a candidate's block (kept); bit1: last k-mer's slots, bit2: next read (measured slower)
+#endif
+
 namespace cgw {
 using namespace cg;
 
@@ -76,20 +83,35 @@ __device__ __noinline__ Hit w_probe(uint64_t key, bool active) {
 }
 
 // query-vs-suffix comparison (cg::match_run): returns 4 * matched length + (ord + 1)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 template <int X>
 __device__ __noinline__ int w_match(RV r, int s, int qstart, uint32_t p, int i, int lim) {
     const IndexView& ix = c_ix[X];
-    uint32_t curb = 0xffffffffu;
-    uint64_t c0 = 0, c1 = 0, tmk = 0;
+    uint32_t curb = 0xffffffffu, nxb = 0xffffffffu;
+    uint64_t c0 = 0, c1 = 0, tmk = 0, n0 = 0, n1 = 0, nmk = 0;
     while (i < lim) {
         uint32_t tp = p + (uint32_t)i;
         uint32_t b = tp >> 6;
         if (b != curb) {
-            u32x4 a = __ldg(&ix.text[2 * (uint64_t)b]);
-            u32x4 c = __ldg(&ix.text[2 * (uint64_t)b + 1]);
-            c0 = (uint64_t)a.x | ((uint64_t)a.y << 32); c1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-            tmk = (uint64_t)c.x | ((uint64_t)c.y << 32);
+            if (b == nxb) { c0 = n0; c1 = n1; tmk = nmk; }
+            else {
+                u32x4 a = __ldg(&ix.text[2 * (uint64_t)b]);
+                u32x4 c = __ldg(&ix.text[2 * (uint64_t)b + 1]);
+                c0 = (uint64_t)a.x | ((uint64_t)a.y << 32); c1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+                tmk = (uint64_t)c.x | ((uint64_t)c.y << 32);
+            }
             curb = b;
+            // the block after this one goes out now when the compared range reaches into it: its latency
+            // overlaps this block's load / comparison instead of following it
+            nxb = 0xffffffffu;
+            if (CG_OPT_TWOBLOCK && (int)(tp & 63) + (lim - i) > 64) {
+                u32x4 a = __ldg(&ix.text[2 * (uint64_t)b + 2]);
+                u32x4 c = __ldg(&ix.text[2 * (uint64_t)b + 3]);
+                n0 = (uint64_t)a.x | ((uint64_t)a.y << 32); n1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+                nmk = (uint64_t)c.x | ((uint64_t)c.y << 32);
+                nxb = b + 1;
+            }
         }
         int half = (tp >> 5) & 1, o5 = tp & 31;
         uint64_t tw = (half ? c1 : c0) >> (2 * o5);
@@ -131,7 +153,11 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
     if (w == 0) { o.lb = ubIn; o.ub = ubIn; o.len = startAt; return o; }        // empty open interval
     if (w <= 32) {
         int l = -1;
-        if ((uint32_t)lane < w) l = w_match<X>(r, s, qstart, __ldg(&ix.sa[lbIn + 1 + lane]), startAt, m) >> 2;
+        if ((uint32_t)lane < w) {
+            const uint32_t p = __ldg(&ix.sa[lbIn + 1 + lane]);
+            if (CG_OPT_PF & 1) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);       // transcript-id half of the block of p, for the hit enumeration
+            l = w_match<X>(r, s, qstart, p, startAt, m) >> 2;
+        }
         int best = __reduce_max_sync(FULL, l);
         unsigned mk = __ballot_sync(FULL, l == best);
         o.lb = lbIn + 1 + (uint32_t)(__ffs(mk) - 1);
@@ -252,6 +278,12 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
     nF = nR = 0; found = false;
     int nKS = 0;
     bool ovf = false;
+    // the forced last look-up (:300-321) probes the k-mer at L - k and its reverse complement: start those two
+    // sectors on their way now
+    if ((CG_OPT_PF & 2) && L > k && lane < 2 && !rv.anyN) {
+        const uint64_t mer = w_chunk(rv, 0, L - k) & kmask(k);
+        prefetch_l2(&c_ix[X].hslots[home_slot(c_ix[X], lane ? revcomp(mer, k) : mer)]);
+    }
     uint32_t fwdHit = 0, rcHit = 0;
     uint32_t lbF = 0, ubF = 0;
     int matched = 0;
