@@ -1,0 +1,192 @@
+// circall_b200 — host side of the drop-in executables: read-pair streaming and the reference's output files.
+//
+// What it mirrors (paths relative to Circall_v1.0.1/ in datngu/Circall):
+//   PairStream        pair_sequence_parser<char**> as Circall_wt.cpp:87,1197-1200 uses it: FASTA or FASTQ,
+//                     detected per file from its first byte; header = the whole line after '>' / '@' (spaces kept,
+//                     the R stage matches on it); any number of files per mate, read strictly sequentially so that
+//                     FIFOs (`<(gunzip -c x.fa.gz)`, Circall_source.sh:273) work.
+//   write_* helpers   the record formats of SURVEY Appendix C (Circall_wt.cpp:352-363,526-538; Circall_bsj.cpp:339-341,
+//                     366-368,392-399; ExportFeq.cpp:81-103).
+// Header-only, no CUDA: the CPU tests drive it through `circall_gpu parse`.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace cgh {
+
+// one mate file list, read record by record
+class SeqStream {
+public:
+    explicit SeqStream(std::vector<std::string> files) : files_(std::move(files)) {}
+    ~SeqStream() { if (f_) fclose(f_); }
+    // next record; false at the end of the last file.  Throws std::string on a malformed file.
+    bool next(std::string& header, std::string& seq) {
+        for (;;) {
+            if (!f_) {
+                if (fi_ >= files_.size()) return false;
+                f_ = fopen(files_[fi_].c_str(), "rb");
+                if (!f_) throw std::string("cannot open ") + files_[fi_];
+                ++fi_;
+                kind_ = 0; have_line_ = false;
+            }
+            if (read_record(header, seq)) return true;
+            fclose(f_); f_ = nullptr;
+        }
+    }
+
+private:
+    bool getline(std::string& s) {
+        if (have_line_) { s.swap(line_); have_line_ = false; return true; }
+        s.clear();
+        int c;
+        bool any = false;
+        while ((c = getc_unlocked(f_)) != EOF) {
+            any = true;
+            if (c == '\n') break;
+            s.push_back((char)c);
+        }
+        if (!any) return false;
+        if (!s.empty() && s.back() == '\r') s.pop_back();
+        return true;
+    }
+    void unget(std::string& s) { line_.swap(s); have_line_ = true; }
+    bool read_record(std::string& header, std::string& seq) {
+        std::string l;
+        do { if (!getline(l)) return false; } while (l.empty());
+        if (kind_ == 0) {
+            if (l[0] == '>') kind_ = 1; else if (l[0] == '@') kind_ = 2;
+            else throw std::string("neither FASTA nor FASTQ: ") + files_[fi_ - 1];
+        }
+        if (l[0] != (kind_ == 1 ? '>' : '@')) throw std::string("malformed record in ") + files_[fi_ - 1];
+        header.assign(l, 1, std::string::npos);
+        seq.clear();
+        if (kind_ == 1) {
+            while (getline(l)) {
+                if (!l.empty() && l[0] == '>') { unget(l); break; }
+                seq += l;
+            }
+        } else {
+            if (!getline(seq)) throw std::string("truncated FASTQ record in ") + files_[fi_ - 1];
+            std::string plus, qual;
+            if (!getline(plus) || plus.empty() || plus[0] != '+' || !getline(qual)) throw std::string("truncated FASTQ record in ") + files_[fi_ - 1];
+        }
+        return true;
+    }
+    std::vector<std::string> files_;
+    size_t fi_ = 0;
+    FILE* f_ = nullptr;
+    int kind_ = 0;
+    std::string line_;
+    bool have_line_ = false;
+};
+
+// one batch of read pairs in the layout cg_session_submit takes (bases back to back + n + 1 offsets per mate)
+struct Batch {
+    char* b1 = nullptr; char* b2 = nullptr;            // caller-provided (pinned) buffers of `cap` bytes each
+    uint64_t cap = 0;
+    std::vector<uint64_t> off1, off2;
+    std::vector<std::string> h1, h2;
+    uint64_t n = 0;
+    void clear() { off1.assign(1, 0); off2.assign(1, 0); h1.clear(); h2.clear(); n = 0; }
+    const char* seq1(uint64_t i) const { return b1 + off1[i]; }
+    const char* seq2(uint64_t i) const { return b2 + off2[i]; }
+    size_t len1(uint64_t i) const { return (size_t)(off1[i + 1] - off1[i]); }
+    size_t len2(uint64_t i) const { return (size_t)(off2[i + 1] - off2[i]); }
+};
+
+class PairStream {
+public:
+    PairStream(std::vector<std::string> f1, std::vector<std::string> f2) : s1_(std::move(f1)), s2_(std::move(f2)) {}
+    // fill b with up to max_pairs pairs (fewer when a buffer is full); false when nothing is left
+    bool fill(Batch& b, uint64_t max_pairs) {
+        b.clear();
+        while (b.n < max_pairs) {
+            if (!pending_) {
+                bool a = s1_.next(ph1_, ps1_), c = s2_.next(ph2_, ps2_);
+                if (a != c) throw std::string("the two mate files hold different numbers of records");
+                if (!a) break;
+                pending_ = true;
+            }
+            if (ps1_.size() > b.cap || ps2_.size() > b.cap) throw std::string("a read is longer than the staging buffer");
+            if (b.off1.back() + ps1_.size() > b.cap || b.off2.back() + ps2_.size() > b.cap) break;
+            memcpy(b.b1 + b.off1.back(), ps1_.data(), ps1_.size());
+            memcpy(b.b2 + b.off2.back(), ps2_.data(), ps2_.size());
+            b.off1.push_back(b.off1.back() + ps1_.size());
+            b.off2.push_back(b.off2.back() + ps2_.size());
+            b.h1.push_back(ph1_); b.h2.push_back(ph2_);
+            ++b.n;
+            pending_ = false;
+        }
+        return b.n > 0;
+    }
+
+private:
+    SeqStream s1_, s2_;
+    std::string ph1_, ph2_, ps1_, ps2_;
+    bool pending_ = false;
+};
+
+inline void put_record(FILE* f, const std::string& header_with_marker, const char* seq, size_t len) {
+    fwrite(header_with_marker.data(), 1, header_with_marker.size(), f);
+    fputc('\n', f);
+    fwrite(seq, 1, len, f);
+    fputc('\n', f);
+}
+
+// The fragment-length prior nobody updates in Circall_wt / Circall_bsj: getNormalFragLengthCounts
+// (Circall_bsj.cpp:832-861: mean 200, sd 80, 10 000 samples over 1000 bins) and the conditional means behind
+// computeSmoothedEffectiveLengths (:977-1006).  These columns are constants of a run and not read downstream.
+struct FragPrior {
+    std::vector<int> counts;
+    std::vector<double> cond_mean;
+    double median = 0, mean = 0, sd = 0;
+    FragPrior(int maxLen = 1000, int samples = 10000, double mu = 200.0, double sigma = 80.0) : counts(maxLen, 0), cond_mean(maxLen, 0.0) {
+        auto kernel = [&](double p) { double inv = 1.0 / sigma, x = inv * (p - mu); return std::exp(-0.5 * x * x) * inv; };
+        double mass = 0;
+        for (int i = 0; i < maxLen; ++i) mass += kernel(i);
+        for (int i = 0; i < maxLen; ++i) counts[i] = (int)std::round(kernel(i) * samples / mass);
+        double tot = 0, s1 = 0;
+        for (int i = 0; i < maxLen; ++i) { tot += counts[i]; s1 += (double)counts[i] * i; }
+        mean = tot > 0 ? s1 / tot : 0;
+        double s2 = 0, cum = 0;
+        bool med = false;
+        for (int i = 0; i < maxLen; ++i) {
+            s2 += counts[i] * (i - mean) * (i - mean);
+            cum += counts[i];
+            if (!med && cum >= tot / 2) { median = i; med = true; }
+        }
+        sd = tot > 0 ? std::sqrt(s2 / tot) : 0;
+        double cm = 0, cd = 0;
+        for (int i = 0; i < maxLen; ++i) {
+            cm += (double)counts[i] * i; cd += counts[i];
+            cond_mean[i] = cd > 0 ? cm / cd : 0.0;
+        }
+    }
+    double effective_length(uint32_t refLen) const {
+        int maxLen = (int)cond_mean.size();
+        double cf = (int)refLen >= maxLen ? cond_mean[maxLen - 1] : cond_mean[refLen];
+        double e = (double)refLen - cf + 1.0;
+        return e < 1.0 ? (double)refLen : e;
+    }
+};
+
+// fragmentInfo.txt, paired-end form (ExportFeq.cpp:81-82)
+inline bool write_fragment_info(const std::string& path, uint32_t readlen, const FragPrior& fp, uint64_t observed, uint64_t mapped, uint64_t hits, int k) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return false;
+    fprintf(f, "readlen\tfragLengthMedian\tfragLengthMean\tfragLengthSd\tnumObservedFragments\tnumMappedFragments\tnumHits\tkmer\n");
+    fprintf(f, "%u\t%g\t%g\t%g\t%llu\t%llu\t%llu\t%d\n", readlen, fp.median, fp.mean, fp.sd, (unsigned long long)observed, (unsigned long long)mapped,
+            (unsigned long long)hits, k);
+    fclose(f);
+    return true;
+}
+
+// equivalence classes accumulated over the batches of a run: key = ascending transcript ids (EquivalenceClassBuilder.hpp:112-130)
+typedef std::map<std::vector<uint32_t>, uint64_t> EqClasses;
+
+}  // namespace cgh

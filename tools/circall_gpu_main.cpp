@@ -1,0 +1,273 @@
+// circall_b200 — drop-in executables over libcircall_gpu.so (C ABI, include/circall_gpu.h).
+//
+// One binary, dispatched on its name (or on the first argument):
+//   Circall_wt   -i TXINDEX  -1 R1.. -2 R2.. -o OUT [-p N] [--gpu D]      src/Circall_wt.cpp main :1415-1739, called at Circall_source.sh:273
+//   Circall_bsj  -i BSJINDEX -1 U1.. -2 U2.. -o OUT [-p N] [--gpu D]      src/Circall_bsj.cpp,         called at Circall_source.sh:291
+//   TxIndexer    -t FASTA -o INDEX [-k 31] [-f]                           src/TxIndexer.cpp:81-94,192-227
+//   circall_gpu fused -i TXINDEX -b BSJINDEX -1 .. -2 .. -o OUTWT -O OUTBSJ   (extension: both steps in one pass, no
+//                intermediate Unmapped_readM_{1,2}.fa; the two output directories receive what the two tools write)
+//   circall_gpu parse -1 .. -2 ..          (no GPU: parses the inputs and prints record counts; used by the CPU tests)
+// Options of the reference that do not apply (-l libtype, bias flags, ...) are accepted and ignored; a value that
+// follows an unknown option is skipped.  Errors go to stderr and exit(1) like the reference (Circall_wt.cpp:1726-1737).
+//
+// The host side streams the reads into two page-locked staging buffers and alternates two sessions, so the copy
+// and the kernels of one batch overlap the parsing and output writing of the other.
+#include <algorithm>
+#include <cstdlib>
+#include <sys/stat.h>
+#include "../include/circall_gpu.h"
+#include "cg_host_io.hpp"
+
+namespace {
+
+[[noreturn]] void die(const std::string& m) { fprintf(stderr, "[circall_gpu] error: %s\n", m.c_str()); exit(1); }
+void ck(int rc, const char* what) { if (rc) die(std::string(what) + ": " + cg_last_error()); }
+
+struct Args {
+    std::string index, bsj_index, out, out_bsj, fasta;
+    std::vector<std::string> m1, m2;
+    int k = 31, gpu = 0, threads = 4, lce = 0;
+    uint64_t batch = 1u << 20;
+    bool force = false;
+};
+
+Args parse_args(int argc, char** argv, int first) {
+    Args a;
+    for (int i = first; i < argc; ++i) {
+        std::string o = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value after " + o); return argv[++i]; };
+        auto vals = [&](std::vector<std::string>& dst) { while (i + 1 < argc && argv[i + 1][0] != '-') dst.push_back(argv[++i]); if (dst.empty()) die("missing value after " + o); };
+        if (o == "-i" || o == "--index") a.index = val();
+        else if (o == "-b" || o == "--bsjindex") a.bsj_index = val();
+        else if (o == "-1" || o == "--mates1") vals(a.m1);
+        else if (o == "-2" || o == "--mates2") vals(a.m2);
+        else if (o == "-o" || o == "--output" || o == "--out") a.out = val();
+        else if (o == "-O" || o == "--output-bsj") a.out_bsj = val();
+        else if (o == "-p" || o == "--threads") a.threads = atoi(val().c_str());
+        else if (o == "-t" || o == "--transcripts") a.fasta = val();
+        else if (o == "-k" || o == "--kmerSize") a.k = atoi(val().c_str());
+        else if (o == "-f" || o == "--force") a.force = true;
+        else if (o == "--gpu") a.gpu = atoi(val().c_str());
+        else if (o == "--batch") a.batch = strtoull(val().c_str(), nullptr, 10);
+        else if (o == "--lce-mode") a.lce = atoi(val().c_str());
+        else if (o.size() > 1 && o[0] == '-') { if (i + 1 < argc && argv[i + 1][0] != '-') ++i; }   // accepted and ignored
+        else die("unexpected argument " + o);
+    }
+    return a;
+}
+
+void make_dir(const std::string& d) {
+    if (d.empty()) die("no output directory given (-o)");
+    std::string cur;
+    for (size_t i = 0; i <= d.size(); ++i) {
+        if (i == d.size() || d[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0777); }
+        if (i < d.size()) cur.push_back(d[i]);
+    }
+    struct stat st;
+    if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) die("cannot create directory " + d);
+}
+FILE* open_append(const std::string& path) {            // "a": outputs accumulate across runs, as in the reference (Circall_wt.cpp:231)
+    FILE* f = fopen(path.c_str(), "a");
+    if (!f) die("cannot open " + path);
+    static std::vector<std::vector<char>> bufs;
+    bufs.emplace_back(1 << 22);
+    setvbuf(f, bufs.back().data(), _IOFBF, bufs.back().size());
+    return f;
+}
+
+struct Outputs {
+    // wt directory
+    FILE* un1 = nullptr; FILE* un2 = nullptr;
+    // bsj directory
+    FILE* jt = nullptr; FILE* c1 = nullptr; FILE* c2 = nullptr;
+    cgh::EqClasses eq;
+};
+
+const char* SUF1[3] = {"", "___11", "___21"};     // header suffix of the record written to UN_read1 (mate code 1 / 2)
+const char* SUF2[3] = {"", "___22", "___12"};
+
+// write what one fetched batch produced.  stage 1: wt files; stage 2: bsj files (rec = pair); stage 0: both
+void emit(int stage, const cgh::Batch& B, const cg_batch_result& r, const cg_index* bsj, Outputs& o) {
+    auto first_seq = [&](uint64_t rec, const char*& s, size_t& n, const char*& s2, size_t& n2, std::string& hA, std::string& hB) {
+        // the (header, sequence) pair Circall_bsj sees for export record `rec`
+        if (stage == 2) { s = B.seq1(rec); n = B.len1(rec); s2 = B.seq2(rec); n2 = B.len2(rec); hA = ">" + B.h1[rec]; hB = ">" + B.h2[rec]; return; }
+        uint32_t i = r.exp_pair[rec]; int code = r.exp_code[rec];
+        hA = ">" + B.h1[i] + SUF1[code]; hB = ">" + B.h1[i] + SUF2[code];      // both use mate 1's header (Circall_wt.cpp:526-527)
+        if (code == 1) { s = B.seq1(i); n = B.len1(i); s2 = B.seq2(i); n2 = B.len2(i); }
+        else { s = B.seq2(i); n = B.len2(i); s2 = B.seq1(i); n2 = B.len1(i); }
+    };
+    const char *s, *s2; size_t n, n2; std::string hA, hB;
+    if (stage != 2 && o.un1) {
+        for (uint64_t k = 0; k < r.n_export; ++k) {                              // Circall_wt.cpp:350-365,525-540
+            first_seq(k, s, n, s2, n2, hA, hB);
+            cgh::put_record(o.un1, hA, s, n);
+            cgh::put_record(o.un2, hB, s2, n2);
+        }
+    }
+    if (stage != 1) {
+        for (uint64_t k = 0; k < r.n_junc; ++k) {                                // Circall_bsj.cpp:339-341,366-368
+            const cg_junction& j = r.junc[k];
+            first_seq(j.rec, s, n, s2, n2, hA, hB);
+            fprintf(o.jt, "%s\t%u\t%u\t%u\t%d\t%s\t%u\n", hA.c_str(), j.dir, j.query_pos, j.len, j.hit_pos, cg_index_tx_name(bsj, j.tid), cg_index_tx_len(bsj, j.tid));
+        }
+        for (uint64_t k = 0; k < r.n_cand; ++k) {                                // Circall_bsj.cpp:392-399
+            first_seq(r.cand_rec[k], s, n, s2, n2, hA, hB);
+            cgh::put_record(o.c1, hA, s, n);
+            cgh::put_record(o.c2, hB, s2, n2);
+        }
+        for (uint64_t c = 0; c < r.n_eq; ++c)                                    // multi-transcript classes (single ones are counted on the device)
+            ++o.eq[std::vector<uint32_t>(r.eq_tids + r.eq_off[c], r.eq_tids + r.eq_off[c + 1])];
+    }
+}
+
+int run_mapper(int stage, const Args& a) {
+    if (a.m1.empty() || a.m2.empty()) die("both -1 and -2 are required (paired-end reads)");
+    int nd = 0;
+    cg_device_count(&nd);
+    if (nd == 0) die("no CUDA device: libcircall_gpu has no CPU path");
+    cg_index *tx = nullptr, *bsj = nullptr;
+    if (stage != 2) ck(cg_index_open(a.index.c_str(), a.gpu, &tx), "opening the transcript index");
+    if (stage != 1) ck(cg_index_open((stage == 2 ? a.index : a.bsj_index).c_str(), a.gpu, &bsj), "opening the BSJ index");
+    const std::string out_wt = a.out, out_bsj = stage == 0 ? a.out_bsj : a.out;
+    Outputs o;
+    const std::string tag = std::to_string(1804289383);          // std::rand() without srand (Circall_wt.cpp:228): any unique tag works
+    if (stage != 2) { make_dir(out_wt); o.un1 = open_append(out_wt + "/UN_read1_" + tag + ".fa"); o.un2 = open_append(out_wt + "/UN_read2_" + tag + ".fa"); }
+    if (stage != 1) {
+        make_dir(out_bsj);
+        o.jt = open_append(out_bsj + "/UN_read1_" + tag + ".fa");
+        o.c1 = open_append(out_bsj + "/BSJ_read1_" + tag + ".fa"); o.c2 = open_append(out_bsj + "/BSJ_read2_" + tag + ".fa");
+    }
+    cg_opts opts; memset(&opts, 0, sizeof opts);
+    opts.lce_mode = a.lce; opts.stage = stage; opts.max_batch_pairs = (uint32_t)a.batch;
+    cg_session* S[2] = {nullptr, nullptr};
+    cgh::Batch B[2];
+    const uint64_t cap = std::max<uint64_t>(a.batch * 160, 1u << 20);
+    for (int x = 0; x < 2; ++x) {
+        ck(cg_session_create(tx, bsj, &opts, &S[x]), "creating a session");
+        void *p1, *p2;
+        ck(cg_host_alloc(cap, &p1), "allocating pinned memory"); ck(cg_host_alloc(cap, &p2), "allocating pinned memory");
+        B[x].b1 = (char*)p1; B[x].b2 = (char*)p2; B[x].cap = cap;
+    }
+    cgh::PairStream in(a.m1, a.m2);
+    uint64_t pairs = 0;
+    int cur = 0;
+    bool pending[2] = {false, false};
+    auto finish = [&](int x) {
+        cg_batch_result r;
+        ck(cg_session_fetch(S[x], 1, &r), "mapping a batch");
+        emit(stage, B[x], r, bsj, o);
+        pending[x] = false;
+    };
+    try {
+        for (;;) {
+            if (pending[cur]) finish(cur);
+            if (!in.fill(B[cur], a.batch)) break;
+            ck(cg_session_submit(S[cur], B[cur].b1, B[cur].off1.data(), B[cur].b2, B[cur].off2.data(), B[cur].n), "submitting a batch");
+            pending[cur] = true;
+            pairs += B[cur].n;
+            cur ^= 1;
+        }
+    } catch (const std::string& e) { die(e); }
+    for (int x = 0; x < 2; ++x) if (pending[x ^ cur]) finish(x ^ cur);
+
+    // totals of the two sessions -> fragmentInfo.txt / rawCount.txt (ExportFeq.cpp:46-105)
+    cg_index_info bi; memset(&bi, 0, sizeof bi);
+    if (bsj) cg_index_get_info(bsj, &bi);
+    std::vector<uint64_t> per(bi.n_tx, 0), tmp(bi.n_tx, 0);
+    cg_counters tot; memset(&tot, 0, sizeof tot);
+    for (int x = 0; x < 2; ++x) {
+        cg_counters c;
+        ck(cg_session_counters(S[x], &c, bsj ? tmp.data() : nullptr, bsj ? bi.n_tx : 0), "reading the counters");
+        tot.wt_num_observed += c.wt_num_observed; tot.wt_num_mapped += c.wt_num_mapped; tot.wt_num_hits += c.wt_num_hits;
+        tot.bsj_num_observed += c.bsj_num_observed; tot.bsj_num_mapped += c.bsj_num_mapped; tot.bsj_num_hits += c.bsj_num_hits;
+        if (!tot.wt_read_len) tot.wt_read_len = c.wt_read_len;
+        if (!tot.bsj_read_len) tot.bsj_read_len = c.bsj_read_len;
+        for (uint32_t t = 0; t < bi.n_tx; ++t) per[t] += tmp[t];
+    }
+    cgh::FragPrior fp;
+    cg_index_info ti; memset(&ti, 0, sizeof ti);
+    if (tx) cg_index_get_info(tx, &ti);
+    if (stage != 2 && !cgh::write_fragment_info(out_wt + "/fragmentInfo.txt", tot.wt_read_len, fp, tot.wt_num_observed, tot.wt_num_mapped, tot.wt_num_hits, ti.k))
+        die("cannot write fragmentInfo.txt");
+    if (stage != 1) {
+        if (!cgh::write_fragment_info(out_bsj + "/fragmentInfo.txt", tot.bsj_read_len, fp, tot.bsj_num_observed, tot.bsj_num_mapped, tot.bsj_num_hits, bi.k))
+            die("cannot write fragmentInfo.txt");
+        FILE* f = fopen((out_bsj + "/rawCount.txt").c_str(), "w");
+        if (!f) die("cannot write rawCount.txt");
+        fprintf(f, "Transcript\tWeight\tCount\teffLens\tRefLength\tEffectiveLength\teqClass\n");       // ExportFeq.cpp:88
+        uint32_t cls = 0;
+        auto row = [&](uint32_t t, double w, uint64_t n) {
+            uint32_t len = cg_index_tx_len(bsj, t);
+            double e = fp.effective_length(len);
+            fprintf(f, "%s\t%g\t%llu\t%g\t%u\t%g\t%u\n", cg_index_tx_name(bsj, t), w, (unsigned long long)n, e, len, e, cls);
+        };
+        for (uint32_t t = 0; t < bi.n_tx; ++t) if (per[t]) { ++cls; row(t, 1.0, per[t]); }
+        for (auto& kv : o.eq) { ++cls; for (uint32_t t : kv.first) row(t, 1.0 / (double)kv.first.size(), kv.second); }   // weights 1/classSize (EquivalenceClassBuilder.hpp:32-40)
+        fclose(f);
+    }
+    for (FILE* f : {o.un1, o.un2, o.jt, o.c1, o.c2}) if (f) fclose(f);
+    fprintf(stderr, "[circall_gpu] %llu pairs", (unsigned long long)pairs);
+    if (stage != 2) fprintf(stderr, "; wt: observed %llu mapped %llu hits %llu", (unsigned long long)tot.wt_num_observed, (unsigned long long)tot.wt_num_mapped, (unsigned long long)tot.wt_num_hits);
+    if (stage != 1) fprintf(stderr, "; bsj: observed %llu mapped %llu hits %llu", (unsigned long long)tot.bsj_num_observed, (unsigned long long)tot.bsj_num_mapped, (unsigned long long)tot.bsj_num_hits);
+    fprintf(stderr, "\n");
+    for (int x = 0; x < 2; ++x) { cg_session_destroy(S[x]); cg_host_free(B[x].b1); cg_host_free(B[x].b2); }
+    if (tx) cg_index_close(tx);
+    if (bsj) cg_index_close(bsj);
+    return 0;
+}
+
+int run_indexer(const Args& a) {
+    if (a.fasta.empty() || a.out.empty()) die("usage: TxIndexer -t transcripts.fa -o indexDir [-k 31] [-f]");
+    struct stat st;
+    if (!a.force && stat((a.out + "/header.json").c_str(), &st) == 0) {          // TxIndexer.cpp:192-200
+        fprintf(stderr, "[circall_gpu] index %s exists (use -f to rebuild)\n", a.out.c_str());
+        return 0;
+    }
+    make_dir(a.out);
+    cg_index* idx = nullptr;
+    ck(cg_index_build_fasta(a.gpu, a.fasta.c_str(), a.k, &idx), "building the index");
+    ck(cg_index_save(idx, a.out.c_str()), "writing the index");
+    cg_index_info i;
+    cg_index_get_info(idx, &i);
+    fprintf(stderr, "[circall_gpu] indexed %u sequences, %llu characters, %llu distinct %d-mers in %.2f s\n", i.n_tx, (unsigned long long)i.text_len,
+            (unsigned long long)i.n_kmers, i.k, i.build_seconds);
+    cg_index_close(idx);
+    return 0;
+}
+
+int run_parse(const Args& a) {
+    cgh::Batch B;
+    std::vector<char> b1(1 << 24), b2(1 << 24);
+    B.b1 = b1.data(); B.b2 = b2.data(); B.cap = b1.size();
+    cgh::PairStream in(a.m1, a.m2);
+    uint64_t pairs = 0, bases = 0, hsum = 0;
+    try {
+        while (in.fill(B, a.batch)) {
+            pairs += B.n; bases += B.off1.back() + B.off2.back();
+            for (uint64_t i = 0; i < B.n; ++i) { for (char c : B.h1[i]) hsum = hsum * 131 + (unsigned char)c; for (char c : B.h2[i]) hsum = hsum * 131 + (unsigned char)c; }
+        }
+    } catch (const std::string& e) { die(e); }
+    printf("pairs %llu bases %llu headers %llu\n", (unsigned long long)pairs, (unsigned long long)bases, (unsigned long long)hsum);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string me = argv[0];
+    size_t sl = me.find_last_of('/');
+    if (sl != std::string::npos) me = me.substr(sl + 1);
+    int first = 1;
+    std::string cmd;
+    if (me == "Circall_wt") cmd = "wt";
+    else if (me == "Circall_bsj") cmd = "bsj";
+    else if (me == "TxIndexer") cmd = "index";
+    else { if (argc < 2) die("usage: circall_gpu {wt|bsj|fused|index|parse} options..."); cmd = argv[1]; first = 2; }
+    Args a = parse_args(argc, argv, first);
+    if (cmd == "wt") return run_mapper(1, a);
+    if (cmd == "bsj") return run_mapper(2, a);
+    if (cmd == "fused") { if (a.bsj_index.empty() || a.out_bsj.empty()) die("fused needs -b BSJINDEX and -O OUTBSJ"); return run_mapper(0, a); }
+    if (cmd == "index") return run_indexer(a);
+    if (cmd == "parse") return run_parse(a);
+    die("unknown command " + cmd);
+}
