@@ -8,7 +8,7 @@ A *step* is one pass of the hot path over the whole synthetic workload (BASELINE
 hg19-scale synthetic transcriptome + BSJ index, 20 M 2x100 bp pairs per GPU), issued to the library in
 batches.  Three legs are measured by the default arm:
   value        inputs resident in HBM, device-timed bracket around K steps
-  e2e          the same work through the C ABI with HOST (pinned) buffers: host->device copies of the reads
+  e2e          the same work through the C ABI with HOST (pinned) buffers (three sessions in rotation): host->device copies of the reads
                and device->host copies of the result lists are inside the timed region
   cpu_baseline the oracle (CPU restatement of the reference algorithm) on a bounded sample, rank 0, N = 1
 `--impl reference` times only the CPU restatement (the reference binary cannot be built here).
@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=400_000, help="pairs per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
+    ap.add_argument("--sessions", type=int, default=3, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
@@ -263,7 +264,8 @@ def main():
     # ---- end to end through the C ABI from pinned host buffers, two sessions so copies overlap kernels
     e2e = None
     if not args.no_e2e:
-        SS = [S, cg.Session(gtx, gbsj, stage=0)]
+        SS = [S] + [cg.Session(gtx, gbsj, stage=0) for _ in range(max(1, args.sessions) - 1)]
+        NS = len(SS)
         h2d = 2 * n * L + 2 * len(batches) * off.nbytes
         d2h = [0]
 
@@ -271,8 +273,8 @@ def main():
             pend = []
             tot = 0
             for i, (b0, nb) in enumerate(batches):
-                s = SS[i % 2]
-                if len(pend) == 2:
+                s = SS[i % NS]
+                if len(pend) == NS:
                     B = pend.pop(0).fetch(want_lists=True, materialize=False)
                     tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
                 s.submit_raw(pin1.ptr + b0 * L, pinoff.ptr, pin2.ptr + b0 * L, pinoff.ptr, nb)
@@ -288,8 +290,9 @@ def main():
             step_host()
         dte = bracket(step_host, args.steps)
         e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": 2}
-        SS[1].close()
+               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS}
+        for x in SS[1:]:
+            x.close()
 
     # ---- cpu baseline + algorithmic bytes from the oracle's counters (rank 0, N = 1 only)
     cpu = None
