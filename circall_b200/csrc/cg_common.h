@@ -28,6 +28,7 @@ struct cg_index {
         v.text = d_text; v.sa = d_sa; v.hslots = d_hslots; v.hmask = hcap - 1; v.offsets = d_offsets;
         v.hshift = 64; for (uint64_t c = hcap; c > 1; c >>= 1) --v.hshift;
         v.n = (uint32_t)n; v.n_tx = n_tx; v.k = k;
+        v.km = cg::kmask(k); v.km3 = v.km / 3;
         return v;
     }
 };

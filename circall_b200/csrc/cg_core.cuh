@@ -95,6 +95,8 @@ struct IndexView {
     uint32_t n;               // text length (last character is '$')
     uint32_t n_tx;
     int k;
+    uint64_t km;              // kmask(k)
+    uint64_t km3;             // kmask(k) / 3: a homopolymer word is (w & 3) * km3
 };
 
 struct TB { uint64_t c0, c1, mask; uint32_t tid0, start0; };
@@ -237,6 +239,7 @@ CG_HD uint64_t kmask(int k) { return (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1)
 
 CG_HD uint64_t revcomp(uint64_t w, int k) { return (rc64(w) >> (64 - 2 * k)) & kmask(k); }
 CG_HD bool homopolymer(uint64_t w, int k) { return w == (w & 3) * (kmask(k) / 3); }
+CG_HD bool homopolymer_ix(uint64_t w, const IndexView& ix) { return w == (w & 3) * ix.km3; }
 
 // forward-strand k-mer word at pos; when the window holds a non-ACGT base the word is cut at the
 // first one and the rest is zero ('A'), which is how the oracle defines Jellyfish's

@@ -47,7 +47,7 @@ typedef cgw::WStateT<cgw::GEN_FI, cgw::GEN_FK> GenState;
 static const size_t GEN_SCRATCH = ((sizeof(GenState) + 15) / 16) * 16 + 2 * (cgw::WSCR * 4 + cgw::WSCR) + 2 * cgw::WSCR * 4;
 // shared-memory bytes of one warp: read view words (+ the fast kernels' collector state, + 64 transcript ids for bsj)
 __host__ __device__ inline int warp_smem_bytes(const PackGeom& g, bool gen, bool bsj) {
-    return (g.W2f + 1 + g.WMf + 1) * 8 + (gen ? 0 : (int)sizeof(FastState) + (bsj ? 64 * 4 : 0));
+    return (2 * (g.W2f + 1) + g.WMf + 1) * 8 + (gen ? 0 : (int)sizeof(FastState) + (bsj ? 64 * 4 : 0));
 }
 // stage the packed read of this warp into shared memory
 __device__ __forceinline__ cgw::RV warp_view(const uint64_t* __restrict__ rec, const PackGeom& g, int L, uint64_t* dst, int lane) {
@@ -55,18 +55,24 @@ __device__ __forceinline__ cgw::RV warp_view(const uint64_t* __restrict__ rec, c
     __syncwarp();
     for (int j = lane; j < g.WT; j += 32) {
         uint64_t v = __ldg(rec + j);
-        dst[j < g.W2f ? j : W2 + (j - g.W2f)] = v;
+        dst[j < g.W2f ? j : 2 * W2 + (j - g.W2f)] = v;
     }
-    if (lane == 0) { dst[g.W2f] = 0; dst[W2 + g.WMf] = ~0ULL; }
+    if (lane == 0) { dst[g.W2f] = 0; dst[2 * W2 + g.WMf] = ~0ULL; }
     __syncwarp();
+    // the reverse-complement strand, once per read: word j = 32 bases from oriented position 32 j (0 past the end)
+    if (lane < W2) {
+        ReadView fv; fv.w = dst; fv.L = L; fv.W2 = W2; fv.WM = 0; fv.anyN = false;
+        dst[W2 + lane] = fv.chunk(1, 32 * lane);
+    }
     // any N below L?  (mask bits past the read's end are set by construction)
     uint64_t m = 0;
     if (lane < g.WMf) {
         int lo = 64 * lane;
-        m = dst[W2 + lane];
+        m = dst[2 * W2 + lane];
         if (lo >= L) m = 0; else if (L - lo < 64) m &= (1ULL << (L - lo)) - 1;
     }
     cgw::RV rv; rv.w = dst; rv.L = L; rv.W2 = W2; rv.anyN = __any_sync(cgw::FULL, m != 0) ? 1 : 0;
+    __syncwarp();
     return rv;
 }
 // hits of both strands merged by transcript (:567-579): number of distinct transcripts
@@ -125,7 +131,7 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
             ok = cgw::w_collect<0, cgw::GEN_FI, cgw::GEN_FK>(rv, lane, lceMode, *gp.st, found, nF, nR);
             fwd = gp.st->fwd; rc = gp.st->rc;
         } else {
-            FastState& st = *reinterpret_cast<FastState*>(mine + (g.W2f + 1 + g.WMf + 1));
+            FastState& st = *reinterpret_cast<FastState*>(mine + (2 * (g.W2f + 1) + g.WMf + 1));
             ok = cgw::w_collect<0, cgw::FAST_FI, cgw::FAST_FK>(rv, lane, lceMode, st, found, nF, nR);
             fwd = st.fwd; rc = st.rc;
         }
@@ -309,7 +315,7 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
             ok = cgw::w_collect<1, cgw::GEN_FI, cgw::GEN_FK>(rv, lane, lceMode, *gp.st, found, nF, nR);
             fwd = gp.st->fwd; rc = gp.st->rc; tl = gp.merged;
         } else {
-            FastState& st = *reinterpret_cast<FastState*>(mine + (g.W2f + 1 + g.WMf + 1));
+            FastState& st = *reinterpret_cast<FastState*>(mine + (2 * (g.W2f + 1) + g.WMf + 1));
             ok = cgw::w_collect<1, cgw::FAST_FI, cgw::FAST_FK>(rv, lane, lceMode, st, found, nF, nR);
             fwd = st.fwd; rc = st.rc; tl = reinterpret_cast<uint32_t*>(&st + 1);
         }

@@ -54,13 +54,21 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ ReadView full_view(RV r) {
-    ReadView v; v.w = r.w; v.L = r.L; v.W2 = r.W2; v.WM = 0; v.anyN = r.anyN != 0;
-    return v;
+// Read view in shared memory: W2 forward code words (32 bases each, the last a zero pad), W2 words of the
+// reverse-complement strand in the same layout (built once per read by warp_view), then the N-mask words of the
+// forward strand.
+// 32-base window of strand s at oriented position i (i < L): three 32-bit words and two funnel shifts
+__device__ __forceinline__ uint64_t w_chunk(RV r, int s, int i) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(r.w + (s ? r.W2 : 0)) + (i >> 4);
+    const int sh = (i & 15) * 2;
+    const uint32_t a = p[0], b = p[1], c = p[2];
+    return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
 }
-// 32-base window / 32 N-mask bits of strand s at oriented position i
-__device__ __noinline__ uint64_t w_chunk(RV r, int s, int i) { return full_view(r).chunk(s, i); }
-__device__ __noinline__ uint32_t w_mask(RV r, int s, int i) { return full_view(r).mask32(s, i); }
+// 32 N-mask bits of strand s at oriented position i (only reads that hold an N get here)
+__device__ __noinline__ uint32_t w_mask(RV r, int s, int i) {
+    ReadView v; v.w = r.w + r.W2; v.L = r.L; v.W2 = r.W2; v.WM = 0; v.anyN = true;     // msk(j) = w[W2 + j]
+    return v.mask32(s, i);
+}
 
 struct Hit { uint32_t b, e; bool found; };
 // table look-up with a different key per lane; every lane of the warp must call
@@ -208,14 +216,14 @@ struct Look { int pos, o_end, jl; unsigned fb; uint32_t b, e; };
 template <int X>
 __device__ __noinline__ Look w_look(RV r, int lane, int s, int o, int lim, uint32_t nbits, bool both, bool once, bool either) {
     const int k = c_ix[X].k, homoSkip = k / 2;
-    const uint64_t KM = kmask(k);
+    const uint64_t KM = c_ix[X].km;
     const int sh = both ? 1 : 0;
     const int np = once ? 1 : (32 >> sh);
     Look R; R.pos = -1; R.jl = 0; R.fb = 0; R.b = R.e = 0; R.o_end = o;
     if (once && !r.anyN && o <= lim) {
         // the common single probe: no N anywhere in the read, so only the homopolymer rule can intervene
         uint64_t mer = w_chunk(r, s, o) & KM;
-        if (!homopolymer(mer, k)) {
+        if (!homopolymer_ix(mer, c_ix[X])) {
             Hit h = w_probe<X>((both && (lane & 1)) ? revcomp(mer, k) : mer, lane < (both ? 2 : 1));
             unsigned fb = __ballot_sync(FULL, h.found);
             if (both && either ? (fb & 3u) : (fb & 1u)) {
@@ -234,7 +242,7 @@ __device__ __noinline__ Look w_look(RV r, int lane, int s, int o, int lim, uint3
         uint32_t m32 = inr ? (r.anyN ? (w_mask(r, s, p) & nbits) : 0u) : 1u;
         uint64_t mer = inr ? (w_chunk(r, s, p) & KM) : 0;
         bool nbad = m32 != 0;
-        bool homo = !nbad && homopolymer(mer, k);
+        bool homo = !nbad && homopolymer_ix(mer, c_ix[X]);
         unsigned inrB = __ballot_sync(FULL, inr), nB = __ballot_sync(FULL, nbad) & inrB, hB = __ballot_sync(FULL, homo) & inrB;
         unsigned visit = 0;
         int q = 0;
@@ -281,7 +289,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
     // the forced last look-up (:300-321) probes the k-mer at L - k and its reverse complement: start those two
     // sectors on their way now
     if ((CG_OPT_PF & 2) && L > k && lane < 2 && !rv.anyN) {
-        const uint64_t mer = w_chunk(rv, 0, L - k) & kmask(k);
+        const uint64_t mer = w_chunk(rv, 0, L - k) & c_ix[X].km;
         prefetch_l2(&c_ix[X].hslots[home_slot(c_ix[X], lane ? revcomp(mer, k) : mer)]);
     }
     uint32_t fwdHit = 0, rcHit = 0;
@@ -349,7 +357,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
                 o = lk.pos;
                 b = __shfl_sync(FULL, lk.b, lk.jl); e = __shfl_sync(FULL, lk.e, lk.jl);
                 if (!expectAbsent) other = (lk.fb >> (lk.jl + 1)) & 1;
-                else other = __shfl_sync(FULL, (int)w_probe<X>(revcomp(w_chunk(rv, s, o) & kmask(k), k), lane == 0).found, 0);   // :268 / :379
+                else other = __shfl_sync(FULL, (int)w_probe<X>(revcomp(w_chunk(rv, s, o) & c_ix[X].km, k), lane == 0).found, 0);   // :268 / :379
                 expectAbsent = false;
                 prevO = o; pB = b; pE = e; pOther = other;
             }
@@ -411,7 +419,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
             uint64_t w = 0;
             if (keep && (f == 0 || r == 0)) {         // k-mer word cut at the first non-base
                 int pos = (int)ks_key(en);
-                w = w_chunk(rv, 0, pos) & kmask(k);
+                w = w_chunk(rv, 0, pos) & c_ix[X].km;
                 uint32_t m = rv.anyN ? (w_mask(rv, 0, pos) & kbits) : 0u;
                 if (m) w &= (1ULL << (2 * ctz32(m))) - 1;
             }

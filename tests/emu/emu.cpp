@@ -68,6 +68,7 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
     E->sa.assign(sa, sa + n);
     E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
     E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0; E->v.hshift = 0;
+    E->v.km = kmask(k); E->v.km3 = E->v.km / 3;
     // k-mer table: heads of runs of equal valid k-mers in SA order
     std::vector<uint64_t> keys; std::vector<uint32_t> begins, endsI;
     bool have = false; uint64_t prev = 0;
