@@ -150,3 +150,41 @@ def test_two_process_pipeline_and_fused_files(exe, tmp_path):
          "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"), "-o", fw, "-O", fb, "--batch", "1700"])
     check_wt(fw)
     check_bsj(fb)
+
+
+@pytest.mark.gpu
+def test_pseudo_files(exe, tmp_path):
+    """Circall_pseudo (step 5): header list + transcript-name lists of the pairs whose mates' hits intersect (or, failing
+    that, orphan hits), against the oracle's collector + mergeLeftRightHitsFuzzy."""
+    import oracle
+    import synth
+    synth.build(); oracle.build()
+    T = synth.Txome(23, 120, p_polya=0.0)
+    obsj = oracle.Index.from_text(T.bsj_text)
+    bsn = [T.bsj_name(t) for t in range(T.n_bsj)]
+    _fasta(tmp_path / "pseudo.fa", bsn, T.bsj_text)
+    r1, r2 = make_reads(T, 12, 3000, circ_frac=0.6, n_rate=0.001)
+    n = r1.shape[0]
+    for fn, r, tagc in ((tmp_path / "b1.fa", r1, 1), (tmp_path / "b2.fa", r2, 2)):
+        with open(fn, "w") as f:
+            for i in range(n):
+                f.write(">cand%d/%d___11\n%s\n" % (i, tagc, bytes(r[i]).decode()))
+    run([exe + "/TxIndexer", "-t", str(tmp_path / "pseudo.fa"), "-o", str(tmp_path / "pIdx"), "-f"])
+    out = str(tmp_path / "pseudo")
+    run([exe + "/Circall_pseudo", "-i", str(tmp_path / "pIdx"), "-1", str(tmp_path / "b1.fa"), "-2", str(tmp_path / "b2.fa"), "-o", out, "-p", "2", "--batch", "1100"])
+    exp_h, exp_m = [], []
+    for i in range(n):
+        f1, _, _, h1 = obsj.collect(r1[i].tobytes(), strict=True)
+        f2, _, _, h2 = obsj.collect(r2[i].tobytes(), strict=True)
+        joint, _tm = oracle.merge_fuzzy(h1, h2, f1, f2, 100, 200)
+        if joint.shape[0] == 0 or joint.shape[0] > 200:
+            continue
+        tids = joint[:, 0].tolist()
+        if joint[0, 6] != 3:
+            tids = sorted(tids)
+        exp_h.append(">cand%d/1___11" % i)
+        exp_m.append("".join(bsn[t] + " " for t in tids))
+    assert len(exp_h) > 200
+    got_h = open(os.path.join(out, [f for f in os.listdir(out) if f.endswith(".rh")][0])).read().split("\n")[:-1]
+    got_m = open(os.path.join(out, [f for f in os.listdir(out) if f.startswith("mapInfo_")][0])).read().split("\n")[:-1]
+    assert got_h == exp_h and got_m == exp_m

@@ -1,5 +1,5 @@
 """Build the drop-in executables: tools/bin/circall_gpu plus the names Circall.sh calls (Circall_wt, Circall_bsj,
-TxIndexer) as symlinks to it.  Plain g++; links libcircall_gpu.so (built by circall_b200/build.py) by rpath."""
+Circall_pseudo, TxIndexer) as symlinks to it.  Plain g++; links libcircall_gpu.so (built by circall_b200/build.py) by rpath."""
 import os
 import subprocess
 import sys
@@ -21,7 +21,7 @@ def build(force=False):
     if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(s) for s in srcs + [lib]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", srcs[0], "-o", exe, "-L" + os.path.dirname(lib), "-lcircall_gpu",
                                "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath-link,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
-    for name in ("Circall_wt", "Circall_bsj", "TxIndexer"):
+    for name in ("Circall_wt", "Circall_bsj", "Circall_pseudo", "TxIndexer"):
         p = os.path.join(out, name)
         if not os.path.islink(p):
             if os.path.exists(p):

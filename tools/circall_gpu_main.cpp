@@ -3,6 +3,7 @@
 // One binary, dispatched on its name (or on the first argument):
 //   Circall_wt   -i TXINDEX  -1 R1.. -2 R2.. -o OUT [-p N] [--gpu D]      src/Circall_wt.cpp main :1415-1739, called at Circall_source.sh:273
 //   Circall_bsj  -i BSJINDEX -1 U1.. -2 U2.. -o OUT [-p N] [--gpu D]      src/Circall_bsj.cpp,         called at Circall_source.sh:291
+//   Circall_pseudo -i PSEUDOINDEX -1 B1.. -2 B2.. -o OUT [-p N]           src/Circall_pseudo.cpp,      called at Circall_source.sh:340
 //   TxIndexer    -t FASTA -o INDEX [-k 31] [-f]                           src/TxIndexer.cpp:81-94,192-227
 //   circall_gpu fused -i TXINDEX -b BSJINDEX -1 .. -2 .. -o OUTWT -O OUTBSJ   (extension: both steps in one pass, no
 //                intermediate Unmapped_readM_{1,2}.fa; the two output directories receive what the two tools write)
@@ -216,6 +217,63 @@ int run_mapper(int stage, const Args& a) {
     return 0;
 }
 
+// Circall_pseudo (src/Circall_pseudo.cpp:216-555, defaults: allowOrphans, ignoreLibCompat, fuzzy intersection): both
+// mates through the collector, mergeLeftRightHitsFuzzy (:271-280, maxNumHits = maxReadOccs = 200), more than 200 joint
+// hits -> none (:296); a pair with joint hits writes its header to Mapped_read_<tag>.rh and the names of the hit
+// transcripts, in transcript order, each followed by a space, to mapInfo_<tag>.txt (:474-508).
+int run_pseudo(const Args& a) {
+    if (a.m1.empty() || a.m2.empty()) die("both -1 and -2 are required (paired-end reads)");
+    int nd = 0;
+    cg_device_count(&nd);
+    if (nd == 0) die("no CUDA device: libcircall_gpu has no CPU path");
+    cg_index* idx = nullptr;
+    ck(cg_index_open(a.index.c_str(), a.gpu, &idx), "opening the pseudo-sequence index");
+    make_dir(a.out);
+    const std::string tag = std::to_string(1804289383);
+    FILE* rh = open_append(a.out + "/Mapped_read_" + tag + ".rh");
+    FILE* mi = open_append(a.out + "/mapInfo_" + tag + ".txt");
+    cgh::Batch B;
+    const uint64_t maxp = std::min<uint64_t>(a.batch, 1u << 18);
+    std::vector<char> b1(std::max<uint64_t>(maxp * 320, 1u << 20)), b2(b1.size());
+    B.b1 = b1.data(); B.b2 = b2.data(); B.cap = b1.size();
+    cgh::PairStream in(a.m1, a.m2);
+    uint64_t pairs = 0, mapped = 0, hits = 0;
+    std::vector<uint64_t> loff, joff;
+    std::vector<uint32_t> ltid; std::vector<int32_t> lpos, joint; std::vector<uint8_t> lfwd, lfound, tm;
+    try {
+        while (in.fill(B, maxp)) {
+            const uint64_t n = B.n;
+            cg_collect_result L, R;
+            ck(cg_collect(idx, B.b1, B.off1.data(), n, 1, a.lce, &L), "mapping mate 1");
+            loff.assign(L.hits_off, L.hits_off + n + 1);                       // the buffers are reused by the next call
+            ltid.assign(L.hit_tid, L.hit_tid + loff[n]); lpos.assign(L.hit_pos, L.hit_pos + loff[n]); lfwd.assign(L.hit_fwd, L.hit_fwd + loff[n]);
+            lfound.assign(L.found, L.found + n);
+            ck(cg_collect(idx, B.b2, B.off2.data(), n, 1, a.lce, &R), "mapping mate 2");
+            const uint64_t cap = loff[n] + R.hits_off[n] + n + 1;
+            joff.assign(n + 1, 0); joint.assign(cap * 7, 0); tm.assign(n, 0);
+            ck(cg_merge_pairs(a.gpu, n, loff.data(), ltid.data(), lpos.data(), lfwd.data(), lfound.data(), R.hits_off, R.hit_tid, R.hit_pos, R.hit_fwd, R.found,
+                              (uint32_t)B.len1(0), 200, joff.data(), joint.data(), cap, tm.data()), "intersecting the mates' hits");
+            for (uint64_t i = 0; i < n; ++i) {
+                const uint64_t nj = joff[i + 1] - joff[i];
+                if (nj == 0 || nj > 200) continue;                                // :296
+                std::vector<uint32_t> t;
+                for (uint64_t h = joff[i]; h < joff[i + 1]; ++h) t.push_back((uint32_t)joint[7 * h]);
+                if (joint[7 * joff[i] + 6] != 3) std::stable_sort(t.begin(), t.end());   // orphans: left then right lists merged by transcript (:304-319)
+                fprintf(rh, ">%s\n", B.h1[i].c_str());
+                for (uint32_t x : t) { fputs(cg_index_tx_name(idx, x), mi); fputc(' ', mi); }
+                fputc('\n', mi);
+                ++mapped; hits += nj;
+            }
+            pairs += n;
+        }
+    } catch (const std::string& e) { die(e); }
+    cg_collect_free();
+    fclose(rh); fclose(mi);
+    fprintf(stderr, "[circall_gpu] %llu pairs; pseudo: mapped %llu hits %llu\n", (unsigned long long)pairs, (unsigned long long)mapped, (unsigned long long)hits);
+    cg_index_close(idx);
+    return 0;
+}
+
 int run_indexer(const Args& a) {
     if (a.fasta.empty() || a.out.empty()) die("usage: TxIndexer -t transcripts.fa -o indexDir [-k 31] [-f]");
     struct stat st;
@@ -261,12 +319,14 @@ int main(int argc, char** argv) {
     std::string cmd;
     if (me == "Circall_wt") cmd = "wt";
     else if (me == "Circall_bsj") cmd = "bsj";
+    else if (me == "Circall_pseudo") cmd = "pseudo";
     else if (me == "TxIndexer") cmd = "index";
-    else { if (argc < 2) die("usage: circall_gpu {wt|bsj|fused|index|parse} options..."); cmd = argv[1]; first = 2; }
+    else { if (argc < 2) die("usage: circall_gpu {wt|bsj|fused|pseudo|index|parse} options..."); cmd = argv[1]; first = 2; }
     Args a = parse_args(argc, argv, first);
     if (cmd == "wt") return run_mapper(1, a);
     if (cmd == "bsj") return run_mapper(2, a);
     if (cmd == "fused") { if (a.bsj_index.empty() || a.out_bsj.empty()) die("fused needs -b BSJINDEX and -O OUTBSJ"); return run_mapper(0, a); }
+    if (cmd == "pseudo") return run_pseudo(a);
     if (cmd == "index") return run_indexer(a);
     if (cmd == "parse") return run_parse(a);
     die("unknown command " + cmd);
