@@ -11,6 +11,7 @@
 #include "cg_kernels.cuh"
 #include "cg_warp.cuh"
 #include "cg_tsm.cuh"
+#include "cg_pre.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstddef>
@@ -613,6 +614,36 @@ k_bsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGe
     }
 }
 
+// ---- front kernel of Circall_wt: one thread per mate, clean full-length matches only (cg_pre.cuh) -----------------
+static const int PRE_THREADS = 128;
+__global__ void __launch_bounds__(PRE_THREADS)
+k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
+         uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf) {
+    extern __shared__ uint32_t pre_smem[];
+    const uint64_t r = (uint64_t)blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint64_t* rec = pk + r * (uint64_t)g.WT;
+    const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+    cgt::TMem m; m.base = pre_smem + threadIdx.x; m.stride = PRE_THREADS; m.W2 = g.W2f + 1;
+    bool anyN = false;
+    for (int j = 0; j < g.WMf; ++j) {
+        const int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = __ldg(rec + g.W2f + j);
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        anyN |= mk != 0;
+    }
+    bool done = false;
+    uint8_t fl = 0; uint32_t nh = 0;
+    if (!anyN) {
+        for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
+        m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
+        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh);
+    }
+    if (done) { flags[r] = fl; nhits[r] = nh; }
+    ovf[r] = done ? 0 : 1;
+}
+
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 } // namespace
@@ -628,6 +659,7 @@ struct cg_session {
     int warp_grid_wt = 0, warp_grid_bsj = 0;     // persistent grids of the warp-per-read kernels (SMs x resident blocks)
     int gen_grid = 0;                            // grid of the general kernels (sized with the per-warp global scratch)
     int sms = 0;
+    bool use_pre = true;                         // Circall_wt front kernel for clean full-length matches (CG_NO_PRE=1 switches it off)
     bool use_tsm = false;                        // first tier = thread state machine (CG_TSM=1 switches it on; experimental: parity-green, not yet faster)
     unsigned char* d_gscratch = nullptr;
     bool pending = false;
@@ -778,11 +810,17 @@ int run_batch(cg_session* s) {
         const dim3 blk(WARPS_PER_BLOCK * 32);
         const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false);
         const uint8_t* ovf_fast = s->d_ovf.as<uint8_t>();
-        if (s->use_tsm) {
-            // tier 1: thread state machine; tier 2: the fast warp kernel over what it handed on
-            BsjOut none; memset(&none, 0, sizeof none);
-            CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, n_reads, s->stream));
-            rc = launch_tsm<false>(s, n_reads, (const uint32_t*)nullptr, none, 0);
+        if (s->use_tsm || s->use_pre) {
+            // tier 1: the front kernel (clean full-length matches, one thread per mate) — or the experimental state
+            // machine; tier 2: the fast warp kernel over the mates it declined
+            if (s->use_tsm) {
+                BsjOut none; memset(&none, 0, sizeof none);
+                CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, n_reads, s->stream));
+                rc = launch_tsm<false>(s, n_reads, (const uint32_t*)nullptr, none, 0);
+            } else {
+                rc = launch(s, k_wt_pre, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
+                            s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>());
+            }
             if (rc) return rc;
             rc = compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt);
             if (rc) return rc;
@@ -870,6 +908,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bw, k_wt_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
         s->sms = sms; s->use_tsm = getenv("CG_TSM") != nullptr && atoi(getenv("CG_TSM")) != 0;
+        s->use_pre = getenv("CG_NO_PRE") == nullptr;
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
         s->gen_grid = sms * 2;

@@ -14,7 +14,8 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "emu.cpp"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_core.cuh"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pipeline.cuh"),
-            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm.cuh")]
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm.cuh"),
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pre.cuh")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     return so
@@ -99,7 +100,7 @@ def run(tx, bsj, r1, off1, r2, off2, lce_mode=0):
         fb = np.zeros(2, np.uint64)
         L.emu_run_fallbacks(h, fb.ctypes.data)
         out["fallbacks"] = fb
-        ts = np.zeros(3 + 32, np.uint64)
+        ts = np.zeros(3 + 32 + 1, np.uint64)
         L.emu_run_tsm(h, ts.ctypes.data)
         out["tsm"] = ts          # [wt mates done by the state machine, bsj records done by it, steps, bail reasons wt[16], bsj[16]]
         L.emu_run_fill(h, *[out[k].ctypes.data for k in ("mate_flags", "mate_nhits", "exp_pair", "exp_code", "junc",

@@ -11,6 +11,7 @@
 #define CG_HOST_EMU 1
 #include "../../circall_b200/csrc/cg_pipeline.cuh"
 #include "../../circall_b200/csrc/cg_tsm.cuh"
+#include "../../circall_b200/csrc/cg_pre.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -39,6 +40,24 @@ static bool tsm_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L
     if (!cgt::tsm_begin(c, m, pk.data(), W2f, WMf, L, pairLen)) return false;
     while (c.pc != cgt::PC_DONE && c.pc != cgt::PC_BAIL) { cgt::tsm_step<BSJ>(c, ix, m, lceMode, sink); ++steps; }
     return c.pc == cgt::PC_DONE;
+}
+
+// the front kernel's per-mate function on the host (false: declined)
+static bool pre_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
+    int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
+    for (int j = 0; j < WMf; ++j) {
+        int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = pk[W2f + j];
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        if (mk) return false;
+    }
+    cgt::TMem m; m.stride = 1; m.W2 = W2f + 1;
+    scratch.assign(cgp::pre_words(m.W2), 0xdeadbeefu);
+    m.base = scratch.data();
+    for (int j = 0; j < W2f; ++j) { m.st(2 * j, (uint32_t)pk[j]); m.st(2 * j + 1, (uint32_t)(pk[j] >> 32)); }
+    m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
+    return cgp::perfect_mate(ix, m, L, pairLen, fl, nh);
 }
 
 extern "C" {
@@ -165,6 +184,7 @@ struct EmuRun {
     uint64_t fallbacks[2] = {0, 0};      // reads the fast path handed to the general path (wt mates, bsj records)
     uint64_t tsm_done[2] = {0, 0};       // reads finished by the thread state machine (first tier), wt mates / bsj records
     uint64_t tsm_steps = 0;
+    uint64_t pre_done = 0;               // wt mates resolved by the thread-per-mate front kernel's function
     uint64_t tsm_why[2][16] = {};        // bail reasons (cgt::BAIL_*) per tool
     int err = 0;
 };
@@ -188,6 +208,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
     std::vector<uint64_t> pk, strands;
     std::vector<uint32_t> tscr;
     const bool use_tsm = getenv("CG_EMU_NO_TSM") == nullptr;
+    const bool use_pre = getenv("CG_EMU_NO_PRE") == nullptr;
     for (uint64_t i = 0; i < n; ++i) {
         int l1 = (int)(off1[i + 1] - off1[i]), l2 = (int)(off2[i + 1] - off2[i]);
         uint8_t fl[2]; uint32_t nh[2];
@@ -196,7 +217,9 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             if (!view_of(m ? r2 + off2[i] : r1 + off1[i], m ? l2 : l1, pk, strands, rv)) R->err = -4;
             // same tiers as the kernels: thread state machine, small-capacity fast path, general path on overflow
             cgt::Ctx tc; cgt::NoSink ns;
-            if (use_tsm && tsm_host<false>(TX->v, pk, m ? l2 : l1, l1, lceMode, tc, tscr, ns, R->tsm_steps)) {
+            tc.why = 0;
+            if (use_pre && pre_host(TX->v, pk, m ? l2 : l1, l1, tscr, fl[m], nh[m])) ++R->pre_done;
+            else if (use_tsm && tsm_host<false>(TX->v, pk, m ? l2 : l1, l1, lceMode, tc, tscr, ns, R->tsm_steps)) {
                 ++R->tsm_done[0]; fl[m] = tc.flags; nh[m] = tc.nh;
             } else if ((use_tsm ? ++R->tsm_why[0][tc.why & 15] : 0), !wt_mate_fast<EFI, EFK, EHC>(TX->v, rv, l1, lceMode, *fs, fl[m], nh[m])) {
                 ++R->fallbacks[0];
@@ -252,7 +275,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
 void emu_run_free(void* r) { delete (EmuRun*)r; }
 int emu_run_err(void* r) { return ((EmuRun*)r)->err; }
 void emu_run_fallbacks(void* r, uint64_t* out) { out[0] = ((EmuRun*)r)->fallbacks[0]; out[1] = ((EmuRun*)r)->fallbacks[1]; }
-void emu_run_tsm(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->tsm_done[0]; out[1] = R->tsm_done[1]; out[2] = R->tsm_steps; for (int t = 0; t < 2; ++t) for (int w = 0; w < 16; ++w) out[3 + 16 * t + w] = R->tsm_why[t][w]; }
+void emu_run_tsm(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->tsm_done[0]; out[1] = R->tsm_done[1]; out[2] = R->tsm_steps; out[35] = R->pre_done; for (int t = 0; t < 2; ++t) for (int w = 0; w < 16; ++w) out[3 + 16 * t + w] = R->tsm_why[t][w]; }
 void emu_run_sizes(void* r, uint64_t* out) {
     EmuRun* R = (EmuRun*)r;
     out[0] = R->expPair.size(); out[1] = R->junc.size() / 6; out[2] = R->cand.size(); out[3] = R->eqTids.size();
