@@ -324,215 +324,7 @@ CG_HD void tsm_control(Ctx& c, const IndexView& ix, const M& m, Sink& sink) {
     const uint32_t maxInterval = 1000;
     switch (c.pc) {
     case PC_START:
-        c.nF = c.nR = 0; c.fwdHit = c.rcHit = 0; c.found = false; c.flags = 0; c.nh = 0; c.split = false;
-        c.lbF = c.ubF = 0; c.matched = 0; c.q0 = 0;
-        // ---- Phase A (:112-200): first position whose k-mer or reverse complement is in the table, `re < read.end()`
-        c.pos = 0; c.a_two = false;                     // a_two: this round looks at two positions
-        while (c.pos + k < L) {
-            c.p_s = 0; c.p_pos = c.pos; c.p_lim = L - k - 1; c.p_mode = c.a_two ? PM_PAIR2 : PM_PAIR1;
-            T_REQ(RQ_PROBE, PC_A_PROBED);               // :131-132
-            if (!(c.fnd & 3u)) {
-                if (c.fnd & 12u) { c.pos += 1; c.fnd >>= 2; c.d.s0 = c.d.s2; }
-                else { c.pos += c.a_two ? 2 : 1; c.a_two = true; continue; }     // the walk goes on whatever the look-ups return
-            }
-            c.hasF = (c.fnd & 1u) != 0; c.hasR = (c.fnd & 2u) != 0;
-            c.a_two = true;
-            if (c.hasF) {
-                c.x_s = 0; c.x_q = c.pos; c.x_lbIn = c.d.s0.z > 0 ? c.d.s0.z - 1 : 0; c.x_ubIn = c.d.s0.w;   // :140
-                T_EXT(PC_A_EXT);                        // :143
-                c.lbF = c.x_lb; c.ubF = c.x_ub; c.matched = c.x_len;
-                if (c.ubF > c.lbF && c.ubF - c.lbF < maxInterval) {              // :149
-                    m.st(m.iv(0, 0), c.lbF); m.st(m.iv(0, 0) + 1, c.ubF); m.st(m.iv(0, 0) + 2, (uint32_t)c.matched | ((uint32_t)c.pos << 16));
-                    c.nF = 1; c.q0 = c.pos;
-                    ++c.fwdHit;
-                    if (c.hasR) ++c.rcHit;
-                }
-            }
-            if (c.hasR && !c.fwdHit) ++c.rcHit;                                  // :178-191
-            if (c.fwdHit + c.rcHit > 0) { c.found = true; break; }
-            ++c.pos;
-        }
-        if (!c.found) T_DONE();                                // :204
-
-        // ---- Phases B (:208-329, forward strand) and C (:332-440, reverse-complement strand)
-        for (c.s = 0; c.s < 2; ++c.s) {
-            c.lastSearch = false; c.expectAbsent = false;
-            if (c.s == 0) {
-                if (!c.fwdHit) continue;
-                c.l_i1 = c.lbF; c.l_i2 = c.ubF - 1; c.l_len = c.matched; c.l_lim = L - (c.q0 + c.matched);   // :219
-                T_LCE(PC_B_LCE0);                                                // :220
-                {
-                    int remaining = L - (c.q0 + c.matched);
-                    int fwdSkip = cmax(c.matched - skipOverlap, c.l_res - skipOverlap);
-                    c.pos = cmin(cmax(0, L - k), c.q0 + fwdSkip);                // :224-228
-                    c.expectAbsent = remaining > 0 && c.pos < L - k;
-                }
-            } else {
-                if (!(c.rcHit >= c.fwdHit)) continue;                            // :332
-                c.pos = 0;
-            }
-            c.prevO = -1; c.pB = c.pE = 0; c.pOther = false;
-            while (c.pos + k <= L) {                                             // :234 / :341-344
-                if (c.pos == c.prevO) { c.ivB = c.pB; c.ivE = c.pE; c.other = c.pOther; }   // the forced last position was just looked up
-                else {
-                    if (!c.expectAbsent) {
-                        // expected present: this k-mer and its reverse complement (:261+:268 / :372+:379)
-                        c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_PAIR1;
-                        T_REQ(RQ_PROBE, PC_B_PROBED);
-                        if (!(c.fnd & 1u)) { c.pos += 1; c.expectAbsent = true; continue; }     // :324 / :436
-                        c.other = (c.fnd & 2u) != 0;
-                        c.ivB = c.d.s0.z; c.ivE = c.d.s0.w;
-                    } else {
-                        // after a mismatch: the windows that cover it, four positions per round
-                        for (;;) {
-                            c.fnd = 0;
-                            if (c.pos + k > L) break;
-                            c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_RUN;
-                            T_REQ(RQ_PROBE, PC_B_RUN);
-                            if (c.fnd) break;
-                            c.pos += 4;
-                        }
-                        if (!c.fnd) { c.pos = L; continue; }                     // ran off the read: the loop ends
-                        if (c.fnd & 1u) { c.ivB = c.d.s0.z; c.ivE = c.d.s0.w; }
-                        else if (c.fnd & 2u) { c.pos += 1; c.ivB = c.d.s1.z; c.ivE = c.d.s1.w; }
-                        else if (c.fnd & 4u) { c.pos += 2; c.ivB = c.d.s2.z; c.ivE = c.d.s2.w; }
-                        else { c.pos += 3; c.ivB = c.d.s3.z; c.ivE = c.d.s3.w; }
-                        // the reverse complement of the k-mer that hit (:268 / :379)
-                        c.p_s = c.s; c.p_pos = c.pos; c.p_lim = L - k; c.p_mode = PM_RC1;
-                        T_REQ(RQ_PROBE, PC_B_RC);
-                        c.other = (c.fnd & 1u) != 0;
-                        c.expectAbsent = false;
-                    }
-                    c.prevO = c.pos; c.pB = c.ivB; c.pE = c.ivE; c.pOther = c.other;
-                }
-                if (c.s == 0) { ++c.fwdHit; if (c.other) ++c.rcHit; }
-                else { ++c.rcHit; if (c.other) ++c.fwdHit; }
-                c.x_s = c.s; c.x_q = c.pos; c.x_lbIn = c.ivB > 0 ? c.ivB - 1 : 0; c.x_ubIn = c.ivE;     // :279 / :392
-                T_EXT(PC_B_EXT);                                                 // :280 / :393
-                c.matched = c.x_len;
-                if (c.x_ub > c.x_lb && c.x_ub - c.x_lb < maxInterval) {          // :285 / :398
-                    int cnt = c.s == 0 ? c.nF : c.nR;
-                    if (cnt >= T_FI) T_BAIL(BAIL_NINT);
-                    int w0 = m.iv(c.s, cnt);
-                    m.st(w0, c.x_lb); m.st(w0 + 1, c.x_ub); m.st(w0 + 2, (uint32_t)c.matched | ((uint32_t)c.pos << 16));
-                    if (c.s == 0) ++c.nF; else ++c.nR;
-                }
-                if (c.lastSearch) break;                                         // :300 / :412
-                if (c.pos + c.matched < L) {
-                    c.l_i1 = c.x_lb; c.l_i2 = c.x_ub - 1; c.l_len = c.matched; c.l_lim = L - (c.pos + c.matched);
-                    T_LCE(PC_B_LCE);                                             // :304 / :416
-                    c.pos = cmax(c.pos + c.l_res - skipOverlap, c.pos + c.matched - skipOverlap);
-                    if (c.pos > L - k) { c.pos = L - k; c.lastSearch = true; }
-                    else c.expectAbsent = true;
-                } else {
-                    c.lastSearch = true; c.pos = L - k;
-                }
-            }
-        }
-
-        // ---- strand vote (:442-490): only the two clear-cut outcomes; a real vote goes to the warp kernels
-        if (c.fwdHit > 0 && c.rcHit == 0) c.nR = 0;
-        else if (c.rcHit > 0 && c.fwdHit == 0) c.nF = 0;
-        else T_BAIL(BAIL_VOTE);
-        if (c.nF + c.nR > 0) c.flags |= MATE_SEEDED;                             // Circall_wt.cpp:311,486
-        c.s = c.nF > 0 ? 0 : 1;                                                  // the strand that kept its intervals
-        c.e_n = (uint32_t)(c.nF > 0 ? c.nF : c.nR);
-        if (c.e_n == 0) T_DONE();
-
-        // ---- hits (:492-563): intersection of the transcript sets of the maximal intervals
-        {
-            // keep = maximal, first of equals; e_mi = narrowest kept interval (first on ties)
-            c.keep = 0; c.e_mi = -1;
-            uint32_t msp = 0xffffffffu;
-            for (int x = 0; x < (int)c.e_n; ++x) {
-                int wx = m.iv(c.s, x);
-                uint32_t bx = m.ld(wx), ex = m.ld(wx + 1), lq = m.ld(wx + 2);
-                int lenx = (int)(lq & 0xffffu), qx = (int)(lq >> 16);
-                if (lenx == c.pairLen) c.flags |= MATE_FULL;                     // :318-342,493-517
-                bool drop = false;
-                for (int y = 0; y < (int)c.e_n && !drop; ++y) {
-                    if (y == x) continue;
-                    int wy = m.iv(c.s, y);
-                    uint32_t lqy = m.ld(wy + 2);
-                    int leny = (int)(lqy & 0xffffu), qy = (int)(lqy >> 16);
-                    if (leny > lenx) drop = qy <= qx && qy + leny >= qx + lenx;
-                    else if (leny == lenx && y < x) drop = m.ld(wy) == bx && m.ld(wy + 1) == ex;
-                }
-                if (!drop) {
-                    c.keep |= 1u << x;
-                    if (ex - bx < msp) { msp = ex - bx; c.e_mi = x; }
-                }
-            }
-            if (msp > (uint32_t)T_HC) T_BAIL(BAIL_NCAND);
-            c.e_c = m.ld(m.iv(c.s, c.e_mi)); c.e_end = m.ld(m.iv(c.s, c.e_mi) + 1);
-        }
-        // candidates: transcript of every position of the narrowest interval, four positions per round
-        c.nc = 0; c.alive = 0; c.e_off = false;
-        while (c.e_c < c.e_end) {
-            T_REQ(RQ_TID, PC_H_TID);
-            for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
-                uint32_t t = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
-                bool fresh = true;                       // one candidate per distinct transcript
-                for (int y = 0; y < c.nc; ++y) if (m.ld(m.cb() + y) == t) { fresh = false; break; }
-                if (fresh) { m.st(m.cb() + c.nc, t); c.alive |= 1u << c.nc; ++c.nc; }
-            }
-        }
-        // a candidate stays alive iff its transcript occurs among the positions of every other maximal interval
-        for (c.e_x = 0; c.e_x < (int)c.e_n && c.alive; ++c.e_x) {
-            if (c.e_x == c.e_mi || !((c.keep >> c.e_x) & 1u)) continue;
-            c.e_c = m.ld(m.iv(c.s, c.e_x)); c.e_end = m.ld(m.iv(c.s, c.e_x) + 1);
-            if (c.e_end - c.e_c > (uint32_t)T_OTHER) T_BAIL(BAIL_WIDE_OTHER);
-            c.seen = 0;
-            while (c.e_c < c.e_end) {
-                T_REQ(RQ_TID, PC_O_TID);
-                for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
-                    uint32_t t = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
-                    for (int y = 0; y < c.nc; ++y) if (m.ld(m.cb() + y) == t) c.seen |= 1u << y;
-                }
-            }
-            c.alive &= c.seen;
-        }
-        c.nh = (uint32_t)popc64(c.alive);
-        if (!BSJ) T_DONE();
-
-        // ---- Circall_bsj: ordered transcript list, then the junction-span filter over every position of every
-        //      interval (src/Circall_bsj.cpp:319-374), four positions per round
-        {
-            int n = 0;                                   // compact the live candidates, then insertion sort
-            for (int y = 0; y < c.nc; ++y) if ((c.alive >> y) & 1u) { m.st(m.cb() + n, m.ld(m.cb() + y)); ++n; }
-            for (int i = 1; i < n; ++i) {
-                uint32_t v = m.ld(m.cb() + i); int j = i - 1;
-                while (j >= 0 && m.ld(m.cb() + j) > v) { m.st(m.cb() + j + 1, m.ld(m.cb() + j)); --j; }
-                m.st(m.cb() + j + 1, v);
-            }
-        }
-        if (c.nh == 0) T_DONE();                               // :319
-        for (int x = 0; x < (int)c.e_n; ++x)             // bail before the first row of this record is emitted, or not at all
-            if (m.ld(m.iv(c.s, x) + 1) - m.ld(m.iv(c.s, x)) > (uint32_t)T_OTHER) T_BAIL(BAIL_WIDE_OTHER);
-        c.e_off = true;
-        for (c.e_x = 0; c.e_x < (int)c.e_n; ++c.e_x) {
-            c.e_c = m.ld(m.iv(c.s, c.e_x)); c.e_end = m.ld(m.iv(c.s, c.e_x) + 1);
-            while (c.e_c < c.e_end) {
-                T_REQ(RQ_TID, PC_J_TID);
-                {
-                    uint32_t lq = m.ld(m.iv(c.s, c.e_x) + 2);
-                    int len = (int)(lq & 0xffffu), qp = (int)(lq >> 16);
-                    for (int z = 0; z < 4 && c.e_c < c.e_end; ++z, ++c.e_c) {
-                        uint32_t p = z == 0 ? c.d.sa0 : z == 1 ? c.d.sa1 : z == 2 ? c.d.sa2 : c.d.sa3;
-                        uint32_t tid = z == 0 ? c.tid0 : z == 1 ? c.tid1 : z == 2 ? c.tid2 : c.tid3;
-                        uint32_t st0 = z == 0 ? c.d.s0.x : z == 1 ? c.d.s0.z : z == 2 ? c.d.s1.x : c.d.s1.z;
-                        uint32_t st1 = z == 0 ? c.d.s0.y : z == 1 ? c.d.s0.w : z == 2 ? c.d.s1.y : c.d.s1.w;
-                        int hitPos = (int)(p - st0);
-                        int junctPos = (int)((st1 - st0 - 1) / 2);                // :333
-                        if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {   // :336 / :364
-                            sink.line((uint32_t)c.s, (uint32_t)qp, (uint32_t)len, hitPos, tid);
-                            c.split = true;
-                        }
-                    }
-                }
-            }
-        }
-        T_DONE();
+#include "cg_tsm_control.inc"
 
     default:
         break;
@@ -598,6 +390,42 @@ CG_HD void tsm_step(Ctx& c, const IndexView& ix, const M& m, int lceMode, Sink& 
     tsm_issue(c, ix, m);
 }
 
+#undef T_REQ
+#undef T_EXT
+#undef T_LCE
+#undef T_BAIL
+#undef T_DONE
+
+// ---- the same control code as plain sequential code: one thread maps one read start to finish -----------------------
+// An engine request runs to completion on the spot (issue the loads, consume them, repeat while the engine wants
+// another round).  No switch, no resume labels: ordinary structured loops, which is what SIMT execution wants when a
+// warp holds 32 reads that mostly do the same thing — and the compiler keeps only the live part of the context in
+// registers.  Result in c.pc (PC_DONE / PC_BAIL), c.flags, c.nh, c.split, the candidate words of `m`.
+template <class M>
+CG_HD void tsm_engine_sync(Ctx& c, const IndexView& ix, const M& m, int lceMode) {
+    tsm_issue(c, ix, m);
+    while (c.req != RQ_NONE) tsm_complete(c, ix, m, lceMode);
+}
+#define T_REQ(rq, label) do { c.req = (rq); tsm_engine_sync(c, ix, m, lceMode); if (c.pc == PC_BAIL) return; } while (0)
+#define T_BAIL(why_) do { c.pc = PC_BAIL; c.why = (why_); return; } while (0)
+#define T_DONE() do { c.pc = PC_DONE; return; } while (0)
+#define T_EXT(label) do { \
+        c.x_m = L - c.x_q; c.x_w = c.x_ubIn - c.x_lbIn - 1; \
+        if (c.x_m <= k) { c.x_lb = c.x_lbIn + 1; c.x_ub = c.x_ubIn; c.x_len = k; } \
+        else if (c.x_w == 0) { c.x_lb = c.x_ubIn; c.x_ub = c.x_ubIn; c.x_len = k; } \
+        else { if (c.x_w > (uint32_t)T_WMAX) T_BAIL(BAIL_WIDE_EXT); T_REQ(RQ_EXT, label); } \
+    } while (0)
+#define T_LCE(label) do { if (c.l_lim <= c.l_len) c.l_res = c.l_len; else T_REQ(RQ_LCE, label); } while (0)
+template <bool BSJ, class M, class Sink>
+CG_HD void tsm_mate_sync(Ctx& c, const IndexView& ix, const M& m, int lceMode, Sink& sink) {
+    const int k = ix.k, L = c.L;
+    const int skipOverlap = k - 1;
+    const uint32_t maxInterval = 1000;
+    c.pc = PC_START; c.req = RQ_NONE; c.zero = 0; c.why = 0;
+    {
+#include "cg_tsm_control.inc"
+    }
+}
 #undef T_REQ
 #undef T_EXT
 #undef T_LCE

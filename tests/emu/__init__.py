@@ -15,7 +15,8 @@ def build(force=False):
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_core.cuh"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pipeline.cuh"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm.cuh"),
-            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pre.cuh")]
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pre.cuh"),
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm_control.inc")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     return so

@@ -38,7 +38,12 @@ static bool tsm_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L
     scratch.assign(cgt::TMem::words(m.W2), 0xdeadbeefu);
     m.base = scratch.data();
     if (!cgt::tsm_begin(c, m, pk.data(), W2f, WMf, L, pairLen)) return false;
-    while (c.pc != cgt::PC_DONE && c.pc != cgt::PC_BAIL) { cgt::tsm_step<BSJ>(c, ix, m, lceMode, sink); ++steps; }
+    if (getenv("CG_EMU_TSM_STEP")) {             // the resumable form, one scheduling round at a time
+        while (c.pc != cgt::PC_DONE && c.pc != cgt::PC_BAIL) { cgt::tsm_step<BSJ>(c, ix, m, lceMode, sink); ++steps; }
+    } else {                                     // the sequential form (what the thread-per-mate chain kernels run)
+        cgt::tsm_mate_sync<BSJ>(c, ix, m, lceMode, sink);
+        ++steps;
+    }
     return c.pc == cgt::PC_DONE;
 }
 

@@ -61,6 +61,17 @@ def _pipeline(world, r1, r2, lce_mode=0):
     return R
 
 
+@pytest.mark.parametrize("step", [False, True])
+def test_pipeline_state_machine_forms(world, step, monkeypatch):
+    """The state-machine tier in its two expansions: sequential (chain kernels) and resumable, one round at a time."""
+    if step:
+        monkeypatch.setenv("CG_EMU_TSM_STEP", "1")
+    monkeypatch.setenv("CG_EMU_NO_PRE", "1")          # let every mate reach it
+    T = world[0]
+    r1, r2 = make_reads(T, 411, 4000)
+    _pipeline(world, r1, r2, 0)
+
+
 @pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0)])
 def test_pipeline(world, L, lce_mode):
     T = world[0]
