@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=400_000, help="pairs per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="pairs per submit of the end-to-end leg (smaller than --batch: the copy of the first batch and the read-back of the last are not overlapped, so short batches shorten the step)")
     ap.add_argument("--sessions", type=int, default=3, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -266,13 +267,15 @@ def main():
     if not args.no_e2e:
         SS = [S] + [cg.Session(gtx, gbsj, stage=0) for _ in range(max(1, args.sessions) - 1)]
         NS = len(SS)
-        h2d = 2 * n * L + 2 * len(batches) * off.nbytes
+        ebatch = min(args.e2e_batch, batch)
+        ebatches = [(b0, min(ebatch, n - b0)) for b0 in range(0, n, ebatch)]
+        h2d = 2 * n * L + 2 * sum(8 * (nb + 1) for _, nb in ebatches)
         d2h = [0]
 
         def step_host():
             pend = []
             tot = 0
-            for i, (b0, nb) in enumerate(batches):
+            for i, (b0, nb) in enumerate(ebatches):
                 s = SS[i % NS]
                 if len(pend) == NS:
                     B = pend.pop(0).fetch(want_lists=True, materialize=False)
@@ -290,7 +293,7 @@ def main():
             step_host()
         dte = bracket(step_host, args.steps)
         e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS}
+               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS, "batch_pairs": ebatch}
         for x in SS[1:]:
             x.close()
 

@@ -56,8 +56,11 @@ CG_HD int pre_match(const IndexView& ix, const cgt::TMem& m, int s, uint32_t p, 
 }
 
 // m holds the forward strand; the reverse-complement strand is derived here when it is needed
-CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pairLen, uint8_t& flags, uint32_t& nh) {
+// cls (1..16) classifies a declined mate by which of the four k-mers are in the table (1 + f0 + 2 f1 + 4 f2 + 8 f3; 1 when it
+// never got to the look-ups): the lockstep tier sorts its work by it so that a warp holds reads that take the same path
+CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pairLen, uint8_t& flags, uint32_t& nh, uint8_t& cls) {
     const int k = ix.k;
+    cls = 1;
     if (L < k + 1 || L > 0xffff) return false;
     const uint64_t mer0 = m.chunk(0, 0) & ix.km, merL = m.chunk(0, L - k) & ix.km;
     if (homopolymer_ix(mer0, ix) || homopolymer_ix(merL, ix)) return false;
@@ -68,6 +71,7 @@ CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pair
     uint32_t b0 = 0, e0 = 0, b1 = 0, e1 = 0, b2 = 0, e2 = 0, b3 = 0, e3 = 0;
     const bool f0 = resolve(ix, mer0, h0, s0, b0, e0), f1 = resolve(ix, rc0, h1, s1, b1, e1);
     const bool f2 = resolve(ix, merL, h2, s2, b2, e2), f3 = resolve(ix, rcL, h3, s3, b3, e3);
+    cls = (uint8_t)(1 + (f0 ? 1 : 0) + (f1 ? 2 : 0) + (f2 ? 4 : 0) + (f3 ? 8 : 0));
     int s; uint32_t b, e, bl, el;                                       // (bl, el): the k-mer interval of the forced last position
     if (f0 && !f1 && f2 && !f3) { s = 0; b = b0; e = e0; bl = b2; el = e2; }      // :131-132 then :261+:268 at L - k
     else if (!f0 && f1 && !f2 && f3) { s = 1; b = b3; e = e3; bl = b1; el = e1; } // :131-132 then :372+:379 at 0 and at L - k

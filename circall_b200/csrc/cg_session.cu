@@ -12,6 +12,7 @@
 #include "cg_warp.cuh"
 #include "cg_tsm.cuh"
 #include "cg_pre.cuh"
+#include "cg_thr.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstddef>
@@ -21,6 +22,19 @@ using namespace cg;
 using namespace cgk;
 using cgi::GrowBuf;
 using cgi::PinBuf;
+
+// page-locked host array that only ever grows; resize() does not keep the old contents
+template <class T>
+struct PinVec {
+    PinBuf b; uint64_t n = 0;
+    cudaError_t resize(uint64_t m) { cudaError_t e = b.reserve(m * sizeof(T) + 16); if (e == cudaSuccess) n = m; return e; }
+    T* data() const { return b.as<T>(); }
+    uint64_t size() const { return n; }
+    T& operator[](uint64_t i) const { return b.as<T>()[i]; }
+    T* begin() const { return data(); }
+    T* end() const { return data() + n; }
+    void release() { b.release(); n = 0; }
+};
 
 namespace {
 
@@ -36,8 +50,10 @@ struct BatchHdr {
     int status;
     uint32_t n_ovf_wt;             // mates / records the fast path handed to the general kernels
     uint32_t n_ovf_bsj;
-    uint32_t n_t2_wt;              // mates / records the thread state machine handed to the warp kernels
+    uint32_t n_t2_wt;              // mates the front kernel (or the state machine) declined / records the state machine declined
     uint32_t n_t2_bsj;
+    uint32_t n_t3_wt;              // mates / records the lockstep thread tier handed to the warp kernels
+    uint32_t n_t3_bsj;
 };
 
 // ---- warp-per-read kernels --------------------------------------------------------------------------
@@ -263,6 +279,68 @@ k_flag_write(const uint8_t* __restrict__ f, uint64_t n, const uint32_t* __restri
     uint32_t o = bc[blockIdx.x] + pre + x - c;
 #pragma unroll
     for (int y = 0; y < CP_ITEMS; ++y) if (v[y]) out[o++] = (uint32_t)(base + y);
+}
+
+// ---- counting sort of the non-zero entries of a class array (values 1..16): indices grouped by class ------------
+// The lockstep thread tier runs one read per lane; a warp is efficient when its 32 reads take the same path, and the path
+// is mostly decided by which of the read's four end k-mers (first, last, their reverse complements) are in the table.
+// bc is class-major (bc[c * nb + block]) so that ONE exclusive scan (k_flag_scan) yields every block's write offsets.
+static const int CLS_N = 16;
+__global__ void __launch_bounds__(CP_THREADS)
+k_cls_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ bc, uint32_t nb) {
+    __shared__ uint32_t sh[CLS_N];
+    if (threadIdx.x < CLS_N) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
+#pragma unroll
+    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) atomicAdd(&sh[(c - 1) & (CLS_N - 1)], 1u); }
+    __syncthreads();
+    if (threadIdx.x < CLS_N) bc[threadIdx.x * nb + blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(CP_THREADS)
+k_cls_write(const uint8_t* __restrict__ f, uint64_t n, const uint32_t* __restrict__ bc, uint32_t nb, uint32_t* __restrict__ out) {
+    __shared__ uint32_t cur[CLS_N];
+    if (threadIdx.x < CLS_N) cur[threadIdx.x] = bc[threadIdx.x * nb + blockIdx.x];
+    __syncthreads();
+    uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
+#pragma unroll
+    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) out[atomicAdd(&cur[(c - 1) & (CLS_N - 1)], 1u)] = (uint32_t)(base + x); }
+}
+
+// Circall_bsj has no front kernel in front of the lockstep tier: this one only classifies the exported records
+// (cls[rec] = 1 + f0 + 2 f1 + 4 f2 + 8 f3 for the k-mers read[0,k), its reverse complement, read[L-k,L), its reverse
+// complement; 1 for a read with an N or shorter than k + 1)
+__global__ void __launch_bounds__(256)
+k_bsj_cls(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
+          const uint32_t* __restrict__ n_dev, uint8_t* __restrict__ cls) {
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_fixed;
+    const uint64_t rec = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (rec >= n) return;
+    const IndexView& ix = cgw::c_ix[1];
+    const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
+    const uint64_t* w = pk + r * (uint64_t)g.WT;
+    const int L = lens[r], k = ix.k;
+    uint8_t c = 1;
+    bool anyN = false;
+    for (int j = 0; j < g.WMf; ++j) {
+        const int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = __ldg(w + g.W2f + j);
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        anyN |= mk != 0;
+    }
+    if (!anyN && L > k) {
+        const int j = (L - k) >> 5, sh = ((L - k) & 31) * 2;
+        const uint64_t lo = __ldg(w + j), hi = sh ? __ldg(w + j + 1) : 0ULL;
+        const uint64_t mer0 = __ldg(w) & ix.km, merL = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & ix.km;
+        const uint64_t rc0 = revcomp(mer0, k), rcL = revcomp(merL, k);
+        const uint64_t h0 = home_slot(ix, mer0), h1 = home_slot(ix, rc0), h2 = home_slot(ix, merL), h3 = home_slot(ix, rcL);
+        const u32x4 s0 = __ldg(&ix.hslots[h0]), s1 = __ldg(&ix.hslots[h1]), s2 = __ldg(&ix.hslots[h2]), s3 = __ldg(&ix.hslots[h3]);
+        uint32_t b, e;
+        c = (uint8_t)(1 + (resolve(ix, mer0, h0, s0, b, e) ? 1 : 0) + (resolve(ix, rc0, h1, s1, b, e) ? 2 : 0)
+                        + (resolve(ix, merL, h2, s2, b, e) ? 4 : 0) + (resolve(ix, rcL, h3, s3, b, e) ? 8 : 0));
+    }
+    cls[rec] = c;
 }
 
 // ---- Circall_bsj ----------------------------------------------------------------------------------
@@ -634,14 +712,100 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
         anyN |= mk != 0;
     }
     bool done = false;
-    uint8_t fl = 0; uint32_t nh = 0;
+    uint8_t fl = 0, cls = 1; uint32_t nh = 0;
     if (!anyN) {
         for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
         m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
-        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh);
+        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh, cls);
     }
     if (done) { flags[r] = fl; nhits[r] = nh; }
-    ovf[r] = done ? 0 : 1;
+    ovf[r] = done ? 0 : cls;          // declined: the look-up class (1..16), see k_cls_*
+}
+
+// ---- lockstep thread tier (cg_thr.cuh): one thread per read, single-strand reads ------------------------------------
+static const int THR_THREADS = 128;
+// stage the packed read of this thread into its scratch; false when the read holds an N (or is empty)
+__device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, const PackGeom& g, int L, const cgq::QMem& m) {
+    bool anyN = L < 1;
+    for (int j = 0; j < g.WMf; ++j) {
+        const int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = __ldg(rec + g.W2f + j);
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        anyN |= mk != 0;
+    }
+    if (anyN) return false;
+    for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
+    m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
+    cgt::tsm_make_rc(m, L);
+    return true;
+}
+
+// Circall_wt: over the mates list[0..*n_list) the front kernel declined (all n_reads mates when list is null); ovf[r] = 1 hands
+// mate r to the warp kernels
+__global__ void __launch_bounds__(THR_THREADS, CG_THR_MINB)
+k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
+         const uint32_t* __restrict__ n_list, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf) {
+    extern __shared__ uint32_t thr_smem[];
+    const uint64_t x = (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
+    if (x >= (list ? (uint64_t)*n_list : n_reads)) return;
+    const uint64_t r = list ? (uint64_t)list[x] : x;
+    const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+    cgq::QMem m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+    uint8_t fl = 0; uint32_t nh = 0; int why = 0;
+    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why);
+    if (done) { flags[r] = fl; nhits[r] = nh; }
+    else ovf[r] = 1;
+}
+
+// Circall_bsj: over the records list[0..*n_list) (every exported record when list is null); ovf[rec] = 1 hands record rec to
+// the warp kernels (nothing was emitted for it)
+__global__ void __launch_bounds__(THR_THREADS, CG_THR_MINB)
+k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
+          const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf) {
+    extern __shared__ uint32_t thr_smem[];
+    const uint64_t n = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
+    const uint64_t x = (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
+    const bool active = x < n;
+    const uint64_t rec = active && list ? (uint64_t)list[x] : x;
+    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
+    if (active) {
+        const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
+        const int L = lens[r];
+        cgq::QMem m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+        JSink sink; sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; sink.rec = (uint32_t)rec;
+        uint32_t nh = 0; bool split = false; int why = 0;
+        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record(cgw::c_ix[1], m, L, lceMode, sink, nh, split, why);
+        if (!done) ovf[rec] = 1;
+        else {
+            // commit (Circall_bsj.cpp:383-491)
+            o.rec_nhits[rec] = nh; o.rec_split[rec] = split ? 1 : 0;
+            upper = nh > 0;                                                       // :383
+            const uint32_t c = nh > (uint32_t)MAX_READ_OCCS ? 0 : nh;             // :385
+            const bool cand = c > 0 && split;                                     // :390
+            obs = 1; mapped = cand; hits = c;                                     // :488-491
+            if (cand) {
+                if (c == 1) { if (do_counts & 1) atomicAdd(&o.per_bsj[m.ld(m.cb())], 1ULL); }     // EquivalenceClassBuilder.hpp:112-130
+                else if (do_counts & 2) {
+                    const unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL), sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)c);
+                    if (e < o.eq_cap && sidx + c <= o.eq_tids_cap) {
+                        o.eq_ent[e] = make_uint4((uint32_t)rec, (uint32_t)sidx, c, 0u);
+                        for (uint32_t t = 0; t < c; ++t) o.eq_tids[sidx + t] = m.ld(m.cb() + t);
+                    }
+                }
+            }
+        }
+    }
+    if (do_counts & 1) {
+        obs = __reduce_add_sync(0xffffffffu, obs); mapped = __reduce_add_sync(0xffffffffu, mapped);
+        hits = __reduce_add_sync(0xffffffffu, hits); upper = __reduce_add_sync(0xffffffffu, upper);
+        if ((threadIdx.x & 31) == 0) {
+            if (obs) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)obs);
+            if (mapped) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)mapped);
+            if (hits) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)hits);
+            if (upper) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)upper);
+        }
+    }
 }
 
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -660,6 +824,7 @@ struct cg_session {
     int gen_grid = 0;                            // grid of the general kernels (sized with the per-warp global scratch)
     int sms = 0;
     bool use_pre = true;                         // Circall_wt front kernel for clean full-length matches (CG_NO_PRE=1 switches it off)
+    bool use_thr = true;                         // lockstep thread tier in front of the warp kernels (CG_NO_THR=1 switches it off)
     bool use_tsm = false;                        // first tier = thread state machine (CG_TSM=1 switches it on; experimental: parity-green, not yet faster)
     unsigned char* d_gscratch = nullptr;
     bool pending = false;
@@ -672,17 +837,20 @@ struct cg_session {
     const uint64_t* in_off1 = nullptr; const uint64_t* in_off2 = nullptr;
     // device buffers
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
-        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2;
+        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3;
     unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
     // host result buffers
     PinBuf h_hdr;
-    std::vector<uint32_t> h_exp_mate, h_exp_pair, h_cand, h_recnh, h_eq_tids_raw, h_eq_tids;
-    std::vector<uint8_t> h_exp_code, h_recsp, h_mflags;
-    std::vector<uint16_t> h_mnhits;
-    std::vector<cg_junction> h_junc;
-    std::vector<uint4> h_eqent;
+    // device -> host landing buffers are page-locked (a copy into pageable memory is staged and blocks the caller)
+    PinVec<uint32_t> h_exp_mate, h_recnh, h_eq_tids_raw;
+    PinVec<uint8_t> h_recsp, h_mflags;
+    PinVec<uint16_t> h_mnhits;
+    PinVec<cg_junction> h_junc;
+    PinVec<uint4> h_eqent;
+    std::vector<uint32_t> h_exp_pair, h_cand, h_eq_tids;
+    std::vector<uint8_t> h_exp_code;
     std::vector<uint64_t> h_eq_off;
     uint32_t wt_read_len = 0, bsj_read_len = 0;
 };
@@ -709,6 +877,15 @@ int compact_flags(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, ui
     return launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, f, n, s->d_bc.as<uint32_t>(), out);
 }
 
+// indices of the non-zero entries of the class array f[0..n), grouped by class (1..16); count into *total
+int compact_classes(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, uint32_t* total) {
+    uint32_t nb = grid_for(n, CP_TILE);
+    int rc = launch(s, k_cls_count, dim3(nb), dim3(CP_THREADS), 0, f, n, s->d_bc.as<uint32_t>(), nb);
+    if (rc) return rc;
+    rc = launch(s, k_flag_scan, dim3(1), dim3(1024), 0, s->d_bc.as<uint32_t>(), nb * CLS_N, total);
+    if (rc) return rc;
+    return launch(s, k_cls_write, dim3(nb), dim3(CP_THREADS), 0, f, n, (const uint32_t*)s->d_bc.as<uint32_t>(), nb, out);
+}
 
 // launch the block-sorted state machine over n_fixed mates (wt) / the exported records (bsj); persistent grid
 template <bool BSJ>
@@ -741,25 +918,42 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     const dim3 blk(WARPS_PER_BLOCK * 32);
     const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, false, true), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, true, true);
     int rc;
-    const uint8_t* ovf_fast = s->d_ovf.as<uint8_t>();
+    // tiers: (experimental state machine,) lockstep thread tier, fast warp kernel, general warp kernel — each over the records
+    // the one before it declined
+    const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;            // records still to map (null: all of them)
     if (s->use_tsm) {
-        // tier 1: thread state machine; tier 2: the fast warp kernel over what it handed on
         rc = launch_tsm<true>(s, s->n_pairs, em, o, do_counts);
         if (rc) return rc;
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
         if (rc) return rc;
-        CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, worst, s->stream));
-        rc = launch(s, k_bsj_warp<false, true>, dim3(s->warp_grid_bsj), blk, smf,
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+        cur_list = s->d_list.as<uint32_t>(); cur_n = &dh->n_t2_bsj;
+    } else if (s->use_thr) {
+        // classify the records by their end k-mers, group them by class, map them one per thread
+        CG_CUDA(cudaMemsetAsync(s->d_ovf3.p, 0, worst, s->stream));
+        rc = launch(s, k_bsj_cls, dim3(grid_for(worst, 256)), dim3(256), 0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs,
+                    em ? (const uint32_t*)&dh->n_exp : (const uint32_t*)nullptr, s->d_ovf3.as<uint8_t>());
         if (rc) return rc;
-        ovf_fast = s->d_ovf2.as<uint8_t>();
-    } else {
+        rc = compact_classes(s, s->d_ovf3.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
+        if (rc) return rc;
+        rc = launch(s, k_bsj_thr, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMem::words(s->geom.W2f + 1) * 4,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj,
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>());
+        if (rc) return rc;
+        rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
+        if (rc) return rc;
+        cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_bsj;
+    }
+    CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, worst, s->stream));
+    const uint8_t* ovf_fast = s->d_ovf2.as<uint8_t>();
+    if (cur_list)
+        rc = launch(s, k_bsj_warp<false, true>, dim3(s->warp_grid_bsj), blk, smf,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, cur_list, cur_n,
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+    else
         rc = launch(s, k_bsj_warp<false, false>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
-        if (rc) return rc;
-    }
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+    if (rc) return rc;
     rc = compact_flags(s, ovf_fast, worst, s->d_list2.as<uint32_t>(), &dh->n_ovf_bsj);
     if (rc) return rc;
     return launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
@@ -778,11 +972,13 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_nhits.reserve(n_reads * 4));
     CG_CUDA(s->d_expflag.reserve(n_reads + 16));
     CG_CUDA(s->d_exp.reserve(n_reads * 4));
-    CG_CUDA(s->d_bc.reserve((n_reads / CP_TILE + 2) * 4));
+    CG_CUDA(s->d_bc.reserve((n_reads / CP_TILE + 2) * 4 * CLS_N));
     CG_CUDA(s->d_ovf.reserve(n_reads + 16));
     CG_CUDA(s->d_list.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_ovf2.reserve(n_reads + 16));
     CG_CUDA(s->d_list2.reserve(n_reads * 4 + 16));
+    CG_CUDA(s->d_ovf3.reserve(n_reads + 16));
+    CG_CUDA(s->d_list3.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
@@ -809,10 +1005,11 @@ int run_batch(cg_session* s) {
         CG_CUDA(cudaMemcpyToSymbolAsync(cgw::c_ix, &v, sizeof(IndexView), 0, cudaMemcpyHostToDevice, s->stream));
         const dim3 blk(WARPS_PER_BLOCK * 32);
         const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false);
-        const uint8_t* ovf_fast = s->d_ovf.as<uint8_t>();
+        // the tiers, each over the mates the one before it declined: front kernel (clean full-length matches, one thread
+        // per mate; or the experimental state machine), lockstep thread tier (single-strand reads with mismatches), fast
+        // warp kernel, general warp kernel
+        const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;        // mates still to map (null: all of them)
         if (s->use_tsm || s->use_pre) {
-            // tier 1: the front kernel (clean full-length matches, one thread per mate) — or the experimental state
-            // machine; tier 2: the fast warp kernel over the mates it declined
             if (s->use_tsm) {
                 BsjOut none; memset(&none, 0, sizeof none);
                 CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, n_reads, s->stream));
@@ -822,20 +1019,33 @@ int run_batch(cg_session* s) {
                             s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>());
             }
             if (rc) return rc;
-            rc = compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt);
+            // the front kernel leaves a look-up class per declined mate: the lockstep tier wants its work grouped by it
+            rc = (s->use_thr && !s->use_tsm) ? compact_classes(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt)
+                                             : compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt);
             if (rc) return rc;
-            CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, n_reads, s->stream));
+            cur_list = s->d_list.as<uint32_t>(); cur_n = &dh->n_t2_wt;
+        }
+        if (s->use_thr) {
+            CG_CUDA(cudaMemsetAsync(s->d_ovf3.p, 0, n_reads, s->stream));
+            rc = launch(s, k_wt_thr, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMem::words(g.W2f + 1) * 4,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, s->opts.lce_mode,
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>());
+            if (rc) return rc;
+            rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
+            if (rc) return rc;
+            cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_wt;
+        }
+        CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, n_reads, s->stream));
+        const uint8_t* ovf_fast = s->d_ovf2.as<uint8_t>();
+        if (cur_list)
             rc = launch(s, k_wt_warp<false, true>, dim3(s->warp_grid_wt), blk, smf,
-                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_wt, s->opts.lce_mode,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, s->opts.lce_mode,
                         s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
-            if (rc) return rc;
-            ovf_fast = s->d_ovf2.as<uint8_t>();
-        } else {
+        else
             rc = launch(s, k_wt_warp<false, false>, dim3(s->warp_grid_wt), blk, smf,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), (unsigned char*)nullptr);
-            if (rc) return rc;
-        }
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+        if (rc) return rc;
         rc = compact_flags(s, ovf_fast, n_reads, s->d_list2.as<uint32_t>(), &dh->n_ovf_wt);
         if (rc) return rc;
         rc = launch(s, k_wt_warp<true, true>, dim3(s->gen_grid), blk, smg,
@@ -865,8 +1075,8 @@ int run_batch(cg_session* s) {
 }
 
 template <class T>
-int d2h(cg_session* s, std::vector<T>& dst, const void* src, uint64_t n) {
-    dst.resize(n);
+int d2h(cg_session* s, PinVec<T>& dst, const void* src, uint64_t n) {
+    CG_CUDA(dst.resize(n));
     if (n) CG_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
     return CG_OK;
 }
@@ -909,6 +1119,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
         s->sms = sms; s->use_tsm = getenv("CG_TSM") != nullptr && atoi(getenv("CG_TSM")) != 0;
         s->use_pre = getenv("CG_NO_PRE") == nullptr;
+        s->use_thr = getenv("CG_NO_THR") == nullptr;
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
         s->gen_grid = sms * 2;
@@ -925,9 +1136,11 @@ void cg_session_destroy(cg_session* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
-                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2})
+                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3})
         b->release();
     s->h_hdr.release();
+    s->h_exp_mate.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();
+    s->h_mnhits.release(); s->h_junc.release(); s->h_eqent.release();
     if (s->d_acc) cudaFree(s->d_acc);
     if (s->d_gscratch) cudaFree(s->d_gscratch);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1019,8 +1232,8 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     out->n_eq = hdr.n_eq;
     out->n_fallback_wt = hdr.n_ovf_wt;
     out->n_fallback_bsj = hdr.n_ovf_bsj;
-    out->n_tier2_wt = hdr.n_t2_wt;
-    out->n_tier2_bsj = hdr.n_t2_bsj;
+    out->n_tier2_wt = s->use_thr ? hdr.n_t3_wt : hdr.n_t2_wt;          // reads that reached the warp kernels
+    out->n_tier2_bsj = s->use_thr && !s->use_tsm ? hdr.n_t3_bsj : hdr.n_t2_bsj;
     if (s->input_on_device && s->wt_read_len == 0 && s->n_pairs) {
         uint16_t l0 = 0;
         CG_CUDA(cudaMemcpy(&l0, s->d_lens.p, 2, cudaMemcpyDeviceToHost));
@@ -1066,7 +1279,7 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
         // classes in record order
         std::sort(s->h_eqent.begin(), s->h_eqent.end(), [](const uint4& a, const uint4& b) { return a.x < b.x; });
         s->h_eq_off.assign(1, 0); s->h_eq_tids.clear();
-        for (auto& e : s->h_eqent) {
+        for (const uint4& e : s->h_eqent) {
             s->h_eq_tids.insert(s->h_eq_tids.end(), s->h_eq_tids_raw.begin() + e.y, s->h_eq_tids_raw.begin() + e.y + e.z);
             s->h_eq_off.push_back(s->h_eq_tids.size());
         }

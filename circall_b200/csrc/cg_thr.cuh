@@ -1,0 +1,435 @@
+// circall_b200 — thread-per-read collector for single-strand reads ("lockstep tier"): second front kernel of
+// k_wt (after cg_pre.cuh) and front kernel of k_bsj.
+//
+// The clean-match front kernel showed what this hardware wants: one THREAD per read with several independent
+// random sectors in flight each, as long as the 32 reads of a warp run the same instructions.  This file gives
+// the same treatment to the reads that carry mismatches (or, in Circall_bsj, lie near a junction): the whole of
+// SACollectorCircall::operator() (include/SACollectorCircall.hpp:24-582) for a read whose hits sit on ONE strand,
+// written so that every heavy operation occurs exactly once in the instruction stream —
+//
+//     for each segment of the read:   LOOK (table look-ups, 8 in flight)  ->  EXTEND (extendSearchNaive, 4 suffixes
+//                                     in flight)  ->  LCE  ->  next position
+//
+// — and the lanes of a warp meet at each of them whatever segment of whatever strand they are on.  (The resumable /
+// sequential state machines of cg_tsm.cuh failed on exactly this: every control state carried its own copy of the
+// engines and the lanes ran them one after the other.)
+//
+// What makes the single loop possible, following the reference statement by statement (k = 31, read without N):
+//   * Phase A (:112-200) looks up the k-mer at 0 and its reverse complement; Phase B's / C's "expected present"
+//     look-ups only ever happen at positions 0 and L - k of the strand being scanned (:224-228 after a match that
+//     reached the read's end, :300-321 the forced last position, :332-344 the start of Phase C).  The four k-mers
+//     involved — read[0,k), read[L-k,L) and their reverse complements — are looked up together up front (as the
+//     clean-match kernel does) and answer all of those.
+//   * every other look-up is part of a walk over positions whose k-mers are expected to be absent (the windows
+//     that cover a mismatch, or the hunt for a first seed): the positions visited do not depend on the results, so
+//     eight go out per round and the first present one is taken.
+//   * a read with hits on both strands (`other` look-up present, :265-272 / :379-385, or both k-mers in Phase A)
+//     needs the kmerScores vote (:442-490): declined.
+// Declined as well (nothing is emitted, the warp-per-read kernels redo the read from scratch with identical
+// results): N in the read, a homopolymer window among the looked-up positions, a k-mer interval starting at SA index
+// 0, an open interval wider than Q_W in the extension, more than Q_FI intervals, a maximal interval wider than Q_W in
+// the hit enumeration, an interval wider than Q_SPAN in the span filter.
+//
+// Hit enumeration: cg_warp.cuh::w_hits_lanes' exact shortcut (intervals whose query range lies inside a longer one
+// of the same strand never change the intersection) with the candidates in the thread's scratch.
+//
+// CG_HD throughout: tests/emu runs the same functions on the host in front of the emulated warp tiers.
+#pragma once
+#include "cg_tsm.cuh"
+
+#ifndef CG_THR_MINB
+#define CG_THR_MINB 5      // resident blocks per SM asked of the lockstep kernels (96 registers; measured: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5, 6 -> 5.46 / 10.8;
+                           // asking for the largest shared-memory carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors)
+#endif
+
+namespace cgq {
+using namespace cg;
+
+static const int Q_FI = 8;        // intervals kept (one strand)
+static const int Q_W = 16;        // widest interval resolved suffix by suffix (extension, hit candidates, intersection)
+static const int Q_SPAN = 64;     // widest interval the span filter walks
+
+// Per-thread scratch of 32-bit words, word j at base[j * stride] (stride = threads per block on the device; 1 on the host)
+//   [0, 2 W2)         forward code words, 16 bases each (W2 = 64-bit words incl. one zero pad word)
+//   [2 W2, 4 W2)      reverse-complement strand, same layout
+//   [4 W2, +3 Q_FI)   intervals: begin, end, len | qpos << 16
+//   then Q_W          hit candidates (transcript ids)
+struct QMem {
+    uint32_t* base; int stride; int W2;
+    CG_HD uint32_t ld(int j) const { return base[(size_t)j * stride]; }
+    CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
+    CG_HD int iv(int i) const { return 4 * W2 + 3 * i; }
+    CG_HD int cb() const { return 4 * W2 + 3 * Q_FI; }
+    CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI + Q_W; }
+    // 32-base window of strand s at oriented position i (i < L)
+    CG_HD uint64_t chunk(int s, int i) const {
+        int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
+        uint32_t a = ld(p), b = ld(p + 1), c = ld(p + 2);
+        return (uint64_t)cgt::fsr(a, b, sh) | ((uint64_t)cgt::fsr(b, c, sh) << 32);
+    }
+};
+
+enum { Q_NOTFOUND = 0, Q_FOUND = 1 };
+// decline reasons (negative return values; tests/emu counts them)
+enum { QD_HOMO = -1, QD_BOTH_A = -2, QD_OTHER = -3, QD_SA0 = -4, QD_WIDE_EXT = -5, QD_NINT = -6, QD_WIDE_HITS = -7, QD_WIDE_SPAN = -8, QD_ODD = -9, QD_N = -10 };
+
+// longest common prefix of strand s of the read from query offset q and the text at p, compared over [i0, lim)
+CG_HD int q_match(const IndexView& ix, const QMem& m, int s, int q, uint32_t p, int i0, int lim) {
+    int i = i0;
+    uint32_t curb = 0xffffffffu;
+    u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
+    cgt::u32x2 mk; mk.x = mk.y = 0;
+    while (i < lim) {
+        const uint32_t tp = p + (uint32_t)i, b = tp >> 6;
+        if (b != curb) { cc = CG_LDG(&ix.text[2 * (uint64_t)b]); mk = CG_LDG(cgt::mask_ptr(ix, b)); curb = b; }
+        const int half = (tp >> 5) & 1, o5 = tp & 31;
+        const uint64_t tw = cgt::half_codes(cc, half) >> (2 * o5);
+        const uint32_t tm = (half ? mk.y : mk.x) >> o5;
+        const int n = cmin(32 - o5, lim - i);
+        const uint64_t x = tw ^ m.chunk(s, q + i);
+        const uint64_t d = (x | (x >> 1)) & EVEN;
+        const int j = cmin(d ? (ctz64(d) >> 1) : 32, tm ? ctz32(tm) : 32);
+        if (j < n) return i + j;
+        i += n;
+    }
+    return i;
+}
+
+// SASearcher::lce on two text positions (cg::lce after its suffix-array reads)
+CG_HD int q_lce(const IndexView& ix, uint32_t o1, uint32_t o2, int startAt, int stopAt, int mode) {
+    if (mode == 0) { o1 += (uint32_t)startAt; o2 += (uint32_t)startAt; }
+    int len = startAt;
+    const uint32_t mx = cmax(o1, o2);
+    const int64_t room = (int64_t)ix.n - (int64_t)mx;
+    const int lim = (int)cmin<int64_t>((int64_t)stopAt, room);
+    uint32_t b1c = 0xffffffffu, b2c = 0xffffffffu;
+    u32x4 c1, c2; c1.x = c1.y = c1.z = c1.w = 0; c2 = c1;
+    cgt::u32x2 m1, m2; m1.x = m1.y = 0; m2 = m1;
+    while (len < lim) {
+        const uint32_t a = o1 + (uint32_t)len, b = o2 + (uint32_t)len;
+        if ((a >> 6) != b1c) { b1c = a >> 6; c1 = CG_LDG(&ix.text[2 * (uint64_t)b1c]); m1 = CG_LDG(cgt::mask_ptr(ix, b1c)); }
+        if ((b >> 6) != b2c) { b2c = b >> 6; if (b2c == b1c) { c2 = c1; m2 = m1; } else { c2 = CG_LDG(&ix.text[2 * (uint64_t)b2c]); m2 = CG_LDG(cgt::mask_ptr(ix, b2c)); } }
+        const int ha = (a >> 5) & 1, oa = a & 31, hb = (b >> 5) & 1, ob = b & 31;
+        const uint64_t wa = cgt::half_codes(c1, ha) >> (2 * oa), wb = cgt::half_codes(c2, hb) >> (2 * ob);
+        const uint32_t ma = (ha ? m1.y : m1.x) >> oa, mb = (hb ? m2.y : m2.x) >> ob;
+        const int n = cmin(cmin(32 - oa, 32 - ob), lim - len);
+        const uint64_t x = wa ^ wb;
+        const uint64_t d = (x | (x >> 1)) & EVEN;
+        const uint32_t mm = ma | mb;
+        const int j = cmin(d ? (ctz64(d) >> 1) : 32, mm ? ctz32(mm) : 32);
+        if (j < n) return len + j;
+        len += n;
+    }
+    return len;
+}
+
+struct QProbe { bool f; uint32_t b, e; };
+
+// The position walk (:112-132 with both = true: k-mer and reverse complement, a position counts when either is there;
+// :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, eight look-ups per round.
+// Returns the first position that hits (F: the k-mer's own look-up, hasR: its reverse complement's, both only) or -1;
+// homo is set when a looked-up window is a homopolymer (the caller declines).
+CG_HD int q_walk(const IndexView& ix, const QMem& m, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
+    const int k = ix.k;
+    const int sh = both ? 1 : 0, per = 8 >> sh;
+    F.f = false; F.b = F.e = 0; hasR = false;
+    while (o <= lim) {
+        uint64_t key[8]; u32x4 sl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int p = o + (i >> sh);
+            const bool in = p <= lim;
+            const uint64_t mer = m.chunk(s, in ? p : o) & ix.km;
+            homo |= in && homopolymer_ix(mer, ix);
+            key[i] = (both && (i & 1)) ? revcomp(mer, k) : mer;
+            sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;          // an empty slot: not found
+            if (in) sl[i] = CG_LDG(&ix.hslots[home_slot(ix, key[i])]);
+        }
+        if (homo) return -1;
+        // resolve from the last look-up to the first: what is left at the end belongs to the first position that hits
+        int pos = -1;
+        bool r = false;                                            // reverse complement of the pair being resolved (both)
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            uint32_t b1 = 0, e1 = 0;
+            const bool f = resolve(ix, key[i], home_slot(ix, key[i]), sl[i], b1, e1);
+            if (both) {
+                if (i & 1) r = f;
+                else if (f || r) { pos = o + (i >> 1); F.f = f; F.b = b1; F.e = e1; hasR = r; }
+            } else if (f) { pos = o + i; F.f = true; F.b = b1; F.e = e1; }
+        }
+        if (pos >= 0) return pos;
+        o += per;
+    }
+    return -1;
+}
+
+// SACollectorCircall::operator() up to and including the strand vote for a read whose hits lie on one strand.
+// Returns Q_FOUND (n intervals of strand S in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.
+CG_HD int q_collect(const IndexView& ix, const QMem& m, int L, int lceMode, int& n, int& S) {
+    const int k = ix.k, skipOverlap = k - 1;
+    n = 0; S = 0;
+    if (L > 0xffff) return QD_ODD;
+    if (!(k < L)) return Q_NOTFOUND;       // Phase A's loop needs rb + k < L (:112)
+    // the four look-ups every path starts with: read[0,k), read[L-k,L) and their reverse complements
+    QProbe F0, R0, FL, RL;
+    {
+        const uint64_t mer0 = m.chunk(0, 0) & ix.km, merL = m.chunk(0, L - k) & ix.km;
+        if (homopolymer_ix(mer0, ix) || homopolymer_ix(merL, ix)) return QD_HOMO;
+        const uint64_t rc0 = revcomp(mer0, k), rcL = revcomp(merL, k);
+        const uint64_t h0 = home_slot(ix, mer0), h1 = home_slot(ix, rc0), h2 = home_slot(ix, merL), h3 = home_slot(ix, rcL);
+        const u32x4 s0 = CG_LDG(&ix.hslots[h0]), s1 = CG_LDG(&ix.hslots[h1]), s2 = CG_LDG(&ix.hslots[h2]), s3 = CG_LDG(&ix.hslots[h3]);
+        F0.b = F0.e = R0.b = R0.e = FL.b = FL.e = RL.b = RL.e = 0;
+        F0.f = resolve(ix, mer0, h0, s0, F0.b, F0.e); R0.f = resolve(ix, rc0, h1, s1, R0.b, R0.e);
+        FL.f = resolve(ix, merL, h2, s2, FL.b, FL.e); RL.f = resolve(ix, rcL, h3, s3, RL.b, RL.e);
+    }
+    bool phaseA = true, firstB = false, expectAbsent = false, lastSearch = false, homo = false;
+    int s = 0, o = 0;
+    for (;;) {
+        // ---------------- LOOK: the next position of strand s whose k-mer is in the table ----------------
+        int pos = -1;
+        QProbe hit; hit.f = false; hit.b = hit.e = 0;
+        bool other = false;
+        bool walk; int wlim;
+        if (phaseA) {
+            wlim = L - k - 1;                                                      // `re < read.end()` (:112)
+            if (F0.f || R0.f) { pos = 0; hit = F0; other = R0.f; walk = false; }   // :131-132 at position 0
+            else { walk = true; o = 1; }
+        } else {
+            wlim = L - k;                                                          // :234 / :341-344
+            walk = expectAbsent;
+            if (!walk) {
+                // expected present (:261+:268 / :372+:379): only ever asked at 0 or L - k, answered up front
+                QProbe a, b;
+                if (o == 0) { if (s == 0) { a = F0; b = R0; } else { a = RL; b = FL; } }
+                else if (o == L - k) { if (s == 0) { a = FL; b = RL; } else { a = R0; b = F0; } }
+                else return QD_ODD;
+                if (a.f) { pos = o; hit = a; other = b.f; }
+                else { o += 1; walk = true; }                                      // :324 / :436, then a walk
+            }
+        }
+        if (walk) {
+            bool hasR = false;
+            pos = q_walk(ix, m, s, o, wlim, phaseA, hit, hasR, homo);
+            if (homo) return QD_HOMO;
+            if (pos >= 0) {
+                if (phaseA) other = hasR;
+                else {                                                             // :268 / :379
+                    uint32_t b2, e2;
+                    other = probe(ix, revcomp(m.chunk(s, pos) & ix.km, k), b2, e2);
+                }
+            }
+        }
+        if (pos < 0) {
+            if (phaseA) return Q_NOTFOUND;                                         // :204
+            break;                                                                 // ran off the read: the strand is done
+        }
+        o = pos;
+        bool extendIt = true;
+        if (phaseA) {
+            phaseA = false;
+            if (hit.f && other) return QD_BOTH_A;                                 // both strands seeded: the vote decides
+            if (hit.f) { S = s = 0; firstB = true; }                               // :134-176, Phase B follows
+            else { S = s = 1; o = 0; expectAbsent = false; extendIt = false; }     // :178-191: rcHit only, Phase C from 0 (:332-346)
+        } else if (other) return QD_OTHER;                                       // :265-272 / :381-385: the other strand scores too
+        if (!extendIt) continue;
+        // ---------------- EXTEND: extendSearchNaive(b - 1, e) from position o (:143 / :280 / :393) ----------------
+        if (hit.b == 0) return QD_SA0;
+        uint32_t lb = hit.b, ub = hit.e;
+        int matched = k;
+        const int mq = L - o;
+        if (mq > k) {
+            const uint32_t w = hit.e - hit.b;
+            if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
+            int best = -1; uint32_t first = 0, last = 0;
+            for (uint32_t c0 = 0; c0 < w; c0 += 4) {
+                uint32_t p[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c0 + c < w) {
+                        const int l = q_match(ix, m, s, o, p[c], k, mq);
+                        if (l > best) { best = l; first = last = c0 + c; }
+                        else if (l == best) last = c0 + c;
+                    }
+                }
+            }
+            lb = hit.b + first; ub = hit.b + last + 1; matched = best;
+        }
+        if (ub > lb && ub - lb < 1000u) {                                          // :149 / :285 / :398 (maxInterval)
+            if (n >= Q_FI) return QD_NINT;
+            m.st(m.iv(n), lb); m.st(m.iv(n) + 1, ub); m.st(m.iv(n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
+            ++n;
+        }
+        if (lastSearch) break;                                                     // :300 / :412
+        // ---------------- LCE and the next position (:219-228 after Phase A, :302-321 / :414-433 in the loop) ----------------
+        const int mismatch = o + matched;
+        const int stopAt = L - mismatch;
+        int l = matched;
+        if (stopAt > matched) {                                                    // else lce returns startAt at once
+            const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
+            l = q_lce(ix, p1, p2, matched, stopAt, lceMode);
+        }
+        if (firstB) {
+            firstB = false;
+            const int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
+            const int o2 = cmin(cmax(0, L - k), o + fwdSkip);                      // :224-228
+            expectAbsent = stopAt > 0 && o2 < L - k;
+            o = o2;
+        } else if (mismatch < L) {
+            o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
+            if (o > L - k) { o = L - k; lastSearch = true; expectAbsent = false; }
+            else expectAbsent = true;
+        } else { lastSearch = true; o = L - k; expectAbsent = false; }
+        if (o + k > L) break;
+    }
+    return Q_FOUND;
+}
+
+// up to four SA positions -> transcript ids, the suffix-array entries then the text sectors as two waves of loads
+CG_HD void q_tids4(const IndexView& ix, uint32_t i0, int nn, uint32_t* tid) {
+    uint32_t p[4]; u32x4 t[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) p[x] = x < nn ? CG_LDG(&ix.sa[i0 + x]) : 0u;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { t[x].x = t[x].y = t[x].z = t[x].w = 0; if (x < nn) t[x] = CG_LDG(&ix.text[2 * (uint64_t)(p[x] >> 6) + 1]); }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) tid[x] = x < nn ? cgt::tid_from(t[x], p[x]) : 0xffffffffu;
+}
+
+// the n intervals of the scratch -> number of hit transcripts (intersectSAHits + collectHitsSimpleSA, or the single-interval
+// enumeration, :492-563); the candidates stay in the scratch (cb + c, c < nc) with `alive` marking the hits.  < 0: declined.
+CG_HD int q_hits(const IndexView& ix, const QMem& m, int n, uint32_t& alive, int& nc) {
+    alive = 0; nc = 0;
+    if (n == 0) return 0;
+    uint32_t keep = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t lqi = m.ld(m.iv(i) + 2);
+        const int li = (int)(lqi & 0xffffu), qi = (int)(lqi >> 16);
+        bool drop = false;
+        for (int y = 0; y < n; ++y) {
+            const uint32_t lqy = m.ld(m.iv(y) + 2);
+            const int ly = (int)(lqy & 0xffffu), qy = (int)(lqy >> 16);
+            drop |= (ly > li && qy <= qi && qy + ly >= qi + li);
+        }
+        if (!drop) keep |= 1u << i;
+    }
+    int mi = -1; uint32_t msp = 0xffffffffu; bool wide = false;
+    for (int i = 0; i < n; ++i) {
+        if (!((keep >> i) & 1u)) continue;
+        const uint32_t sp = m.ld(m.iv(i) + 1) - m.ld(m.iv(i));
+        if (sp > (uint32_t)Q_W) wide = true;
+        if (sp < msp) { msp = sp; mi = i; }
+    }
+    if (wide || mi < 0) return QD_WIDE_HITS;
+    const uint32_t mb = m.ld(m.iv(mi)), me = m.ld(m.iv(mi) + 1);
+    for (uint32_t c0 = 0; c0 < msp; c0 += 4) {
+        uint32_t t[4];
+        const int nn = (int)cmin<uint32_t>(4u, msp - c0);
+        q_tids4(ix, mb + c0, nn, t);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) if (x < nn) m.st(m.cb() + (int)c0 + x, t[x]);
+    }
+    nc = (int)msp;
+    for (int c = 0; c < nc; ++c) {                          // one candidate per distinct transcript
+        const uint32_t tc = m.ld(m.cb() + c);
+        bool dup = false;
+        for (int y = 0; y < c; ++y) dup |= m.ld(m.cb() + y) == tc;
+        if (!dup) alive |= 1u << c;
+    }
+    for (int x = 0; x < n; ++x) {
+        if (x == mi || !((keep >> x) & 1u)) continue;
+        const uint32_t ib = m.ld(m.iv(x)), ie = m.ld(m.iv(x) + 1);
+        if (ib == mb && ie == me) continue;                  // same positions: cannot drop a transcript
+        uint32_t seen = 0;
+        for (uint32_t c0 = ib; c0 < ie; c0 += 4) {
+            uint32_t t[4];
+            const int nn = (int)cmin<uint32_t>(4u, ie - c0);
+            q_tids4(ix, c0, nn, t);
+            for (int c = 0; c < nc; ++c) {
+                const uint32_t tc = m.ld(m.cb() + c);
+                if (tc == t[0] || tc == t[1] || tc == t[2] || tc == t[3]) seen |= 1u << c;      // unused entries are 0xffffffff
+            }
+        }
+        alive &= seen;
+    }
+#if defined(__CUDA_ARCH__)
+    return __popc(alive);
+#else
+    return __builtin_popcount(alive);
+#endif
+}
+
+// one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517): false = declined
+CG_HD bool q_wt_mate(const IndexView& ix, const QMem& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why) {
+    int n, S;
+    const int r = q_collect(ix, m, L, lceMode, n, S);
+    why = r;
+    if (r < 0) return false;
+    flags = 0; nh = 0;
+    if (r == Q_NOTFOUND) return true;
+    bool full = false;
+    for (int i = 0; i < n; ++i) full |= (int)(m.ld(m.iv(i) + 2) & 0xffffu) == pairLen;          // :318-342,493-517
+    uint32_t alive; int nc;
+    const int h = q_hits(ix, m, n, alive, nc);
+    if (h < 0) { why = h; return false; }
+    if (n > 0) flags |= MATE_SEEDED;                                                             // :311,486
+    if (full) flags |= MATE_FULL;
+    nh = (uint32_t)h;
+    return true;
+}
+
+// one record of Circall_bsj (src/Circall_bsj.cpp:300-399): false = declined (nothing was emitted).  On success the
+// hit transcripts are left in ascending order in the candidate words (cb + t, t < nh).
+template <class Sink>
+CG_HD bool q_bsj_record(const IndexView& ix, const QMem& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& why) {
+    int n, S;
+    const int r = q_collect(ix, m, L, lceMode, n, S);
+    why = r;
+    if (r < 0) return false;
+    nh = 0; split = false;
+    if (r == Q_NOTFOUND) return true;
+    uint32_t alive; int nc;
+    const int h = q_hits(ix, m, n, alive, nc);
+    if (h < 0) { why = h; return false; }
+    if (h == 0) return true;                                                                     // :319
+    for (int i = 0; i < n; ++i) if (m.ld(m.iv(i) + 1) - m.ld(m.iv(i)) > (uint32_t)Q_SPAN) { why = QD_WIDE_SPAN; return false; }
+    nh = (uint32_t)h;
+    // span filter over every SA position of every interval (:323-374)
+    for (int i = 0; i < n; ++i) {
+        const uint32_t ib = m.ld(m.iv(i)), ie = m.ld(m.iv(i) + 1), lq = m.ld(m.iv(i) + 2);
+        const int len = (int)(lq & 0xffffu);
+        for (uint32_t i0 = ib; i0 < ie; i0 += 4) {                                               // :326 / :355
+            const int nn = (int)cmin<uint32_t>(4u, ie - i0);
+            uint32_t tt[4], ll[4], o0[4], o1[4];
+            sa_tids4(ix, i0, nn, tt, ll);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) { o0[z] = o1[z] = 0; if (z < nn) { o0[z] = CG_LDG(&ix.offsets[tt[z]]); o1[z] = CG_LDG(&ix.offsets[tt[z] + 1]); } }
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+                if (z < nn) {
+                    const uint32_t refLen = o1[z] - o0[z] - 1;
+                    const int hitPos = (int)ll[z];
+                    const int junctPos = (int)(refLen / 2);                                      // :333
+                    if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {                  // :336 / :364
+                        sink.line((uint32_t)S, lq >> 16, (uint32_t)len, hitPos, tt[z]);
+                        split = true;
+                    }
+                }
+            }
+        }
+    }
+    // class key: the hit transcripts in ascending order
+    int j = 0;
+    for (int c = 0; c < nc; ++c) if ((alive >> c) & 1u) { m.st(m.cb() + j, m.ld(m.cb() + c)); ++j; }
+    for (int i = 1; i < j; ++i) {
+        const uint32_t v = m.ld(m.cb() + i);
+        int y = i - 1;
+        while (y >= 0 && m.ld(m.cb() + y) > v) { m.st(m.cb() + y + 1, m.ld(m.cb() + y)); --y; }
+        m.st(m.cb() + y + 1, v);
+    }
+    return true;
+}
+
+} // namespace cgq

@@ -72,11 +72,12 @@ def main():
             rd, wr = r[h.index("dram__bytes_read.sum")], r[h.index("dram__bytes_write.sum")]
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             b = float(rd) * scale[u[h.index("dram__bytes_read.sum")]] + float(wr) * scale[u[h.index("dram__bytes_write.sum")]]
-            key = "k_wt" if "k_wt" in k else "k_bsj" if "k_bsj" in k else k
-            if "false, false" in k.replace("(bool)0", "false") or "<0, 0>" in k or "0, (bool)0" in k:
-                traffic.setdefault(key, []).append(b)
-    tj = {k: sum(v) / len(v) for k, v in traffic.items()}
-    tj["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch of the fast (first-tier) instantiation, ncu --set full, %s" % os.path.basename(rep)
+            key = "k_wt" if "k_wt" in k else "k_bsj" if "k_bsj" in k else None
+            if key:
+                traffic.setdefault(key, {}).setdefault(k, []).append(b)
+    # a stage (what bench.py brackets with events as k_wt / k_bsj) = all of its tiers: mean bytes per launch of each kernel, summed
+    tj = {key: sum(sum(v) / len(v) for v in d.values()) for key, d in traffic.items()}
+    tj["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per batch, summed over the kernels (tiers) of the stage, ncu --set full, %s" % os.path.basename(rep)
     json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(open(os.path.join(ROOT, "profiles", tag + "_launches.txt")).read())
     print(json.dumps(tj, indent=1))

@@ -12,6 +12,7 @@
 #include "../../circall_b200/csrc/cg_pipeline.cuh"
 #include "../../circall_b200/csrc/cg_tsm.cuh"
 #include "../../circall_b200/csrc/cg_pre.cuh"
+#include "../../circall_b200/csrc/cg_thr.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -62,7 +63,44 @@ static bool pre_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L
     m.base = scratch.data();
     for (int j = 0; j < W2f; ++j) { m.st(2 * j, (uint32_t)pk[j]); m.st(2 * j + 1, (uint32_t)(pk[j] >> 32)); }
     m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
-    return cgp::perfect_mate(ix, m, L, pairLen, fl, nh);
+    uint8_t cls;
+    return cgp::perfect_mate(ix, m, L, pairLen, fl, nh, cls);
+}
+
+// the lockstep thread tier's per-read functions on the host (false: declined)
+static bool thr_stage(const std::vector<uint64_t>& pk, int L, std::vector<uint32_t>& scratch, cgq::QMem& m) {
+    int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
+    for (int j = 0; j < WMf; ++j) {
+        int lo = 64 * j;
+        if (lo >= L) break;
+        uint64_t mk = pk[W2f + j];
+        if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
+        if (mk) return false;
+    }
+    if (L < 1) return false;
+    m.stride = 1; m.W2 = W2f + 1;
+    scratch.assign(cgq::QMem::words(m.W2), 0xdeadbeefu);
+    m.base = scratch.data();
+    for (int j = 0; j < W2f; ++j) { m.st(2 * j, (uint32_t)pk[j]); m.st(2 * j + 1, (uint32_t)(pk[j] >> 32)); }
+    m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
+    cgt::tsm_make_rc(m, L);
+    return true;
+}
+static uint64_t g_thr_why[2][16];
+static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
+    cgq::QMem m;
+    int why = cgq::QD_N;
+    bool ok = thr_stage(pk, L, scratch, m) && cgq::q_wt_mate(ix, m, L, pairLen, lceMode, fl, nh, why);
+    if (!ok) ++g_thr_why[0][(-why) & 15];
+    return ok;
+}
+template <class Sink>
+static bool thr_bsj_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int lceMode, std::vector<uint32_t>& scratch, Sink& sink, uint32_t& nh, bool& split, uint32_t* tids) {
+    cgq::QMem m;
+    int why = cgq::QD_N;
+    if (!thr_stage(pk, L, scratch, m) || !cgq::q_bsj_record(ix, m, L, lceMode, sink, nh, split, why)) { ++g_thr_why[1][(-why) & 15]; return false; }
+    for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(m.cb() + t);
+    return true;
 }
 
 extern "C" {
@@ -190,6 +228,7 @@ struct EmuRun {
     uint64_t tsm_done[2] = {0, 0};       // reads finished by the thread state machine (first tier), wt mates / bsj records
     uint64_t tsm_steps = 0;
     uint64_t pre_done = 0;               // wt mates resolved by the thread-per-mate front kernel's function
+    uint64_t thr_done[2] = {0, 0};       // wt mates / bsj records resolved by the lockstep thread tier
     uint64_t tsm_why[2][16] = {};        // bail reasons (cgt::BAIL_*) per tool
     int err = 0;
 };
@@ -214,6 +253,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
     std::vector<uint32_t> tscr;
     const bool use_tsm = getenv("CG_EMU_NO_TSM") == nullptr;
     const bool use_pre = getenv("CG_EMU_NO_PRE") == nullptr;
+    const bool use_thr = getenv("CG_EMU_NO_THR") == nullptr;
     for (uint64_t i = 0; i < n; ++i) {
         int l1 = (int)(off1[i + 1] - off1[i]), l2 = (int)(off2[i + 1] - off2[i]);
         uint8_t fl[2]; uint32_t nh[2];
@@ -224,6 +264,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             cgt::Ctx tc; cgt::NoSink ns;
             tc.why = 0;
             if (use_pre && pre_host(TX->v, pk, m ? l2 : l1, l1, tscr, fl[m], nh[m])) ++R->pre_done;
+            else if (use_thr && thr_wt_host(TX->v, pk, m ? l2 : l1, l1, lceMode, tscr, fl[m], nh[m])) ++R->thr_done[0];
             else if (use_tsm && tsm_host<false>(TX->v, pk, m ? l2 : l1, l1, lceMode, tc, tscr, ns, R->tsm_steps)) {
                 ++R->tsm_done[0]; fl[m] = tc.flags; nh[m] = tc.nh;
             } else if ((use_tsm ? ++R->tsm_why[0][tc.why & 15] : 0), !wt_mate_fast<EFI, EFK, EHC>(TX->v, rv, l1, lceMode, *fs, fl[m], nh[m])) {
@@ -254,7 +295,10 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             cgt::Ctx tc;
             std::vector<int64_t> tmpj; VecSink tsink{&tmpj, rec};
             int Lr = (int)(m ? off2[i + 1] - off2[i] : off1[i + 1] - off1[i]);
-            if (use_tsm && tsm_host<true>(BS->v, pk, Lr, Lr, lceMode, tc, tscr, tsink, R->tsm_steps)) {
+            if (use_thr && thr_bsj_host(BS->v, pk, Lr, lceMode, tscr, tsink, nh, split, tids)) {
+                ++R->thr_done[1];
+                R->junc.insert(R->junc.end(), tmpj.begin(), tmpj.end());
+            } else if ((tmpj.clear(), use_tsm) && tsm_host<true>(BS->v, pk, Lr, Lr, lceMode, tc, tscr, tsink, R->tsm_steps)) {
                 ++R->tsm_done[1]; nh = tc.nh; split = tc.split;
                 R->junc.insert(R->junc.end(), tmpj.begin(), tmpj.end());
                 cgt::TMem tm; tm.base = tscr.data(); tm.stride = 1; tm.W2 = std::max(1, (Lr + 31) / 32) + 1;
@@ -280,7 +324,7 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
 void emu_run_free(void* r) { delete (EmuRun*)r; }
 int emu_run_err(void* r) { return ((EmuRun*)r)->err; }
 void emu_run_fallbacks(void* r, uint64_t* out) { out[0] = ((EmuRun*)r)->fallbacks[0]; out[1] = ((EmuRun*)r)->fallbacks[1]; }
-void emu_run_tsm(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->tsm_done[0]; out[1] = R->tsm_done[1]; out[2] = R->tsm_steps; out[35] = R->pre_done; for (int t = 0; t < 2; ++t) for (int w = 0; w < 16; ++w) out[3 + 16 * t + w] = R->tsm_why[t][w]; }
+void emu_run_tsm(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->tsm_done[0]; out[1] = R->tsm_done[1]; out[2] = R->tsm_steps; out[35] = R->pre_done; out[36] = R->thr_done[0]; out[37] = R->thr_done[1]; for (int t = 0; t < 2; ++t) for (int w = 0; w < 16; ++w) out[3 + 16 * t + w] = R->tsm_why[t][w]; }
 void emu_run_sizes(void* r, uint64_t* out) {
     EmuRun* R = (EmuRun*)r;
     out[0] = R->expPair.size(); out[1] = R->junc.size() / 6; out[2] = R->cand.size(); out[3] = R->eqTids.size();
@@ -297,6 +341,8 @@ void emu_run_fill(void* r, uint8_t* mateFlags, uint16_t* mateNHits, uint64_t* ex
     cp(eqLens, R->eqLens.data(), R->eqLens.size() * 4); cp(eqTids, R->eqTids.data(), R->eqTids.size() * 4);
     memcpy(ctr, R->ctr, sizeof R->ctr);
 }
+
+void emu_thr_why(uint64_t* out, int reset) { memcpy(out, g_thr_why, sizeof g_thr_why); if (reset) memset(g_thr_why, 0, sizeof g_thr_why); }
 
 // std::sort replica check: sorts packed kmerScores entries with cg::StdSort
 void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort<true>(n); }

@@ -58,7 +58,25 @@ def _pipeline(world, r1, r2, lce_mode=0):
         key = tuple(int(x) for x in E["eq_tids"][p0:p0 + ln]); p0 += int(ln)
         eq[key] = eq.get(key, 0) + 1
     assert eq == R.eq_classes(1)
+    R.emu = E
     return R
+
+
+@pytest.mark.parametrize("L", [100, 75, 150])
+def test_pipeline_lockstep_tier_coverage(world, L, monkeypatch):
+    """The lockstep thread tier (cg_thr.cuh) in front of the warp tiers: parity, and it must take most of what the
+    clean-match kernel declines (with and without that kernel in front of it)."""
+    T = world[0]
+    r1, r2 = make_reads(T, 900 + L, 4000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
+    R = _pipeline(world, r1, r2, 0)
+    ts = R.emu["tsm"]
+    pre, thr_wt, thr_bsj = int(ts[35]), int(ts[36]), int(ts[37])
+    n_mates, n_rec = 2 * r1.shape[0], len(R.emu["exp_pair"])
+    assert thr_wt > 0.4 * (n_mates - pre), (pre, thr_wt, n_mates)       # the test reads are N-rich (18 % of them hold one)
+    assert thr_bsj > 0.4 * n_rec, (thr_bsj, n_rec)
+    monkeypatch.setenv("CG_EMU_NO_PRE", "1")
+    R = _pipeline(world, r1, r2, 1)
+    assert int(R.emu["tsm"][36]) > 0.6 * n_mates
 
 
 @pytest.mark.parametrize("step", [False, True])
@@ -67,6 +85,7 @@ def test_pipeline_state_machine_forms(world, step, monkeypatch):
     if step:
         monkeypatch.setenv("CG_EMU_TSM_STEP", "1")
     monkeypatch.setenv("CG_EMU_NO_PRE", "1")          # let every mate reach it
+    monkeypatch.setenv("CG_EMU_NO_THR", "1")
     T = world[0]
     r1, r2 = make_reads(T, 411, 4000)
     _pipeline(world, r1, r2, 0)

@@ -95,6 +95,22 @@ def test_pipeline_parity(gpu_world, L, lce_mode):
     assert B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0
 
 
+@pytest.mark.parametrize("off", ["CG_NO_THR", "CG_NO_PRE", "CG_NO_THR,CG_NO_PRE"])
+def test_pipeline_parity_tier_subsets(gpu_world, off, monkeypatch):
+    """Every read through the tiers that remain when the thread-per-read front kernels are switched off one by one (the
+    lockstep tier alone in front, the clean-match kernel alone, the warp kernels alone): same outputs; and with all of
+    them on (the default) the warp kernels must see only a small part of the reads."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    for v in off.split(","):
+        monkeypatch.setenv(v, "1")
+    r1, r2 = make_reads(T, 511, 20000, n_rate=0.0)
+    a, b = ragged(r1, r2, 9)
+    _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, a, b)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, 0)
+    if off == "CG_NO_PRE":
+        assert 0 < B.n_tier2_wt < 0.3 * 2 * r1.shape[0] and 0 < B.n_tier2_bsj < 0.4 * B.n_export
+
+
 @pytest.mark.parametrize("L", [100, 150])
 def test_pipeline_parity_state_machine_tier(gpu_world, L, monkeypatch):
     """The experimental first tier (block-sorted state machine, cg_tsm.cuh; CG_TSM=1) in front of the warp kernels:
