@@ -121,11 +121,14 @@ __device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) 
 // K2-K6: one warp per mate (persistent warps, grid-stride).
 //   GEN = false: over all n mates, state in shared memory; ovf[r] = 1 hands the mate to the general kernel
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
+#ifndef CG_GEN_MINB
+#define CG_GEN_MINB 3      // resident blocks per SM of the general kernels (latency-bound tails over a few thousand reads: more warps in flight)
+#endif
 #ifndef CG_WARP_MINB
 #define CG_WARP_MINB 4     // resident blocks per SM asked of the fast warp kernels: 64 registers, 32 warps per SM (the kernels are latency-bound)
 #endif
 template <bool GEN, bool LIST>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? 1 : CG_WARP_MINB)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
           uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
@@ -369,7 +372,7 @@ struct BsjOut {
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
 // do_counts bit0: accumulate the scalar and per-BSJ counters; bit1: record the multi-transcript classes.
 template <bool GEN, bool LIST>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? 1 : CG_WARP_MINB)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
            const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
            int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
@@ -1122,7 +1125,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         s->use_thr = getenv("CG_NO_THR") == nullptr;
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
-        s->gen_grid = sms * 2;
+        s->gen_grid = sms * CG_GEN_MINB;
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_gscratch, (size_t)s->gen_grid * WARPS_PER_BLOCK * GEN_SCRATCH);
     }
     if (e != cudaSuccess) { int rc = cgi::cuda_fail(e, "session set-up", __FILE__, __LINE__); cg_session_destroy(s); return rc; }

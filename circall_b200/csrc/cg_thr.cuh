@@ -146,17 +146,45 @@ CG_HD int q_walk(const IndexView& ix, const QMem& m, int s, int o, int lim, bool
             if (in) sl[i] = CG_LDG(&ix.hslots[home_slot(ix, key[i])]);
         }
         if (homo) return -1;
-        // resolve from the last look-up to the first: what is left at the end belongs to the first position that hits
+        // Resolve all eight together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
+        // of the look-ups; the odd slot of the same sector (an L1 hit) settles almost all of those.  Both steps are
+        // straight-line code for the whole warp; only what is still open afterwards takes the generic probe loop.
+        uint32_t fb = 0, pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
+            if (kk == key[i]) fb |= 1u << i;
+            else if (kk != ~0ULL) pend |= 1u << i;
+        }
+        if (pend) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[home_slot(ix, key[i]) + 1]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((pend >> i) & 1u) {
+                    const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
+                    if (kk == key[i]) { fb |= 1u << i; pend &= ~(1u << i); }
+                    else if (kk == ~0ULL) pend &= ~(1u << i);
+                }
+            }
+            if (pend) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if ((pend >> i) & 1u) {
+                        const uint64_t h = (home_slot(ix, key[i]) + 2) & ix.hmask;
+                        uint32_t b1 = 0, e1 = 0;
+                        if (resolve(ix, key[i], h, CG_LDG(&ix.hslots[h]), b1, e1)) { fb |= 1u << i; sl[i].z = b1; sl[i].w = e1; }
+                    }
+                }
+            }
+        }
+        // the first position that hits; sl[i].z / .w are the interval of look-up i when it was found
         int pos = -1;
-        bool r = false;                                            // reverse complement of the pair being resolved (both)
 #pragma unroll
         for (int i = 7; i >= 0; --i) {
-            uint32_t b1 = 0, e1 = 0;
-            const bool f = resolve(ix, key[i], home_slot(ix, key[i]), sl[i], b1, e1);
             if (both) {
-                if (i & 1) r = f;
-                else if (f || r) { pos = o + (i >> 1); F.f = f; F.b = b1; F.e = e1; hasR = r; }
-            } else if (f) { pos = o + i; F.f = true; F.b = b1; F.e = e1; }
+                if (!(i & 1) && ((fb >> i) & 3u)) { pos = o + (i >> 1); F.f = (fb >> i) & 1u; F.b = sl[i].z; F.e = sl[i].w; hasR = (fb >> (i + 1)) & 1u; }
+            } else if ((fb >> i) & 1u) { pos = o + i; F.f = true; F.b = sl[i].z; F.e = sl[i].w; }
         }
         if (pos >= 0) return pos;
         o += per;
