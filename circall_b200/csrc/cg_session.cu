@@ -289,6 +289,14 @@ k_flag_write(const uint8_t* __restrict__ f, uint64_t n, const uint32_t* __restri
 // is mostly decided by which of the read's four end k-mers (first, last, their reverse complements) are in the table.
 // bc is class-major (bc[c * nb + block]) so that ONE exclusive scan (k_flag_scan) yields every block's write offsets.
 static const int CLS_N = 16;
+static const int CLS_VOTE = 12;       // first bucket of the two-strand classes
+// bucket of class c (1..16): the four classes whose first k-mer AND its reverse complement are in the table (both strands
+// seeded: the read needs the kmerScores vote) come last, so that the two-strand instantiation of the lockstep kernels
+// runs over the tail [bc[CLS_VOTE * nb], total) of the sorted list and the lean one over the head
+__device__ __forceinline__ int cls_bucket(uint8_t c) {
+    const int v = (c - 1) & (CLS_N - 1), lo = v & 3, hi = v >> 2;
+    return lo == 3 ? CLS_VOTE + hi : hi * 3 + lo;
+}
 __global__ void __launch_bounds__(CP_THREADS)
 k_cls_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ bc, uint32_t nb) {
     __shared__ uint32_t sh[CLS_N];
@@ -296,7 +304,7 @@ k_cls_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ bc
     __syncthreads();
     uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
 #pragma unroll
-    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) atomicAdd(&sh[(c - 1) & (CLS_N - 1)], 1u); }
+    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) atomicAdd(&sh[cls_bucket(c)], 1u); }
     __syncthreads();
     if (threadIdx.x < CLS_N) bc[threadIdx.x * nb + blockIdx.x] = sh[threadIdx.x];
 }
@@ -307,7 +315,7 @@ k_cls_write(const uint8_t* __restrict__ f, uint64_t n, const uint32_t* __restric
     __syncthreads();
     uint64_t base = blockIdx.x * (uint64_t)CP_TILE + threadIdx.x * CP_ITEMS;
 #pragma unroll
-    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) out[atomicAdd(&cur[(c - 1) & (CLS_N - 1)], 1u)] = (uint32_t)(base + x); }
+    for (int x = 0; x < CP_ITEMS; ++x) if (base + x < n) { uint8_t c = f[base + x]; if (c) out[atomicAdd(&cur[cls_bucket(c)], 1u)] = (uint32_t)(base + x); }
 }
 
 // Circall_bsj has no front kernel in front of the lockstep tier: this one only classifies the exported records
@@ -728,7 +736,8 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
 // ---- lockstep thread tier (cg_thr.cuh): one thread per read, single-strand reads ------------------------------------
 static const int THR_THREADS = 128;
 // stage the packed read of this thread into its scratch; false when the read holds an N (or is empty)
-__device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, const PackGeom& g, int L, const cgq::QMem& m) {
+template <class M>
+__device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, const PackGeom& g, int L, const M& m) {
     bool anyN = L < 1;
     for (int j = 0; j < g.WMf; ++j) {
         const int lo = 64 * j;
@@ -744,41 +753,49 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
     return true;
 }
 
-// Circall_wt: over the mates list[0..*n_list) the front kernel declined (all n_reads mates when list is null); ovf[r] = 1 hands
-// mate r to the warp kernels
-__global__ void __launch_bounds__(THR_THREADS, CG_THR_MINB)
+// Circall_wt: over the mates list[..] the front kernel declined (all n_reads mates when list is null); ovf[r] = 1 hands mate r
+// to the warp kernels.  The list is grouped by look-up class: the lean instantiation (VOTE = false) takes its head
+// [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
+template <bool VOTE>
+__global__ void __launch_bounds__(THR_THREADS, VOTE ? 3 : CG_THR_MINB)
 k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
-         const uint32_t* __restrict__ n_list, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf) {
+         const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
+         uint8_t* __restrict__ ovf) {
     extern __shared__ uint32_t thr_smem[];
-    const uint64_t x = (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
-    if (x >= (list ? (uint64_t)*n_list : n_reads)) return;
+    const uint64_t total = list ? (uint64_t)*n_list : n_reads;
+    const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
+    const uint64_t x = lo + (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
+    if (x >= hi) return;
     const uint64_t r = list ? (uint64_t)list[x] : x;
     const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
-    cgq::QMem m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+    cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
     uint8_t fl = 0; uint32_t nh = 0; int why = 0;
-    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why);
+    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why);
     if (done) { flags[r] = fl; nhits[r] = nh; }
     else ovf[r] = 1;
 }
 
-// Circall_bsj: over the records list[0..*n_list) (every exported record when list is null); ovf[rec] = 1 hands record rec to
-// the warp kernels (nothing was emitted for it)
-__global__ void __launch_bounds__(THR_THREADS, CG_THR_MINB)
+// Circall_bsj: over the records list[..] (every exported record when list is null); ovf[rec] = 1 hands record rec to the warp
+// kernels (nothing was emitted for it).  seg as in k_wt_thr.
+template <bool VOTE>
+__global__ void __launch_bounds__(THR_THREADS, VOTE ? 3 : CG_THR_MINB)
 k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
-          const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf) {
+          const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, BsjOut o, int do_counts,
+          uint8_t* __restrict__ ovf) {
     extern __shared__ uint32_t thr_smem[];
-    const uint64_t n = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
-    const uint64_t x = (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
-    const bool active = x < n;
+    const uint64_t total = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
+    const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
+    const uint64_t x = lo + (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
+    const bool active = x < hi;
     const uint64_t rec = active && list ? (uint64_t)list[x] : x;
     uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
     if (active) {
         const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
         const int L = lens[r];
-        cgq::QMem m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+        cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
         JSink sink; sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; sink.rec = (uint32_t)rec;
-        uint32_t nh = 0; bool split = false; int why = 0;
-        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record(cgw::c_ix[1], m, L, lceMode, sink, nh, split, why);
+        uint32_t nh = 0; bool split = false; int why = 0, at = 0;
+        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why);
         if (!done) ovf[rec] = 1;
         else {
             // commit (Circall_bsj.cpp:383-491)
@@ -788,12 +805,12 @@ k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
             const bool cand = c > 0 && split;                                     // :390
             obs = 1; mapped = cand; hits = c;                                     // :488-491
             if (cand) {
-                if (c == 1) { if (do_counts & 1) atomicAdd(&o.per_bsj[m.ld(m.cb())], 1ULL); }     // EquivalenceClassBuilder.hpp:112-130
+                if (c == 1) { if (do_counts & 1) atomicAdd(&o.per_bsj[m.ld(at)], 1ULL); }          // EquivalenceClassBuilder.hpp:112-130
                 else if (do_counts & 2) {
                     const unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL), sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)c);
                     if (e < o.eq_cap && sidx + c <= o.eq_tids_cap) {
                         o.eq_ent[e] = make_uint4((uint32_t)rec, (uint32_t)sidx, c, 0u);
-                        for (uint32_t t = 0; t < c; ++t) o.eq_tids[sidx + t] = m.ld(m.cb() + t);
+                        for (uint32_t t = 0; t < c; ++t) o.eq_tids[sidx + t] = m.ld(at + t);
                     }
                 }
             }
@@ -938,8 +955,13 @@ int run_bsj_stage(cg_session* s, int do_counts) {
         if (rc) return rc;
         rc = compact_classes(s, s->d_ovf3.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
         if (rc) return rc;
-        rc = launch(s, k_bsj_thr, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMem::words(s->geom.W2f + 1) * 4,
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj,
+        const uint32_t* seg = (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(worst, CP_TILE));
+        rc = launch(s, k_bsj_thr<false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>());
+        if (rc) return rc;
+        rc = launch(s, k_bsj_thr<true>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4,
+                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
                     s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>());
         if (rc) return rc;
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
@@ -1030,10 +1052,20 @@ int run_batch(cg_session* s) {
         }
         if (s->use_thr) {
             CG_CUDA(cudaMemsetAsync(s->d_ovf3.p, 0, n_reads, s->stream));
-            rc = launch(s, k_wt_thr, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMem::words(g.W2f + 1) * 4,
-                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, s->opts.lce_mode,
+            // the class-sorted list has its two-strand classes at the end (compact_classes): lean instantiation over the head,
+            // two-strand instantiation over the tail; an unsorted list (or none) goes through the lean one alone
+            const bool sorted = cur_list && s->use_pre && !s->use_tsm;
+            const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
+            rc = launch(s, k_wt_thr<false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
                         s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>());
             if (rc) return rc;
+            if (sorted) {
+                rc = launch(s, k_wt_thr<true>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4,
+                            s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
+                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>());
+                if (rc) return rc;
+            }
             rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
             if (rc) return rc;
             cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_wt;

@@ -49,18 +49,23 @@ static const int Q_FI = 8;        // intervals kept (one strand)
 static const int Q_W = 16;        // widest interval resolved suffix by suffix (extension, hit candidates, intersection)
 static const int Q_SPAN = 64;     // widest interval the span filter walks
 
+static const int Q_FK = 16;       // kmerScores entries (two-strand instantiation; <= 16: libstdc++'s sort is a plain insertion sort)
+
 // Per-thread scratch of 32-bit words, word j at base[j * stride] (stride = threads per block on the device; 1 on the host)
 //   [0, 2 W2)         forward code words, 16 bases each (W2 = 64-bit words incl. one zero pad word)
 //   [2 W2, 4 W2)      reverse-complement strand, same layout
-//   [4 W2, +3 Q_FI)   intervals: begin, end, len | qpos << 16
-//   then Q_W          hit candidates (transcript ids)
-struct QMem {
+//   then 3 Q_FI       intervals of a strand: begin, end, len | qpos << 16   (VOTE: forward list, then reverse-complement list)
+//   VOTE: Q_FK        kmerScores entries (cg::ks_pack)
+//   then Q_W          hit candidates (transcript ids) of a strand            (VOTE: one area per strand)
+template <bool VOTE>
+struct QMemT {
     uint32_t* base; int stride; int W2;
     CG_HD uint32_t ld(int j) const { return base[(size_t)j * stride]; }
     CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
-    CG_HD int iv(int i) const { return 4 * W2 + 3 * i; }
-    CG_HD int cb() const { return 4 * W2 + 3 * Q_FI; }
-    CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI + Q_W; }
+    CG_HD int iv(int s, int i) const { return 4 * W2 + 3 * ((VOTE ? s * Q_FI : 0) + i); }
+    CG_HD int ks(int j) const { return 4 * W2 + 3 * Q_FI * 2 + j; }
+    CG_HD int cb(int s) const { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + s * Q_W : 0); }
+    CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + 2 * Q_W : Q_W); }
     // 32-base window of strand s at oriented position i (i < L)
     CG_HD uint64_t chunk(int s, int i) const {
         int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
@@ -68,13 +73,15 @@ struct QMem {
         return (uint64_t)cgt::fsr(a, b, sh) | ((uint64_t)cgt::fsr(b, c, sh) << 32);
     }
 };
+typedef QMemT<false> QMem;
 
 enum { Q_NOTFOUND = 0, Q_FOUND = 1 };
 // decline reasons (negative return values; tests/emu counts them)
-enum { QD_HOMO = -1, QD_BOTH_A = -2, QD_OTHER = -3, QD_SA0 = -4, QD_WIDE_EXT = -5, QD_NINT = -6, QD_WIDE_HITS = -7, QD_WIDE_SPAN = -8, QD_ODD = -9, QD_N = -10 };
+enum { QD_HOMO = -1, QD_BOTH_A = -2, QD_OTHER = -3, QD_SA0 = -4, QD_WIDE_EXT = -5, QD_NINT = -6, QD_WIDE_HITS = -7, QD_WIDE_SPAN = -8, QD_ODD = -9, QD_N = -10, QD_NKS = -11 };
 
 // longest common prefix of strand s of the read from query offset q and the text at p, compared over [i0, lim)
-CG_HD int q_match(const IndexView& ix, const QMem& m, int s, int q, uint32_t p, int i0, int lim) {
+template <class M>
+CG_HD int q_match(const IndexView& ix, const M& m, int s, int q, uint32_t p, int i0, int lim) {
     int i = i0;
     uint32_t curb = 0xffffffffu;
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
@@ -129,7 +136,8 @@ struct QProbe { bool f; uint32_t b, e; };
 // :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, eight look-ups per round.
 // Returns the first position that hits (F: the k-mer's own look-up, hasR: its reverse complement's, both only) or -1;
 // homo is set when a looked-up window is a homopolymer (the caller declines).
-CG_HD int q_walk(const IndexView& ix, const QMem& m, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
+template <class M>
+CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
     const int k = ix.k;
     const int sh = both ? 1 : 0, per = 8 >> sh;
     F.f = false; F.b = F.e = 0; hasR = false;
@@ -192,11 +200,14 @@ CG_HD int q_walk(const IndexView& ix, const QMem& m, int s, int o, int lim, bool
     return -1;
 }
 
-// SACollectorCircall::operator() up to and including the strand vote for a read whose hits lie on one strand.
-// Returns Q_FOUND (n intervals of strand S in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.
-CG_HD int q_collect(const IndexView& ix, const QMem& m, int L, int lceMode, int& n, int& S) {
+// SACollectorCircall::operator() up to and including the strand vote.
+//   VOTE = false: reads whose hits lie on one strand (a look-up that scores for the other strand declines the read)
+//   VOTE = true : both strands — Phase B then Phase C when rcHit >= fwdHit (:332), the kmerScores list and its vote (:442-490)
+// Returns Q_FOUND (nF / nR post-vote intervals in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.
+template <bool VOTE>
+CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, int& nF, int& nR) {
     const int k = ix.k, skipOverlap = k - 1;
-    n = 0; S = 0;
+    nF = nR = 0;
     if (L > 0xffff) return QD_ODD;
     if (!(k < L)) return Q_NOTFOUND;       // Phase A's loop needs rb + k < L (:112)
     // the four look-ups every path starts with: read[0,k), read[L-k,L) and their reverse complements
@@ -211,9 +222,12 @@ CG_HD int q_collect(const IndexView& ix, const QMem& m, int L, int lceMode, int&
         F0.f = resolve(ix, mer0, h0, s0, F0.b, F0.e); R0.f = resolve(ix, rc0, h1, s1, R0.b, R0.e);
         FL.f = resolve(ix, merL, h2, s2, FL.b, FL.e); RL.f = resolve(ix, rcL, h3, s3, RL.b, RL.e);
     }
-    bool phaseA = true, firstB = false, expectAbsent = false, lastSearch = false, homo = false;
-    int s = 0, o = 0;
+    bool phaseA = true, firstB = false, aOther = false, expectAbsent = false, lastSearch = false, homo = false;
+    int s = 0, o = 0, nKS = 0;
+    uint32_t fwdHit = 0, rcHit = 0;
+#define Q_PUSH_KS(kp, f, r) do { if (VOTE) { if (nKS >= Q_FK) return QD_NKS; m.st(m.ks(nKS), ks_pack((kp), (f), (r))); ++nKS; } } while (0)
     for (;;) {
+        bool done = false;                                                         // this strand is finished
         // ---------------- LOOK: the next position of strand s whose k-mer is in the table ----------------
         int pos = -1;
         QProbe hit; hit.f = false; hit.b = hit.e = 0;
@@ -250,67 +264,128 @@ CG_HD int q_collect(const IndexView& ix, const QMem& m, int L, int lceMode, int&
         }
         if (pos < 0) {
             if (phaseA) return Q_NOTFOUND;                                         // :204
-            break;                                                                 // ran off the read: the strand is done
+            done = true;                                                           // ran off the read
         }
-        o = pos;
-        bool extendIt = true;
-        if (phaseA) {
-            phaseA = false;
-            if (hit.f && other) return QD_BOTH_A;                                 // both strands seeded: the vote decides
-            if (hit.f) { S = s = 0; firstB = true; }                               // :134-176, Phase B follows
-            else { S = s = 1; o = 0; expectAbsent = false; extendIt = false; }     // :178-191: rcHit only, Phase C from 0 (:332-346)
-        } else if (other) return QD_OTHER;                                       // :265-272 / :381-385: the other strand scores too
-        if (!extendIt) continue;
-        // ---------------- EXTEND: extendSearchNaive(b - 1, e) from position o (:143 / :280 / :393) ----------------
-        if (hit.b == 0) return QD_SA0;
-        uint32_t lb = hit.b, ub = hit.e;
-        int matched = k;
-        const int mq = L - o;
-        if (mq > k) {
-            const uint32_t w = hit.e - hit.b;
-            if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
-            int best = -1; uint32_t first = 0, last = 0;
-            for (uint32_t c0 = 0; c0 < w; c0 += 4) {
-                uint32_t p[4];
+        if (!done) {
+            o = pos;
+            bool extendIt = true;
+            if (phaseA) {
+                phaseA = false;
+                if (!VOTE && hit.f && other) return QD_BOTH_A;                     // both strands seeded: the vote decides
+                if (hit.f) { s = 0; firstB = true; aOther = other; }               // :134-176, Phase B follows
+                else {                                                             // :178-191: rcHit only, Phase C from 0 (:332-346)
+                    ++rcHit; Q_PUSH_KS(pos, -1, 1);
+                    s = 1; o = 0; expectAbsent = false; extendIt = false;
+                }
+            } else {
+                if (!VOTE && other) return QD_OTHER;                               // :265-272 / :381-385: the other strand scores too
+                const int fpos = s == 0 ? o : L - (o + k);                         // :366
+                if (s == 0) { ++fwdHit; if (other) ++rcHit; Q_PUSH_KS(fpos, 1, other ? 1 : 0); }
+                else { ++rcHit; if (other) ++fwdHit; Q_PUSH_KS(fpos, other ? 1 : 0, 1); }
+            }
+            if (extendIt) {
+                // ---------------- EXTEND: extendSearchNaive(b - 1, e) from position o (:143 / :280 / :393) ----------------
+                if (hit.b == 0) return QD_SA0;
+                uint32_t lb = hit.b, ub = hit.e;
+                int matched = k;
+                const int mq = L - o;
+                if (mq > k) {
+                    const uint32_t w = hit.e - hit.b;
+                    if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
+                    int best = -1; uint32_t first = 0, last = 0;
+                    for (uint32_t c0 = 0; c0 < w; c0 += 4) {
+                        uint32_t p[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
+                        for (int c = 0; c < 4; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c0 + c < w) {
-                        const int l = q_match(ix, m, s, o, p[c], k, mq);
-                        if (l > best) { best = l; first = last = c0 + c; }
-                        else if (l == best) last = c0 + c;
+                        for (int c = 0; c < 4; ++c) {
+                            if (c0 + c < w) {
+                                const int l = q_match(ix, m, s, o, p[c], k, mq);
+                                if (l > best) { best = l; first = last = c0 + c; }
+                                else if (l == best) last = c0 + c;
+                            }
+                        }
                     }
+                    lb = hit.b + first; ub = hit.b + last + 1; matched = best;
+                }
+                const bool valid = ub > lb && ub - lb < 1000u;                     // :149 / :285 / :398 (maxInterval)
+                if (valid) {
+                    int& n = s == 0 ? nF : nR;
+                    if (n >= Q_FI) return QD_NINT;
+                    m.st(m.iv(s, n), lb); m.st(m.iv(s, n) + 1, ub); m.st(m.iv(s, n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
+                    ++n;
+                }
+                if (firstB) {                                                      // Phase A's bookkeeping (:149-191)
+                    if (valid) {
+                        ++fwdHit;
+                        if (aOther) { ++rcHit; Q_PUSH_KS(o, 1, 1); } else Q_PUSH_KS(o, 1, -1);
+                        if (o + matched < L) Q_PUSH_KS(o + matched - skipOverlap, -1, 0);      // :165-168
+                    } else return QD_ODD;                                          // (an interval of >= 1000 suffixes: not this tier's read)
+                } else if (valid && o + matched < L) {                             // :291 / :404
+                    Q_PUSH_KS(s == 0 ? o + matched - skipOverlap : L - (o + matched), 0, 0);
+                }
+                if (lastSearch) done = true;                                       // :300 / :412
+                else {
+                    // ---------------- LCE and the next position (:219-228 after Phase A, :302-321 / :414-433 in the loop) ----------------
+                    const int mismatch = o + matched;
+                    const int stopAt = L - mismatch;
+                    int l = matched;
+                    if (stopAt > matched) {                                        // else lce returns startAt at once
+                        const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
+                        l = q_lce(ix, p1, p2, matched, stopAt, lceMode);
+                    }
+                    if (firstB) {
+                        firstB = false;
+                        const int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
+                        const int o2 = cmin(cmax(0, L - k), o + fwdSkip);          // :224-228
+                        expectAbsent = stopAt > 0 && o2 < L - k;
+                        o = o2;
+                    } else if (mismatch < L) {
+                        o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
+                        if (o > L - k) { o = L - k; lastSearch = true; expectAbsent = false; }
+                        else expectAbsent = true;
+                    } else { lastSearch = true; o = L - k; expectAbsent = false; }
+                    if (o + k > L) done = true;
                 }
             }
-            lb = hit.b + first; ub = hit.b + last + 1; matched = best;
         }
-        if (ub > lb && ub - lb < 1000u) {                                          // :149 / :285 / :398 (maxInterval)
-            if (n >= Q_FI) return QD_NINT;
-            m.st(m.iv(n), lb); m.st(m.iv(n) + 1, ub); m.st(m.iv(n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
-            ++n;
+        if (done) {
+            if (VOTE && s == 0 && rcHit >= fwdHit) {                               // Phase C after Phase B (:332-346)
+                s = 1; o = 0; expectAbsent = false; lastSearch = false;
+                continue;
+            }
+            break;
         }
-        if (lastSearch) break;                                                     // :300 / :412
-        // ---------------- LCE and the next position (:219-228 after Phase A, :302-321 / :414-433 in the loop) ----------------
-        const int mismatch = o + matched;
-        const int stopAt = L - mismatch;
-        int l = matched;
-        if (stopAt > matched) {                                                    // else lce returns startAt at once
-            const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
-            l = q_lce(ix, p1, p2, matched, stopAt, lceMode);
+    }
+#undef Q_PUSH_KS
+    // ---- strand vote (:442-490)
+    if (VOTE) {
+        if (fwdHit > 0 && rcHit == 0) nR = 0;
+        else if (rcHit > 0 && fwdHit == 0) nF = 0;
+        else {
+            for (int i = 1; i < nKS; ++i) {                                        // std::sort of <= 16 entries: a stable insertion sort
+                const uint32_t v = m.ld(m.ks(i)); int j = i - 1;
+                while (j >= 0 && ks_key(v) < ks_key(m.ld(m.ks(j)))) { m.st(m.ks(j + 1), m.ld(m.ks(j))); --j; }
+                m.st(m.ks(j + 1), v);
+            }
+            int fs = 0, rs = 0;
+            uint32_t prevKey = 0xffffffffu;
+            for (int i = 0; i < nKS; ++i) {                                        // std::unique keeps the first of each run
+                const uint32_t en = m.ld(m.ks(i));
+                if (ks_key(en) == prevKey) continue;
+                prevKey = ks_key(en);
+                int f = ks_f(en), r = ks_r(en);
+                if (f == 0 || r == 0) {
+                    const uint64_t w = m.chunk(0, (int)ks_key(en)) & ix.km;       // (no N in this tier's reads)
+                    bool pf = false, pr = false; uint32_t b1, e1, b2, e2;
+                    probe2(ix, w, revcomp(w, k), pf, b1, e1, pr, b2, e2);
+                    if (f == 0) f = pf ? 1 : -1;                                   // :461-464
+                    if (r == 0) r = pr ? 1 : -1;                                   // :469-473
+                }
+                fs += f; rs += r;
+            }
+            if (fs > rs) nR = 0; else if (rs > fs) nF = 0;                         // :482-488
         }
-        if (firstB) {
-            firstB = false;
-            const int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
-            const int o2 = cmin(cmax(0, L - k), o + fwdSkip);                      // :224-228
-            expectAbsent = stopAt > 0 && o2 < L - k;
-            o = o2;
-        } else if (mismatch < L) {
-            o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
-            if (o > L - k) { o = L - k; lastSearch = true; expectAbsent = false; }
-            else expectAbsent = true;
-        } else { lastSearch = true; o = L - k; expectAbsent = false; }
-        if (o + k > L) break;
     }
     return Q_FOUND;
 }
@@ -326,18 +401,28 @@ CG_HD void q_tids4(const IndexView& ix, uint32_t i0, int nn, uint32_t* tid) {
     for (int x = 0; x < 4; ++x) tid[x] = x < nn ? cgt::tid_from(t[x], p[x]) : 0xffffffffu;
 }
 
-// the n intervals of the scratch -> number of hit transcripts (intersectSAHits + collectHitsSimpleSA, or the single-interval
-// enumeration, :492-563); the candidates stay in the scratch (cb + c, c < nc) with `alive` marking the hits.  < 0: declined.
-CG_HD int q_hits(const IndexView& ix, const QMem& m, int n, uint32_t& alive, int& nc) {
+CG_HD int q_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// the n intervals of strand s in the scratch -> number of hit transcripts (intersectSAHits + collectHitsSimpleSA, or the
+// single-interval enumeration, :492-563); the candidates stay in the scratch (cb(s) + c, c < nc) with `alive` marking the
+// hits.  < 0: declined.
+template <class M>
+CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive, int& nc) {
     alive = 0; nc = 0;
     if (n == 0) return 0;
     uint32_t keep = 0;
     for (int i = 0; i < n; ++i) {
-        const uint32_t lqi = m.ld(m.iv(i) + 2);
+        const uint32_t lqi = m.ld(m.iv(s, i) + 2);
         const int li = (int)(lqi & 0xffffu), qi = (int)(lqi >> 16);
         bool drop = false;
         for (int y = 0; y < n; ++y) {
-            const uint32_t lqy = m.ld(m.iv(y) + 2);
+            const uint32_t lqy = m.ld(m.iv(s, y) + 2);
             const int ly = (int)(lqy & 0xffffu), qy = (int)(lqy >> 16);
             drop |= (ly > li && qy <= qi && qy + ly >= qi + li);
         }
@@ -346,29 +431,30 @@ CG_HD int q_hits(const IndexView& ix, const QMem& m, int n, uint32_t& alive, int
     int mi = -1; uint32_t msp = 0xffffffffu; bool wide = false;
     for (int i = 0; i < n; ++i) {
         if (!((keep >> i) & 1u)) continue;
-        const uint32_t sp = m.ld(m.iv(i) + 1) - m.ld(m.iv(i));
+        const uint32_t sp = m.ld(m.iv(s, i) + 1) - m.ld(m.iv(s, i));
         if (sp > (uint32_t)Q_W) wide = true;
         if (sp < msp) { msp = sp; mi = i; }
     }
     if (wide || mi < 0) return QD_WIDE_HITS;
-    const uint32_t mb = m.ld(m.iv(mi)), me = m.ld(m.iv(mi) + 1);
+    const uint32_t mb = m.ld(m.iv(s, mi)), me = m.ld(m.iv(s, mi) + 1);
+    const int cb = m.cb(s);
     for (uint32_t c0 = 0; c0 < msp; c0 += 4) {
         uint32_t t[4];
         const int nn = (int)cmin<uint32_t>(4u, msp - c0);
         q_tids4(ix, mb + c0, nn, t);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) if (x < nn) m.st(m.cb() + (int)c0 + x, t[x]);
+        for (int x = 0; x < 4; ++x) if (x < nn) m.st(cb + (int)c0 + x, t[x]);
     }
     nc = (int)msp;
     for (int c = 0; c < nc; ++c) {                          // one candidate per distinct transcript
-        const uint32_t tc = m.ld(m.cb() + c);
+        const uint32_t tc = m.ld(cb + c);
         bool dup = false;
-        for (int y = 0; y < c; ++y) dup |= m.ld(m.cb() + y) == tc;
+        for (int y = 0; y < c; ++y) dup |= m.ld(cb + y) == tc;
         if (!dup) alive |= 1u << c;
     }
     for (int x = 0; x < n; ++x) {
         if (x == mi || !((keep >> x) & 1u)) continue;
-        const uint32_t ib = m.ld(m.iv(x)), ie = m.ld(m.iv(x) + 1);
+        const uint32_t ib = m.ld(m.iv(s, x)), ie = m.ld(m.iv(s, x) + 1);
         if (ib == mb && ie == me) continue;                  // same positions: cannot drop a transcript
         uint32_t seen = 0;
         for (uint32_t c0 = ib; c0 < ie; c0 += 4) {
@@ -376,86 +462,121 @@ CG_HD int q_hits(const IndexView& ix, const QMem& m, int n, uint32_t& alive, int
             const int nn = (int)cmin<uint32_t>(4u, ie - c0);
             q_tids4(ix, c0, nn, t);
             for (int c = 0; c < nc; ++c) {
-                const uint32_t tc = m.ld(m.cb() + c);
+                const uint32_t tc = m.ld(cb + c);
                 if (tc == t[0] || tc == t[1] || tc == t[2] || tc == t[3]) seen |= 1u << c;      // unused entries are 0xffffffff
             }
         }
         alive &= seen;
     }
-#if defined(__CUDA_ARCH__)
-    return __popc(alive);
-#else
-    return __builtin_popcount(alive);
-#endif
+    return q_popc(alive);
+}
+
+// hits of both strands: each strand's candidates compacted to its hits (cb(s)[0 .. h_s)); returns hF + hR - common, the size
+// of the list merged by transcript (:567-579), or < 0.  VOTE = false: only the strand that holds intervals.
+template <bool VOTE>
+CG_HD int q_hits2(const IndexView& ix, const QMemT<VOTE>& m, int nF, int nR, int& hF, int& hR) {
+    hF = hR = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int n = s == 0 ? nF : nR;
+        if (n == 0) continue;
+        uint32_t alive; int nc;
+        const int h = q_hits(ix, m, s, n, alive, nc);
+        if (h < 0) return h;
+        int j = 0;
+        for (int c = 0; c < nc; ++c) if ((alive >> c) & 1u) { m.st(m.cb(s) + j, m.ld(m.cb(s) + c)); ++j; }
+        if (s == 0) hF = h; else hR = h;
+    }
+    int common = 0;
+    if (VOTE && hF && hR)
+        for (int a = 0; a < hF; ++a) { const uint32_t t = m.ld(m.cb(0) + a); for (int b = 0; b < hR; ++b) common += m.ld(m.cb(1) + b) == t; }
+    return hF + hR - common;
 }
 
 // one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517): false = declined
-CG_HD bool q_wt_mate(const IndexView& ix, const QMem& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why) {
-    int n, S;
-    const int r = q_collect(ix, m, L, lceMode, n, S);
+template <bool VOTE>
+CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why) {
+    int nF, nR;
+    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
     why = r;
     if (r < 0) return false;
     flags = 0; nh = 0;
     if (r == Q_NOTFOUND) return true;
     bool full = false;
-    for (int i = 0; i < n; ++i) full |= (int)(m.ld(m.iv(i) + 2) & 0xffffu) == pairLen;          // :318-342,493-517
-    uint32_t alive; int nc;
-    const int h = q_hits(ix, m, n, alive, nc);
+    for (int i = 0; i < nF; ++i) full |= (int)(m.ld(m.iv(0, i) + 2) & 0xffffu) == pairLen;       // :318-342,493-517
+    for (int i = 0; i < nR; ++i) full |= (int)(m.ld(m.iv(1, i) + 2) & 0xffffu) == pairLen;
+    int hF, hR;
+    const int h = q_hits2<VOTE>(ix, m, nF, nR, hF, hR);
     if (h < 0) { why = h; return false; }
-    if (n > 0) flags |= MATE_SEEDED;                                                             // :311,486
+    if (nF + nR > 0) flags |= MATE_SEEDED;                                                       // :311,486
     if (full) flags |= MATE_FULL;
     nh = (uint32_t)h;
     return true;
 }
 
 // one record of Circall_bsj (src/Circall_bsj.cpp:300-399): false = declined (nothing was emitted).  On success the
-// hit transcripts are left in ascending order in the candidate words (cb + t, t < nh).
-template <class Sink>
-CG_HD bool q_bsj_record(const IndexView& ix, const QMem& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& why) {
-    int n, S;
-    const int r = q_collect(ix, m, L, lceMode, n, S);
+// hit transcripts are left in ascending order at tids_at (word index in the scratch), nh of them.
+template <bool VOTE, class Sink>
+CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why) {
+    int nF, nR;
+    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
     why = r;
+    tids_at = m.cb(0);
     if (r < 0) return false;
     nh = 0; split = false;
     if (r == Q_NOTFOUND) return true;
-    uint32_t alive; int nc;
-    const int h = q_hits(ix, m, n, alive, nc);
+    int hF, hR;
+    const int h = q_hits2<VOTE>(ix, m, nF, nR, hF, hR);
     if (h < 0) { why = h; return false; }
     if (h == 0) return true;                                                                     // :319
-    for (int i = 0; i < n; ++i) if (m.ld(m.iv(i) + 1) - m.ld(m.iv(i)) > (uint32_t)Q_SPAN) { why = QD_WIDE_SPAN; return false; }
+    if (h > Q_W) { why = QD_WIDE_HITS; return false; }
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < (s == 0 ? nF : nR); ++i)
+            if (m.ld(m.iv(s, i) + 1) - m.ld(m.iv(s, i)) > (uint32_t)Q_SPAN) { why = QD_WIDE_SPAN; return false; }
     nh = (uint32_t)h;
-    // span filter over every SA position of every interval (:323-374)
-    for (int i = 0; i < n; ++i) {
-        const uint32_t ib = m.ld(m.iv(i)), ie = m.ld(m.iv(i) + 1), lq = m.ld(m.iv(i) + 2);
-        const int len = (int)(lq & 0xffffu);
-        for (uint32_t i0 = ib; i0 < ie; i0 += 4) {                                               // :326 / :355
-            const int nn = (int)cmin<uint32_t>(4u, ie - i0);
-            uint32_t tt[4], ll[4], o0[4], o1[4];
-            sa_tids4(ix, i0, nn, tt, ll);
+    // span filter over every SA position of every interval, forward list then reverse-complement list (:323-374)
+    for (int s = 0; s < 2; ++s) {
+        for (int i = 0; i < (s == 0 ? nF : nR); ++i) {
+            const uint32_t ib = m.ld(m.iv(s, i)), ie = m.ld(m.iv(s, i) + 1), lq = m.ld(m.iv(s, i) + 2);
+            const int len = (int)(lq & 0xffffu);
+            for (uint32_t i0 = ib; i0 < ie; i0 += 4) {                                           // :326 / :355
+                const int nn = (int)cmin<uint32_t>(4u, ie - i0);
+                uint32_t tt[4], ll[4], o0[4], o1[4];
+                sa_tids4(ix, i0, nn, tt, ll);
 #pragma unroll
-            for (int z = 0; z < 4; ++z) { o0[z] = o1[z] = 0; if (z < nn) { o0[z] = CG_LDG(&ix.offsets[tt[z]]); o1[z] = CG_LDG(&ix.offsets[tt[z] + 1]); } }
+                for (int z = 0; z < 4; ++z) { o0[z] = o1[z] = 0; if (z < nn) { o0[z] = CG_LDG(&ix.offsets[tt[z]]); o1[z] = CG_LDG(&ix.offsets[tt[z] + 1]); } }
 #pragma unroll
-            for (int z = 0; z < 4; ++z) {
-                if (z < nn) {
-                    const uint32_t refLen = o1[z] - o0[z] - 1;
-                    const int hitPos = (int)ll[z];
-                    const int junctPos = (int)(refLen / 2);                                      // :333
-                    if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {                  // :336 / :364
-                        sink.line((uint32_t)S, lq >> 16, (uint32_t)len, hitPos, tt[z]);
-                        split = true;
+                for (int z = 0; z < 4; ++z) {
+                    if (z < nn) {
+                        const uint32_t refLen = o1[z] - o0[z] - 1;
+                        const int hitPos = (int)ll[z];
+                        const int junctPos = (int)(refLen / 2);                                  // :333
+                        if (hitPos < junctPos - 5 && hitPos + len > junctPos + 5) {              // :336 / :364
+                            sink.line((uint32_t)s, lq >> 16, (uint32_t)len, hitPos, tt[z]);
+                            split = true;
+                        }
                     }
                 }
             }
         }
     }
-    // class key: the hit transcripts in ascending order
-    int j = 0;
-    for (int c = 0; c < nc; ++c) if ((alive >> c) & 1u) { m.st(m.cb() + j, m.ld(m.cb() + c)); ++j; }
+    // class key: the hit transcripts of both strands merged, in ascending order
+    int j;
+    if (hF == 0) { tids_at = m.cb(VOTE ? 1 : 0); j = hR; }
+    else {
+        j = hF;
+        if (VOTE)
+            for (int b = 0; b < hR; ++b) {
+                const uint32_t t = m.ld(m.cb(1) + b);
+                bool dup = false;
+                for (int a = 0; a < hF; ++a) dup |= m.ld(m.cb(0) + a) == t;
+                if (!dup) { m.st(m.cb(0) + j, t); ++j; }                             // j <= h <= Q_W: stays inside the forward area
+            }
+    }
     for (int i = 1; i < j; ++i) {
-        const uint32_t v = m.ld(m.cb() + i);
+        const uint32_t v = m.ld(tids_at + i);
         int y = i - 1;
-        while (y >= 0 && m.ld(m.cb() + y) > v) { m.st(m.cb() + y + 1, m.ld(m.cb() + y)); --y; }
-        m.st(m.cb() + y + 1, v);
+        while (y >= 0 && m.ld(tids_at + y) > v) { m.st(tids_at + y + 1, m.ld(tids_at + y)); --y; }
+        m.st(tids_at + y + 1, v);
     }
     return true;
 }

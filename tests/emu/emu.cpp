@@ -67,8 +67,10 @@ static bool pre_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L
     return cgp::perfect_mate(ix, m, L, pairLen, fl, nh, cls);
 }
 
-// the lockstep thread tier's per-read functions on the host (false: declined)
-static bool thr_stage(const std::vector<uint64_t>& pk, int L, std::vector<uint32_t>& scratch, cgq::QMem& m) {
+// the lockstep thread tier's per-read functions on the host (false: declined).  As in the kernels, a read whose first k-mer
+// and its reverse complement are both in the table goes to the two-strand (vote) instantiation, the rest to the lean one.
+template <bool VOTE>
+static bool thr_stage(const std::vector<uint64_t>& pk, int L, std::vector<uint32_t>& scratch, cgq::QMemT<VOTE>& m) {
     int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
     for (int j = 0; j < WMf; ++j) {
         int lo = 64 * j;
@@ -79,28 +81,50 @@ static bool thr_stage(const std::vector<uint64_t>& pk, int L, std::vector<uint32
     }
     if (L < 1) return false;
     m.stride = 1; m.W2 = W2f + 1;
-    scratch.assign(cgq::QMem::words(m.W2), 0xdeadbeefu);
+    scratch.assign(cgq::QMemT<VOTE>::words(m.W2), 0xdeadbeefu);
     m.base = scratch.data();
     for (int j = 0; j < W2f; ++j) { m.st(2 * j, (uint32_t)pk[j]); m.st(2 * j + 1, (uint32_t)(pk[j] >> 32)); }
     m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
     cgt::tsm_make_rc(m, L);
     return true;
 }
+// look-up class of a read as k_wt_pre / k_bsj_cls compute it: bit 0 / 1 = read[0,k) / its reverse complement in the table
+static bool both_class(const IndexView& ix, const std::vector<uint64_t>& pk, int L) {
+    if (L <= ix.k) return false;
+    uint64_t mer0 = pk[0] & ix.km;
+    return present(ix, mer0) && present(ix, revcomp(mer0, ix.k));
+}
 static uint64_t g_thr_why[2][16];
+static uint64_t g_thr_vote[2];
 static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
-    cgq::QMem m;
     int why = cgq::QD_N;
-    bool ok = thr_stage(pk, L, scratch, m) && cgq::q_wt_mate(ix, m, L, pairLen, lceMode, fl, nh, why);
+    bool ok;
+    if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
+        cgq::QMemT<true> m;
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why);
+        if (ok) ++g_thr_vote[0];
+    } else {
+        cgq::QMemT<false> m;
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_wt_mate<false>(ix, m, L, pairLen, lceMode, fl, nh, why);
+    }
     if (!ok) ++g_thr_why[0][(-why) & 15];
     return ok;
 }
 template <class Sink>
 static bool thr_bsj_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int lceMode, std::vector<uint32_t>& scratch, Sink& sink, uint32_t& nh, bool& split, uint32_t* tids) {
-    cgq::QMem m;
-    int why = cgq::QD_N;
-    if (!thr_stage(pk, L, scratch, m) || !cgq::q_bsj_record(ix, m, L, lceMode, sink, nh, split, why)) { ++g_thr_why[1][(-why) & 15]; return false; }
-    for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(m.cb() + t);
-    return true;
+    int why = cgq::QD_N, at = 0;
+    bool ok;
+    if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
+        cgq::QMemT<true> m;
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why);
+        if (ok) { ++g_thr_vote[1]; for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t); }
+    } else {
+        cgq::QMemT<false> m;
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_bsj_record<false>(ix, m, L, lceMode, sink, nh, split, at, why);
+        if (ok) for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t);
+    }
+    if (!ok) ++g_thr_why[1][(-why) & 15];
+    return ok;
 }
 
 extern "C" {
@@ -342,7 +366,7 @@ void emu_run_fill(void* r, uint8_t* mateFlags, uint16_t* mateNHits, uint64_t* ex
     memcpy(ctr, R->ctr, sizeof R->ctr);
 }
 
-void emu_thr_why(uint64_t* out, int reset) { memcpy(out, g_thr_why, sizeof g_thr_why); if (reset) memset(g_thr_why, 0, sizeof g_thr_why); }
+void emu_thr_why(uint64_t* out, int reset) { memcpy(out, g_thr_why, sizeof g_thr_why); out[15] = g_thr_vote[0]; out[31] = g_thr_vote[1]; if (reset) { memset(g_thr_why, 0, sizeof g_thr_why); memset(g_thr_vote, 0, sizeof g_thr_vote); } }
 
 // std::sort replica check: sorts packed kmerScores entries with cg::StdSort
 void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort<true>(n); }
