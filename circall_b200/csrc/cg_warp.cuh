@@ -446,8 +446,8 @@ __device__ __forceinline__ uint32_t tid_at(uint32_t p) {
 }
 
 // SA interval list of one strand -> its hits (intersectSAHits + collectHitsSimpleSA, or the single-interval
-// enumeration, :492-563), narrow form: every interval spans <= 32 positions, lane c holds transcript id `tid`
-// and `alive` says whether it is a hit.  ok = false when an interval is wider (the general kernel's job).
+// enumeration, :492-563), narrow form: the narrowest maximal interval spans <= 32 positions, lane c holds transcript id `tid`
+// and `alive` says whether it is a hit.  ok = false when the narrowest maximal interval is wider (the general kernel's job).
 struct Hits { uint32_t tid; bool alive, ok; uint32_t count; };
 template <int X>
 __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n) {
@@ -470,15 +470,13 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
     const unsigned skipB = __ballot_sync(FULL, drop);
     int mi = -1;
     uint32_t msp = 0xffffffffu;
-    bool wide = false;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         if ((skipB >> i) & 1) continue;
         uint32_t sp = ints[i].end - ints[i].begin;
-        if (sp > 32) wide = true;
         if (sp < msp) { msp = sp; mi = i; }
     }
-    if (wide) { H.ok = false; return H; }
+    if (msp > 32) { H.ok = false; return H; }       // the candidates (narrowest interval) must fit the lanes; the others may be wider
     const uint32_t mb = ints[mi].begin, me = ints[mi].end;
     bool have = (uint32_t)lane < msp;
     if (have) H.tid = tid_at<X>(__ldg(&ix.sa[mb + lane]));
@@ -493,16 +491,21 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
 #pragma unroll 1
         for (int y = 0; y < x && !dup; ++y) dup = (y != mi && ints[y].begin == ib && ints[y].end == ie);
         if (dup) continue;
-        uint32_t t = 0xffffffffu;
-        if ((uint32_t)lane < ie - ib) t = tid_at<X>(__ldg(&ix.sa[ib + lane]));
-        // a candidate stays alive iff its transcript occurs among this interval's positions
-        unsigned aB = __ballot_sync(FULL, H.alive);
+        // a candidate stays alive iff its transcript occurs among this interval's positions (32 of them per round)
+        const unsigned aB = __ballot_sync(FULL, H.alive);
+        unsigned seenB = 0;
 #pragma unroll 1
-        for (unsigned m = aB; m; m &= m - 1) {
-            int a = __ffs(m) - 1;
-            uint32_t ta = __shfl_sync(FULL, H.tid, a);
-            if (!__any_sync(FULL, t == ta) && lane == a) H.alive = false;
+        for (uint32_t c0 = ib; c0 < ie; c0 += 32) {
+            uint32_t t = 0xffffffffu;
+            if (c0 + (uint32_t)lane < ie) t = tid_at<X>(__ldg(&ix.sa[c0 + lane]));
+#pragma unroll 1
+            for (unsigned m = aB & ~seenB; m; m &= m - 1) {
+                int a = __ffs(m) - 1;
+                uint32_t ta = __shfl_sync(FULL, H.tid, a);
+                if (__any_sync(FULL, t == ta)) seenB |= 1u << a;
+            }
         }
+        if (H.alive && !((seenB >> lane) & 1u)) H.alive = false;
     }
     H.count = __popc(__ballot_sync(FULL, H.alive));
     return H;
