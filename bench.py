@@ -8,7 +8,7 @@ A *step* is one pass of the hot path over the whole synthetic workload (BASELINE
 hg19-scale synthetic transcriptome + BSJ index, 20 M 2x100 bp pairs per GPU), issued to the library in
 batches.  Three legs are measured by the default arm:
   value        inputs resident in HBM, device-timed bracket around K steps
-  e2e          the same work through the C ABI with HOST (pinned) buffers (three sessions in rotation): host->device copies of the reads
+  e2e          the same work through the C ABI with HOST (pinned) buffers (four sessions in rotation): host->device copies of the reads
                and device->host copies of the result lists are inside the timed region
   cpu_baseline the oracle (CPU restatement of the reference algorithm) on a bounded sample, rank 0, N = 1
 `--impl reference` times only the CPU restatement (the reference binary cannot be built here).
@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="pairs per submit of the end-to-end leg (smaller than --batch: the copy of the first batch and the read-back of the last are not overlapped, so short batches shorten the step)")
-    ap.add_argument("--sessions", type=int, default=3, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
+    ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
