@@ -1155,6 +1155,8 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         s->sms = sms; s->use_tsm = getenv("CG_TSM") != nullptr && atoi(getenv("CG_TSM")) != 0;
         s->use_pre = getenv("CG_NO_PRE") == nullptr;
         s->use_thr = getenv("CG_NO_THR") == nullptr;
+        // the lockstep tier keeps table slot numbers in 32 bits (cg_thr.cuh::q_walk)
+        if ((tx && tx->hcap > (1ULL << 32)) || (bsj && bsj->hcap > (1ULL << 32))) s->use_thr = false;
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
         s->gen_grid = sms * CG_GEN_MINB;

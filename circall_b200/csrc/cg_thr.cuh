@@ -142,16 +142,23 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
     const int sh = both ? 1 : 0, per = 8 >> sh;
     F.f = false; F.b = F.e = 0; hasR = false;
     while (o <= lim) {
-        uint64_t key[8]; u32x4 sl[8];
+        uint64_t key[8]; u32x4 sl[8]; uint32_t hs[8];
+        // the (at most) eight windows of this round start within 8 bases of each other: they are cut out of four words of the
+        // strand read once, instead of three scratch loads per window
+        const int wb = (s ? 2 * m.W2 : 0) + (o >> 4), sh0 = (o & 15) * 2;
+        const uint32_t w0 = m.ld(wb), w1 = m.ld(wb + 1), w2 = m.ld(wb + 2), w3 = m.ld(wb + 3);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int p = o + (i >> sh);
-            const bool in = p <= lim;
-            const uint64_t mer = m.chunk(s, in ? p : o) & ix.km;
-            homo |= in && homopolymer_ix(mer, ix);
+            const int j = i >> sh;                                             // position o + j
+            const bool in = o + j <= lim;
+            const int bit = sh0 + 2 * j, hi = bit >> 5, sf = bit & 31;         // bit < 46: the window starts in word 0 or 1
+            const uint32_t a = hi ? w1 : w0, b = hi ? w2 : w1, c = hi ? w3 : w2;
+            const uint64_t mer = ((uint64_t)cgt::fsr(a, b, sf) | ((uint64_t)cgt::fsr(b, c, sf) << 32)) & ix.km;
+            if (!(both && (i & 1))) homo |= in && homopolymer_ix(mer, ix);
             key[i] = (both && (i & 1)) ? revcomp(mer, k) : mer;
-            sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;          // an empty slot: not found
-            if (in) sl[i] = CG_LDG(&ix.hslots[home_slot(ix, key[i])]);
+            hs[i] = (uint32_t)home_slot(ix, key[i]);                           // (a table has fewer than 2^32 slots)
+            sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;            // an empty slot: not found
+            if (in) sl[i] = CG_LDG(&ix.hslots[hs[i]]);
         }
         if (homo) return -1;
         // Resolve all eight together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
@@ -166,7 +173,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
         }
         if (pend) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[home_slot(ix, key[i]) + 1]);
+            for (int i = 0; i < 8; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if ((pend >> i) & 1u) {
@@ -179,7 +186,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if ((pend >> i) & 1u) {
-                        const uint64_t h = (home_slot(ix, key[i]) + 2) & ix.hmask;
+                        const uint64_t h = ((uint64_t)hs[i] + 2) & ix.hmask;
                         uint32_t b1 = 0, e1 = 0;
                         if (resolve(ix, key[i], h, CG_LDG(&ix.hslots[h]), b1, e1)) { fb |= 1u << i; sl[i].z = b1; sl[i].w = e1; }
                     }
