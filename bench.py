@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="pairs per submit of the end-to-end leg (smaller than --batch: the copy of the first batch and the read-back of the last are not overlapped, so short batches shorten the step)")
+    ap.add_argument("--e2e-no-lists", action="store_true", help="experiment: the end-to-end leg without the per-record result lists (counts only)")
     ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -278,12 +279,12 @@ def main():
             for i, (b0, nb) in enumerate(ebatches):
                 s = SS[i % NS]
                 if len(pend) == NS:
-                    B = pend.pop(0).fetch(want_lists=True, materialize=False)
+                    B = pend.pop(0).fetch(want_lists=not args.e2e_no_lists, materialize=False)
                     tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
                 s.submit_raw(pin1.ptr + b0 * L, pinoff.ptr, pin2.ptr + b0 * L, pinoff.ptr, nb)
                 pend.append(s)
             for s in pend:
-                B = s.fetch(want_lists=True, materialize=False)
+                B = s.fetch(want_lists=not args.e2e_no_lists, materialize=False)
                 tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
             d2h[0] = tot
             if world > 1:
