@@ -87,12 +87,12 @@ def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0):
     return B, R
 
 
-@pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0)])
+@pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0), (250, 0), (33, 0)])
 def test_pipeline_parity(gpu_world, L, lce_mode):
     cg, T, otx, obsj, gtx, gbsj = gpu_world
     r1, r2 = make_reads(T, 100 + L, 20000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
     B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode)
-    assert B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0
+    assert L < 50 or (B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0)
 
 
 @pytest.mark.parametrize("off", ["CG_NO_THR", "CG_NO_PRE", "CG_NO_THR,CG_NO_PRE"])
