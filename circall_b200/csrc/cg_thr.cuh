@@ -80,15 +80,17 @@ enum { Q_NOTFOUND = 0, Q_FOUND = 1 };
 enum { QD_HOMO = -1, QD_BOTH_A = -2, QD_OTHER = -3, QD_SA0 = -4, QD_WIDE_EXT = -5, QD_NINT = -6, QD_WIDE_HITS = -7, QD_WIDE_SPAN = -8, QD_ODD = -9, QD_N = -10, QD_NKS = -11 };
 
 // longest common prefix of strand s of the read from query offset q and the text at p, compared over [i0, lim)
+// (out of line, arguments by value: the lockstep kernels are as sensitive to their code size as the warp kernels — a
+// quarter of the stall samples of the first version were instruction-fetch stalls)
 template <class M>
-CG_HD int q_match(const IndexView& ix, const M& m, int s, int q, uint32_t p, int i0, int lim) {
+CG_HDN int q_match(const u32x4* text, M m, int s, int q, uint32_t p, int i0, int lim) {
     int i = i0;
     uint32_t curb = 0xffffffffu;
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
     cgt::u32x2 mk; mk.x = mk.y = 0;
     while (i < lim) {
         const uint32_t tp = p + (uint32_t)i, b = tp >> 6;
-        if (b != curb) { cc = CG_LDG(&ix.text[2 * (uint64_t)b]); mk = CG_LDG(cgt::mask_ptr(ix, b)); curb = b; }
+        if (b != curb) { cc = CG_LDG(&text[2 * (uint64_t)b]); mk = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b + 1])); curb = b; }
         const int half = (tp >> 5) & 1, o5 = tp & 31;
         const uint64_t tw = cgt::half_codes(cc, half) >> (2 * o5);
         const uint32_t tm = (half ? mk.y : mk.x) >> o5;
@@ -103,19 +105,19 @@ CG_HD int q_match(const IndexView& ix, const M& m, int s, int q, uint32_t p, int
 }
 
 // SASearcher::lce on two text positions (cg::lce after its suffix-array reads)
-CG_HD int q_lce(const IndexView& ix, uint32_t o1, uint32_t o2, int startAt, int stopAt, int mode) {
+CG_HDN int q_lce(const u32x4* text, uint32_t n_text, uint32_t o1, uint32_t o2, int startAt, int stopAt, int mode) {
     if (mode == 0) { o1 += (uint32_t)startAt; o2 += (uint32_t)startAt; }
     int len = startAt;
     const uint32_t mx = cmax(o1, o2);
-    const int64_t room = (int64_t)ix.n - (int64_t)mx;
+    const int64_t room = (int64_t)n_text - (int64_t)mx;
     const int lim = (int)cmin<int64_t>((int64_t)stopAt, room);
     uint32_t b1c = 0xffffffffu, b2c = 0xffffffffu;
     u32x4 c1, c2; c1.x = c1.y = c1.z = c1.w = 0; c2 = c1;
     cgt::u32x2 m1, m2; m1.x = m1.y = 0; m2 = m1;
     while (len < lim) {
         const uint32_t a = o1 + (uint32_t)len, b = o2 + (uint32_t)len;
-        if ((a >> 6) != b1c) { b1c = a >> 6; c1 = CG_LDG(&ix.text[2 * (uint64_t)b1c]); m1 = CG_LDG(cgt::mask_ptr(ix, b1c)); }
-        if ((b >> 6) != b2c) { b2c = b >> 6; if (b2c == b1c) { c2 = c1; m2 = m1; } else { c2 = CG_LDG(&ix.text[2 * (uint64_t)b2c]); m2 = CG_LDG(cgt::mask_ptr(ix, b2c)); } }
+        if ((a >> 6) != b1c) { b1c = a >> 6; c1 = CG_LDG(&text[2 * (uint64_t)b1c]); m1 = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b1c + 1])); }
+        if ((b >> 6) != b2c) { b2c = b >> 6; if (b2c == b1c) { c2 = c1; m2 = m1; } else { c2 = CG_LDG(&text[2 * (uint64_t)b2c]); m2 = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b2c + 1])); } }
         const int ha = (a >> 5) & 1, oa = a & 31, hb = (b >> 5) & 1, ob = b & 31;
         const uint64_t wa = cgt::half_codes(c1, ha) >> (2 * oa), wb = cgt::half_codes(c2, hb) >> (2 * ob);
         const uint32_t ma = (ha ? m1.y : m1.x) >> oa, mb = (hb ? m2.y : m2.x) >> ob;
@@ -131,6 +133,18 @@ CG_HD int q_lce(const IndexView& ix, uint32_t o1, uint32_t o2, int startAt, int 
 }
 
 struct QProbe { bool f; uint32_t b, e; };
+
+// the generic probe loop from slot h on (what the two straight-line passes of a walk round leave open): x = found, y / z = interval
+CG_HDN u32x4 q_resolve_from(const u32x4* hslots, uint64_t hmask, uint64_t key, uint64_t h) {
+    u32x4 r; r.x = r.y = r.z = r.w = 0;
+    for (;;) {
+        const u32x4 sl = CG_LDG(&hslots[h]);
+        const uint64_t kk = (uint64_t)sl.x | ((uint64_t)sl.y << 32);
+        if (kk == key) { r.x = 1; r.y = sl.z; r.z = sl.w; return r; }
+        if (kk == ~0ULL) return r;
+        h = (h + 1) & hmask;
+    }
+}
 
 // The position walk (:112-132 with both = true: k-mer and reverse complement, a position counts when either is there;
 // :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, eight look-ups per round.
@@ -186,9 +200,8 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if ((pend >> i) & 1u) {
-                        const uint64_t h = ((uint64_t)hs[i] + 2) & ix.hmask;
-                        uint32_t b1 = 0, e1 = 0;
-                        if (resolve(ix, key[i], h, CG_LDG(&ix.hslots[h]), b1, e1)) { fb |= 1u << i; sl[i].z = b1; sl[i].w = e1; }
+                        const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 2) & ix.hmask);
+                        if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
                     }
                 }
             }
@@ -307,7 +320,7 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (c0 + c < w) {
-                                const int l = q_match(ix, m, s, o, p[c], k, mq);
+                                const int l = q_match(ix.text, m, s, o, p[c], k, mq);
                                 if (l > best) { best = l; first = last = c0 + c; }
                                 else if (l == best) last = c0 + c;
                             }
@@ -339,7 +352,7 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
                     int l = matched;
                     if (stopAt > matched) {                                        // else lce returns startAt at once
                         const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
-                        l = q_lce(ix, p1, p2, matched, stopAt, lceMode);
+                        l = q_lce(ix.text, ix.n, p1, p2, matched, stopAt, lceMode);
                     }
                     if (firstB) {
                         firstB = false;
@@ -397,15 +410,18 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
     return Q_FOUND;
 }
 
-// up to four SA positions -> transcript ids, the suffix-array entries then the text sectors as two waves of loads
-CG_HD void q_tids4(const IndexView& ix, uint32_t i0, int nn, uint32_t* tid) {
-    uint32_t p[4]; u32x4 t[4];
+// up to four SA positions -> transcript ids (x, y, z, w; 0xffffffff past nn), the suffix-array entries then the text sectors as
+// two waves of loads
+CG_HDN u32x4 q_tids4(const uint32_t* sa, const u32x4* text, uint32_t i0, int nn) {
+    uint32_t p[4], tid[4]; u32x4 t[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) p[x] = x < nn ? CG_LDG(&ix.sa[i0 + x]) : 0u;
+    for (int x = 0; x < 4; ++x) p[x] = x < nn ? CG_LDG(&sa[i0 + x]) : 0u;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) { t[x].x = t[x].y = t[x].z = t[x].w = 0; if (x < nn) t[x] = CG_LDG(&ix.text[2 * (uint64_t)(p[x] >> 6) + 1]); }
+    for (int x = 0; x < 4; ++x) { t[x].x = t[x].y = t[x].z = t[x].w = 0; if (x < nn) t[x] = CG_LDG(&text[2 * (uint64_t)(p[x] >> 6) + 1]); }
 #pragma unroll
     for (int x = 0; x < 4; ++x) tid[x] = x < nn ? cgt::tid_from(t[x], p[x]) : 0xffffffffu;
+    u32x4 r; r.x = tid[0]; r.y = tid[1]; r.z = tid[2]; r.w = tid[3];
+    return r;
 }
 
 CG_HD int q_popc(uint32_t x) {
@@ -446,11 +462,12 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
     const uint32_t mb = m.ld(m.iv(s, mi)), me = m.ld(m.iv(s, mi) + 1);
     const int cb = m.cb(s);
     for (uint32_t c0 = 0; c0 < msp; c0 += 4) {
-        uint32_t t[4];
         const int nn = (int)cmin<uint32_t>(4u, msp - c0);
-        q_tids4(ix, mb + c0, nn, t);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) if (x < nn) m.st(cb + (int)c0 + x, t[x]);
+        const u32x4 t = q_tids4(ix.sa, ix.text, mb + c0, nn);
+        m.st(cb + (int)c0, t.x);
+        if (nn > 1) m.st(cb + (int)c0 + 1, t.y);
+        if (nn > 2) m.st(cb + (int)c0 + 2, t.z);
+        if (nn > 3) m.st(cb + (int)c0 + 3, t.w);
     }
     nc = (int)msp;
     for (int c = 0; c < nc; ++c) {                          // one candidate per distinct transcript
@@ -465,12 +482,11 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
         if (ib == mb && ie == me) continue;                  // same positions: cannot drop a transcript
         uint32_t seen = 0;
         for (uint32_t c0 = ib; c0 < ie; c0 += 4) {
-            uint32_t t[4];
             const int nn = (int)cmin<uint32_t>(4u, ie - c0);
-            q_tids4(ix, c0, nn, t);
+            const u32x4 t = q_tids4(ix.sa, ix.text, c0, nn);
             for (int c = 0; c < nc; ++c) {
                 const uint32_t tc = m.ld(cb + c);
-                if (tc == t[0] || tc == t[1] || tc == t[2] || tc == t[3]) seen |= 1u << c;      // unused entries are 0xffffffff
+                if (tc == t.x || tc == t.y || tc == t.z || tc == t.w) seen |= 1u << c;          // unused entries are 0xffffffff
             }
         }
         alive &= seen;
@@ -483,6 +499,7 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
 template <bool VOTE>
 CG_HD int q_hits2(const IndexView& ix, const QMemT<VOTE>& m, int nF, int nR, int& hF, int& hR) {
     hF = hR = 0;
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         const int n = s == 0 ? nF : nR;
         if (n == 0) continue;
