@@ -37,6 +37,11 @@
 #pragma once
 #include "cg_tsm.cuh"
 
+#ifndef CG_THR_WALK
+#define CG_THR_WALK 4      // table look-ups per thread in a walk round.  Measured (k_wt_thr / k_bsj_thr, ms per 4 M pairs): 8 -> 4.93 / 9.28,
+                           // 4 -> 4.72 / 8.17, 2 -> 4.92 / 8.60 at 5 blocks per SM: the narrower round over-fetches less when the walk ends, needs
+                           // 16 registers less and halves the unrolled code; the number of rounds does not matter
+#endif
 #ifndef CG_THR_MINB
 #define CG_THR_MINB 5      // resident blocks per SM asked of the lockstep kernels (96 registers; measured: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5, 6 -> 5.46 / 10.8;
                            // asking for the largest shared-memory carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors)
@@ -45,6 +50,7 @@
 namespace cgq {
 using namespace cg;
 
+static const int QW = CG_THR_WALK;
 static const int Q_FI = 8;        // intervals kept (one strand)
 static const int Q_W = 16;        // widest interval resolved suffix by suffix (extension, hit candidates, intersection)
 static const int Q_SPAN = 64;     // widest interval the span filter walks
@@ -147,22 +153,22 @@ CG_HDN u32x4 q_resolve_from(const u32x4* hslots, uint64_t hmask, uint64_t key, u
 }
 
 // The position walk (:112-132 with both = true: k-mer and reverse complement, a position counts when either is there;
-// :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, eight look-ups per round.
+// :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, QW look-ups per round.
 // Returns the first position that hits (F: the k-mer's own look-up, hasR: its reverse complement's, both only) or -1;
 // homo is set when a looked-up window is a homopolymer (the caller declines).
 template <class M>
 CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
     const int k = ix.k;
-    const int sh = both ? 1 : 0, per = 8 >> sh;
+    const int sh = both ? 1 : 0, per = QW >> sh;
     F.f = false; F.b = F.e = 0; hasR = false;
     while (o <= lim) {
-        uint64_t key[8]; u32x4 sl[8]; uint32_t hs[8];
-        // the (at most) eight windows of this round start within 8 bases of each other: they are cut out of four words of the
+        uint64_t key[QW]; u32x4 sl[QW]; uint32_t hs[QW];
+        // the (at most) QW windows of this round start within QW bases of each other: they are cut out of four words of the
         // strand read once, instead of three scratch loads per window
         const int wb = (s ? 2 * m.W2 : 0) + (o >> 4), sh0 = (o & 15) * 2;
         const uint32_t w0 = m.ld(wb), w1 = m.ld(wb + 1), w2 = m.ld(wb + 2), w3 = m.ld(wb + 3);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < QW; ++i) {
             const int j = i >> sh;                                             // position o + j
             const bool in = o + j <= lim;
             const int bit = sh0 + 2 * j, hi = bit >> 5, sf = bit & 31;         // bit < 46: the window starts in word 0 or 1
@@ -175,21 +181,21 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
             if (in) sl[i] = CG_LDG(&ix.hslots[hs[i]]);
         }
         if (homo) return -1;
-        // Resolve all eight together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
+        // Resolve all of them together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
         // of the look-ups; the odd slot of the same sector (an L1 hit) settles almost all of those.  Both steps are
         // straight-line code for the whole warp; only what is still open afterwards takes the generic probe loop.
         uint32_t fb = 0, pend = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < QW; ++i) {
             const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
             if (kk == key[i]) fb |= 1u << i;
             else if (kk != ~0ULL) pend |= 1u << i;
         }
         if (pend) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
+            for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < QW; ++i) {
                 if ((pend >> i) & 1u) {
                     const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
                     if (kk == key[i]) { fb |= 1u << i; pend &= ~(1u << i); }
@@ -198,7 +204,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
             }
             if (pend) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < QW; ++i) {
                     if ((pend >> i) & 1u) {
                         const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 2) & ix.hmask);
                         if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
@@ -209,7 +215,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
         // the first position that hits; sl[i].z / .w are the interval of look-up i when it was found
         int pos = -1;
 #pragma unroll
-        for (int i = 7; i >= 0; --i) {
+        for (int i = QW - 1; i >= 0; --i) {
             if (both) {
                 if (!(i & 1) && ((fb >> i) & 3u)) { pos = o + (i >> 1); F.f = (fb >> i) & 1u; F.b = sl[i].z; F.e = sl[i].w; hasR = (fb >> (i + 1)) & 1u; }
             } else if ((fb >> i) & 1u) { pos = o + i; F.f = true; F.b = sl[i].z; F.e = sl[i].w; }
