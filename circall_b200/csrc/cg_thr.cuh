@@ -202,11 +202,27 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
                     else if (kk == ~0ULL) pend &= ~(1u << i);
                 }
             }
+            // both slots of the home sector taken by other k-mers (up to 9 % of the look-ups at this table's load): the two slots
+            // of the next sector, again for all look-ups together — one lane at a time in the probe loop this was 16 % of the
+            // kernel's time — and the loop only for what is left after that
+#pragma unroll 1
+            for (int step = 2; step < 4 && pend; ++step) {
+#pragma unroll
+                for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[((uint64_t)hs[i] + step) & ix.hmask]);
+#pragma unroll
+                for (int i = 0; i < QW; ++i) {
+                    if ((pend >> i) & 1u) {
+                        const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
+                        if (kk == key[i]) { fb |= 1u << i; pend &= ~(1u << i); }
+                        else if (kk == ~0ULL) pend &= ~(1u << i);
+                    }
+                }
+            }
             if (pend) {
 #pragma unroll
                 for (int i = 0; i < QW; ++i) {
                     if ((pend >> i) & 1u) {
-                        const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 2) & ix.hmask);
+                        const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 4) & ix.hmask);
                         if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
                     }
                 }
