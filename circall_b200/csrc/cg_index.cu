@@ -217,10 +217,14 @@ int build_khash(cg_index* idx) {
     CG_CUDA(cudaGetLastError());
     unsigned long long nk = 0;
     CG_CUDA(cudaMemcpy(&nk, cnt.p, 8, cudaMemcpyDeviceToHost));
-    // load factor <= 0.25: unsuccessful look-ups (the bulk of the mapper's probes) stop after ~1.3 slots
+#ifndef CG_TABLE_SLOTS_PER_KMER
+#define CG_TABLE_SLOTS_PER_KMER 8       // measured: 4 -> 21.98 ms per 4 M pairs, 8 -> 20.86 (fewer collided home slots, so fewer second and third
+                                        // resolution passes); costs 26 GB more of the 180 GB for config 2
+#endif
+    // load factor <= 0.125: unsuccessful look-ups (the bulk of the mapper's probes) stop after ~1.3 slots
     uint64_t cap = 16;
     int hshift = 60;
-    while (cap < nk * 4 + 2) { cap <<= 1; --hshift; }
+    while (cap < nk * CG_TABLE_SLOTS_PER_KMER + 2) { cap <<= 1; --hshift; }
     bnd.alloc(0); tmp.alloc(0);
     CG_CUDA(cudaMalloc((void**)&idx->d_hslots, cap * 16));
     CG_CUDA(cudaMemset(idx->d_hslots, 0xFF, cap * 16));
