@@ -734,7 +734,10 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
 }
 
 // ---- lockstep thread tier (cg_thr.cuh): one thread per read, single-strand reads ------------------------------------
-static const int THR_THREADS = 128;
+#ifndef CG_THR_THREADS
+#define CG_THR_THREADS 64        // measured 32 / 64 / 128 / 256: k_bsj_thr 7.70 / 7.45 / 7.57 / 7.70 ms, the two-strand kernels 0.41 / 0.41 / 0.56 / 0.64
+#endif
+static const int THR_THREADS = CG_THR_THREADS;
 // stage the packed read of this thread into its scratch; false when the read holds an N (or is empty)
 template <class M>
 __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, const PackGeom& g, int L, const M& m) {
@@ -757,7 +760,7 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
 // to the warp kernels.  The list is grouped by look-up class: the lean instantiation (VOTE = false) takes its head
 // [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
 template <bool VOTE>
-__global__ void __launch_bounds__(THR_THREADS, VOTE ? 3 : CG_THR_MINB)
+__global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
          const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
          uint8_t* __restrict__ ovf) {
@@ -778,7 +781,7 @@ k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
 // Circall_bsj: over the records list[..] (every exported record when list is null); ovf[rec] = 1 hands record rec to the warp
 // kernels (nothing was emitted for it).  seg as in k_wt_thr.
 template <bool VOTE>
-__global__ void __launch_bounds__(THR_THREADS, VOTE ? 3 : CG_THR_MINB)
+__global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, BsjOut o, int do_counts,
           uint8_t* __restrict__ ovf) {

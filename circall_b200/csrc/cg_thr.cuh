@@ -51,6 +51,10 @@ namespace cgq {
 using namespace cg;
 
 static const int QW = CG_THR_WALK;
+#ifndef CG_THR_EXT
+#define CG_THR_EXT 4       // suffixes per round of the extension
+#endif
+static const int QX = CG_THR_EXT;
 static const int Q_FI = 8;        // intervals kept (one strand)
 static const int Q_W = 16;        // widest interval resolved suffix by suffix (extension, hit candidates, intersection)
 static const int Q_SPAN = 64;     // widest interval the span filter walks
@@ -335,12 +339,12 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
                     const uint32_t w = hit.e - hit.b;
                     if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
                     int best = -1; uint32_t first = 0, last = 0;
-                    for (uint32_t c0 = 0; c0 < w; c0 += 4) {
-                        uint32_t p[4];
+                    for (uint32_t c0 = 0; c0 < w; c0 += QX) {
+                        uint32_t p[QX];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
+                        for (int c = 0; c < QX; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < QX; ++c) {
                             if (c0 + c < w) {
                                 const int l = q_match(ix.text, m, s, o, p[c], k, mq);
                                 if (l > best) { best = l; first = last = c0 + c; }
