@@ -37,6 +37,10 @@ static const unsigned FULL = 0xffffffffu;
 // entries; <= 16 entries: libstdc++'s sort is a plain insertion sort); the general one, run on the reads the
 // fast one hands over, keeps worst-case state (a 256-base read cannot produce more) in per-warp global scratch
 static const int FAST_FI = 8, FAST_FK = 16, GEN_FI = 232, GEN_FK = 928;
+#ifndef CG_W_LINEAR
+#define CG_W_LINEAR 256
+#endif
+static const int W_LINEAR = CG_W_LINEAR;     // widest open interval the extension resolves candidate by candidate (32 per round)
 
 __constant__ IndexView c_ix[2];          // [0] txIdx, [1] bsjIdx — written by the session before each stage
 
@@ -159,17 +163,27 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
     if (m <= startAt) { o.lb = lbIn + 1; o.ub = ubIn; o.len = startAt; return o; }
     const uint32_t w = ubIn - lbIn - 1;
     if (w == 0) { o.lb = ubIn; o.ub = ubIn; o.len = startAt; return o; }        // empty open interval
-    if (w <= 32) {
-        int l = -1;
-        if ((uint32_t)lane < w) {
-            const uint32_t p = __ldg(&ix.sa[lbIn + 1 + lane]);
-            if (CG_OPT_PF & 1) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);       // transcript-id half of the block of p, for the hit enumeration
-            l = w_match<X>(r, s, qstart, p, startAt, m) >> 2;
+    if (w <= (uint32_t)W_LINEAR) {
+        // every candidate suffix by its own lane, 32 per round: the suffixes that share the longest prefix are contiguous in
+        // SA order, so the answer is the first and the last index that reach the maximum.  Up to W_LINEAR candidates this
+        // beats the three binary searches below (2 x 3 x log2(w) dependent loads) on latency.
+        int best = -1; uint32_t first = 0, last = 0;
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < w; c0 += 32) {
+            int l = -1;
+            if (c0 + (uint32_t)lane < w) {
+                const uint32_t p = __ldg(&ix.sa[lbIn + 1 + c0 + lane]);
+                if ((CG_OPT_PF & 1) && w <= 32) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);   // transcript-id half of the block of p, for the hit enumeration
+                l = w_match<X>(r, s, qstart, p, startAt, m) >> 2;
+            }
+            const int cb = __reduce_max_sync(FULL, l);
+            const unsigned mk = __ballot_sync(FULL, l == cb);
+            const uint32_t f = c0 + (uint32_t)(__ffs(mk) - 1), e = c0 + (uint32_t)(31 - __clz(mk));
+            if (cb > best) { best = cb; first = f; last = e; }
+            else if (cb == best) last = e;
         }
-        int best = __reduce_max_sync(FULL, l);
-        unsigned mk = __ballot_sync(FULL, l == best);
-        o.lb = lbIn + 1 + (uint32_t)(__ffs(mk) - 1);
-        o.ub = lbIn + 1 + (uint32_t)(31 - __clz(mk)) + 1;
+        o.lb = lbIn + 1 + first;
+        o.ub = lbIn + 1 + last + 1;
         o.len = best;
         return o;
     }
