@@ -28,6 +28,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner and, with NCCL_DEBUG set,
+# everything else to stdout), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the real stdout.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "read-pairs/sec quasi-mapped+BSJ-filtered (fused Circall_wt+Circall_bsj)"
 UNIT = "read-pairs/s"
 
@@ -138,7 +157,7 @@ def reference_arm(args):
                                                             "the Circall binary itself cannot be built here"}),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -176,6 +195,7 @@ def main():
     ap.add_argument("--e2e-no-lists", action="store_true", help="experiment: the end-to-end leg without the per-record result lists (counts only)")
     ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
+    _claim_stdout()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -360,7 +380,7 @@ def main():
                                                   "exported_records_per_step": int(n_exp), "junction_rows_per_step": int(n_junc)}),
                 "device_ms_per_step": dev_ms, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                 "counters": {k: int(v) for k, v in ctr.items()}}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     S.close()
     if world > 1:
         dist.destroy_process_group()
