@@ -289,7 +289,17 @@ def main():
         SS = [S] + [cg.Session(gtx, gbsj, stage=0) for _ in range(max(1, args.sessions) - 1)]
         NS = len(SS)
         ebatch = min(args.e2e_batch, batch)
-        ebatches = [(b0, min(ebatch, n - b0)) for b0 in range(0, n, ebatch)]
+        # submit sizes ramp up (and down at the end): the copy of the very first submit and the read-back of the very last one
+        # cannot overlap anything, so they are kept short
+        ebatches, b0, size = [], 0, max(ebatch // 8, 1 << 16)
+        while b0 < n:
+            left = n - b0
+            nb = min(size, left)
+            if left - nb < ebatch // 4:          # the tail: two short submits instead of one long
+                nb = left if left <= ebatch // 4 else left - ebatch // 8
+            ebatches.append((b0, nb))
+            b0 += nb
+            size = min(2 * size, ebatch)
         h2d = 2 * n * L + 2 * sum(8 * (nb + 1) for _, nb in ebatches)
         d2h = [0]
 

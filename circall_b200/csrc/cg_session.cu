@@ -54,6 +54,7 @@ struct BatchHdr {
     uint32_t n_t2_bsj;
     uint32_t n_t3_wt;              // mates / records the lockstep thread tier handed to the warp kernels
     uint32_t n_t3_bsj;
+    uint32_t n_cand;               // BSJ candidate records (Circall_bsj.cpp:390)
 };
 
 // ---- warp-per-read kernels --------------------------------------------------------------------------
@@ -831,6 +832,26 @@ k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     }
 }
 
+// ---- result lists derived on the device (the host used to loop over every exported record for them) -------------------
+// export list -> (pair, mate code 1 / 2) per record; exp == nullptr: record r is mate 1 of pair r (stage 2)
+__global__ void __launch_bounds__(256)
+k_exp_split(const uint32_t* __restrict__ exp, const uint32_t* __restrict__ n_dev, uint64_t n_fixed, uint32_t* __restrict__ pair, uint8_t* __restrict__ code) {
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_fixed;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = exp ? exp[r] : (uint32_t)(2 * r);
+        pair[r] = m >> 1; code[r] = (uint8_t)((m & 1) + 1);
+    }
+}
+// candidate flag of every record slot 0 .. worst (Circall_bsj.cpp:385-390): hits in 1 .. maxReadOccs and a junction row
+__global__ void __launch_bounds__(256)
+k_cand_flag(const uint32_t* __restrict__ nh, const uint8_t* __restrict__ sp, const uint32_t* __restrict__ n_dev, uint64_t n_fixed, uint64_t worst,
+            uint8_t* __restrict__ flag) {
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_fixed;
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= worst) return;
+    flag[r] = (r < n && sp[r] && nh[r] > 0 && nh[r] <= (uint32_t)MAX_READ_OCCS) ? 1 : 0;
+}
+
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 } // namespace
@@ -860,20 +881,19 @@ struct cg_session {
     const uint64_t* in_off1 = nullptr; const uint64_t* in_off2 = nullptr;
     // device buffers
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
-        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3;
+        d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3, d_exppair, d_expcode, d_cand;
     unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
     // host result buffers
     PinBuf h_hdr;
     // device -> host landing buffers are page-locked (a copy into pageable memory is staged and blocks the caller)
-    PinVec<uint32_t> h_exp_mate, h_recnh, h_eq_tids_raw;
-    PinVec<uint8_t> h_recsp, h_mflags;
+    PinVec<uint32_t> h_exp_pair, h_cand, h_recnh, h_eq_tids_raw;
+    PinVec<uint8_t> h_exp_code, h_recsp, h_mflags;
     PinVec<uint16_t> h_mnhits;
     PinVec<cg_junction> h_junc;
     PinVec<uint4> h_eqent;
-    std::vector<uint32_t> h_exp_pair, h_cand, h_eq_tids;
-    std::vector<uint8_t> h_exp_code;
+    std::vector<uint32_t> h_eq_tids;
     std::vector<uint64_t> h_eq_off;
     uint32_t wt_read_len = 0, bsj_read_len = 0;
 };
@@ -984,9 +1004,15 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     if (rc) return rc;
     rc = compact_flags(s, ovf_fast, worst, s->d_list2.as<uint32_t>(), &dh->n_ovf_bsj);
     if (rc) return rc;
-    return launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
-                  s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list2.as<uint32_t>(),
-                  (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch);
+    rc = launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
+                s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list2.as<uint32_t>(),
+                (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch);
+    if (rc) return rc;
+    // the candidate list (records with a junction row and 1 .. maxReadOccs hits), in record order; d_ovf2 is free again
+    rc = launch(s, k_cand_flag, dim3(grid_for(worst, 256)), dim3(256), 0, (const uint32_t*)o.rec_nhits, (const uint8_t*)o.rec_split,
+                em ? (const uint32_t*)&dh->n_exp : (const uint32_t*)nullptr, s->n_pairs, worst, s->d_ovf2.as<uint8_t>());
+    if (rc) return rc;
+    return compact_flags(s, s->d_ovf2.as<uint8_t>(), worst, s->d_cand.as<uint32_t>(), &dh->n_cand);
 }
 
 int run_batch(cg_session* s) {
@@ -1007,6 +1033,9 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_list2.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_ovf3.reserve(n_reads + 16));
     CG_CUDA(s->d_list3.reserve(n_reads * 4 + 16));
+    CG_CUDA(s->d_exppair.reserve(n_reads * 4 + 16));
+    CG_CUDA(s->d_expcode.reserve(n_reads + 16));
+    if (stage != 1) CG_CUDA(s->d_cand.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
@@ -1097,10 +1126,18 @@ int run_batch(cg_session* s) {
         if (rc) return rc;
         rc = compact_flags(s, s->d_expflag.as<uint8_t>(), n_reads, s->d_exp.as<uint32_t>(), &dh->n_exp);
         if (rc) return rc;
+        rc = launch(s, k_exp_split, dim3(s->sms * 8), dim3(256), 0, (const uint32_t*)s->d_exp.as<uint32_t>(), (const uint32_t*)&dh->n_exp, (uint64_t)0,
+                    s->d_exppair.as<uint32_t>(), s->d_expcode.as<uint8_t>());
+        if (rc) return rc;
     } else if (stage != 2) {
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
     }
-    if (stage == 2) CG_CUDA(cudaEventRecord(s->evw, s->stream));
+    if (stage == 2) {
+        CG_CUDA(cudaEventRecord(s->evw, s->stream));
+        rc = launch(s, k_exp_split, dim3(s->sms * 8), dim3(256), 0, (const uint32_t*)nullptr, (const uint32_t*)nullptr, n_pairs,
+                    s->d_exppair.as<uint32_t>(), s->d_expcode.as<uint8_t>());
+        if (rc) return rc;
+    }
     CG_CUDA(cudaEventRecord(s->evc, s->stream));
     if (stage != 1) {
         rc = run_bsj_stage(s, 3);
@@ -1176,10 +1213,10 @@ void cg_session_destroy(cg_session* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
-                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3})
+                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3, &s->d_exppair, &s->d_expcode, &s->d_cand})
         b->release();
     s->h_hdr.release();
-    s->h_exp_mate.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();
+    s->h_exp_pair.release(); s->h_exp_code.release(); s->h_cand.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();
     s->h_mnhits.release(); s->h_junc.release(); s->h_eqent.release();
     if (s->d_acc) cudaFree(s->d_acc);
     if (s->d_gscratch) cudaFree(s->d_gscratch);
@@ -1270,6 +1307,7 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     out->n_export = n_exp;
     out->n_junc = hdr.n_junc;
     out->n_eq = hdr.n_eq;
+    out->n_cand = stage != 1 ? hdr.n_cand : 0;
     out->n_fallback_wt = hdr.n_ovf_wt;
     out->n_fallback_bsj = hdr.n_ovf_bsj;
     out->n_tier2_wt = s->use_thr ? hdr.n_t3_wt : hdr.n_t2_wt;          // reads that reached the warp kernels
@@ -1287,35 +1325,27 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     }
     if (!want_lists) return CG_OK;
     int rc;
-    if (stage != 2) {
-        if ((rc = d2h(s, s->h_exp_mate, s->d_exp.p, n_exp))) return rc;
-    }
+    if ((rc = d2h(s, s->h_exp_pair, s->d_exppair.p, n_exp))) return rc;
+    if ((rc = d2h(s, s->h_exp_code, s->d_expcode.p, n_exp))) return rc;
     if (s->opts.keep_mate_detail && stage != 2) {
         if ((rc = d2h(s, s->h_mflags, s->d_mflags.p, 2 * s->n_pairs))) return rc;
         if ((rc = d2h(s, s->h_mnhits, s->d_mnhits.p, 2 * s->n_pairs))) return rc;
     }
     if (stage != 1) {
         if ((rc = d2h(s, s->h_junc, s->d_junc.p, hdr.n_junc))) return rc;
+        if ((rc = d2h(s, s->h_cand, s->d_cand.p, hdr.n_cand))) return rc;
         if ((rc = d2h(s, s->h_recnh, s->d_recnh.p, n_exp))) return rc;
         if ((rc = d2h(s, s->h_recsp, s->d_recsp.p, n_exp))) return rc;
         if ((rc = d2h(s, s->h_eqent, s->d_eqent.p, hdr.n_eq))) return rc;
         if ((rc = d2h(s, s->h_eq_tids_raw, s->d_eqtids.p, hdr.n_eq_tids))) return rc;
     }
     CG_CUDA(cudaStreamSynchronize(s->stream));
-    s->h_exp_pair.resize(n_exp); s->h_exp_code.resize(n_exp);
-    for (uint64_t r = 0; r < n_exp; ++r) {
-        uint32_t m = stage == 2 ? (uint32_t)(2 * r) : s->h_exp_mate[r];
-        s->h_exp_pair[r] = m >> 1; s->h_exp_code[r] = (uint8_t)((m & 1) + 1);
-    }
     out->exp_pair = s->h_exp_pair.data(); out->exp_code = s->h_exp_code.data();
     if (s->opts.keep_mate_detail && stage != 2) { out->mate_flags = s->h_mflags.data(); out->mate_nhits = s->h_mnhits.data(); }
     if (stage != 1) {
         out->junc = s->h_junc.data();
         out->rec_nhits = s->h_recnh.data(); out->rec_split = s->h_recsp.data();
-        s->h_cand.clear();
-        for (uint64_t r = 0; r < n_exp; ++r)
-            if (s->h_recsp[r] && s->h_recnh[r] > 0 && s->h_recnh[r] <= (uint32_t)MAX_READ_OCCS) s->h_cand.push_back((uint32_t)r);
-        out->n_cand = s->h_cand.size(); out->cand_rec = s->h_cand.data();
+        out->cand_rec = s->h_cand.data();
         // classes in record order
         std::sort(s->h_eqent.begin(), s->h_eqent.end(), [](const uint4& a, const uint4& b) { return a.x < b.x; });
         s->h_eq_off.assign(1, 0); s->h_eq_tids.clear();
