@@ -7,7 +7,7 @@
 // SACollectorCircall::operator() (include/SACollectorCircall.hpp:24-582) for a read whose hits sit on ONE strand,
 // written so that every heavy operation occurs exactly once in the instruction stream —
 //
-//     for each segment of the read:   LOOK (table look-ups, 8 in flight)  ->  EXTEND (extendSearchNaive, 4 suffixes
+//     for each segment of the read:   LOOK (table look-ups, QW per round)   ->  EXTEND (extendSearchNaive, 4 suffixes
 //                                     in flight)  ->  LCE  ->  next position
 //
 // — and the lanes of a warp meet at each of them whatever segment of whatever strand they are on.  (The resumable /
@@ -22,7 +22,7 @@
 //     clean-match kernel does) and answer all of those.
 //   * every other look-up is part of a walk over positions whose k-mers are expected to be absent (the windows
 //     that cover a mismatch, or the hunt for a first seed): the positions visited do not depend on the results, so
-//     eight go out per round and the first present one is taken.
+//     QW of them go out per round and the first present one is taken.
 //   * a read with hits on both strands (`other` look-up present, :265-272 / :379-385, or both k-mers in Phase A)
 //     needs the kmerScores vote (:442-490): declined.
 // Declined as well (nothing is emitted, the warp-per-read kernels redo the read from scratch with identical
