@@ -705,7 +705,10 @@ k_bsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGe
 }
 
 // ---- front kernel of Circall_wt: one thread per mate, clean full-length matches only (cg_pre.cuh) -----------------
-static const int PRE_THREADS = 128;
+#ifndef CG_PRE_THREADS
+#define CG_PRE_THREADS 128
+#endif
+static const int PRE_THREADS = CG_PRE_THREADS;
 __global__ void __launch_bounds__(PRE_THREADS)
 k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf) {
