@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
     ap.add_argument("--genes", type=int, default=0, help="override the gene count (smaller index for quick runs)")
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU per step")
-    ap.add_argument("--batch", type=int, default=1 << 22, help="pairs per library batch")
+    ap.add_argument("--batch", type=int, default=1 << 25, help="pairs per library batch (the whole 20 M-pair step of config 2 is one batch: 4 Mi -> 197.9, 10 M -> 207.2, 20 M -> 211.3 M pairs/s; the latency tails of the warp / general kernels are per launch)")
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="pairs in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=400_000, help="pairs per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -370,8 +370,9 @@ def main():
         kern = {"k_wt": (by_wt, k_avg[1]), "k_bsj": (by_bsj, k_avg[3])}
         dom = max(kern, key=lambda k: kern[k][1])
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        try:   # ncu's DRAM bytes of one captured batch, scaled to this run's launch size (the capture records its own)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj[dom] * pairs_per_launch / tj.get("pairs_per_batch", 4_000_000)
         except Exception:
             pass
         ach = kern[dom][0] * pairs_per_launch / (kern[dom][1] * 1e-3) / 1e9

@@ -1,6 +1,6 @@
 """Turn the ncu outputs brought back in gpurun_out/ into the small tracked summaries under profiles/.
 
-  python scripts/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep>
+  python scripts/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep> [pairs per batch of the profiled run]
 
   profiles/<tag>_launches.txt      per-kernel launch count, total and share of the device time (launch list pass)
   profiles/<tag>_kernels.csv       headline metrics of every captured launch (ncu --set full)
@@ -29,6 +29,7 @@ def short(name):
 
 def main():
     tag, launches, rep = sys.argv[1:4]
+    pairs_per_batch = int(sys.argv[4]) if len(sys.argv) > 4 else 8_000_000      # of the profiled command (bench.py --pairs 8000000, one batch)
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     # ---- launch list
     rows = [r for r in csv.reader(open(launches)) if r and not r[0].startswith("==")]
@@ -77,6 +78,7 @@ def main():
                 traffic.setdefault(key, {}).setdefault(k, []).append(b)
     # a stage (what bench.py brackets with events as k_wt / k_bsj) = all of its tiers: mean bytes per launch of each kernel, summed
     tj = {key: sum(sum(v) / len(v) for v in d.values()) for key, d in traffic.items()}
+    tj["pairs_per_batch"] = pairs_per_batch
     tj["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per batch, summed over the kernels (tiers) of the stage, ncu --set full, %s" % os.path.basename(rep)
     json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(open(os.path.join(ROOT, "profiles", tag + "_launches.txt")).read())
