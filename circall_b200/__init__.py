@@ -123,6 +123,7 @@ def lib():
     L.cg_host_free.argtypes = [vp]
     L.cg_device_flush_l2.argtypes = [i32]
     L.cg_bench_gather.argtypes = [i32, u64, u32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.cg_pack_reads.argtypes = [i32, vp, vp, vp, vp, u64, i32, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_double)]
     _LIB = L
     return L
 
@@ -416,6 +417,25 @@ class PinnedBuffer:
 
 def flush_l2(device=0):
     _check(lib().cg_device_flush_l2(device))
+
+
+def pack_reads(r1, off1, r2, off2, max_len, general=False, iters=1, device=0):
+    """The read-packing kernel on its own (cg_pack_reads): r1 / r2 concatenated ASCII bases (uint8 arrays), off1 / off2
+    uint64 offsets (n_pairs + 1).  Returns (packed [2 n_pairs, W2 + WM] uint64, lens uint16, status, ms per launch)."""
+    import numpy as np
+    r1 = np.ascontiguousarray(r1, dtype=np.uint8); r2 = np.ascontiguousarray(r2, dtype=np.uint8)
+    off1 = np.ascontiguousarray(off1, dtype=np.uint64); off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+    n = len(off1) - 1
+    assert len(off2) == n + 1
+    w2 = max(1, (max_len + 31) // 32)
+    wt = w2 + (w2 + 1) // 2
+    packed = np.zeros((2 * n, wt), dtype=np.uint64)
+    lens = np.zeros(2 * n, dtype=np.uint16)
+    st = ctypes.c_int(0)
+    ms = ctypes.c_double(0.0)
+    _check(lib().cg_pack_reads(device, r1.ctypes.data, off1.ctypes.data, r2.ctypes.data, off2.ctypes.data, n, max_len, int(general), iters,
+                               packed.ctypes.data, lens.ctypes.data, ctypes.byref(st), ctypes.byref(ms)))
+    return packed, lens, st.value, ms.value
 
 
 def bench_gather(nbytes, per_thread=64, iters=5, device=0):

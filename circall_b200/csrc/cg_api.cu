@@ -235,7 +235,7 @@ int cg_collect(const cg_index* idx, const char* bases, const uint64_t* offsets, 
         CG_CUDA(cudaMemcpy(dOff.p, off2.data(), (nc + 1) * 8, cudaMemcpyHostToDevice));
         CG_CUDA(cudaMemset(dSt.p, 0, 4));
         // k_pack takes pairs: hand it the chunk as both mate files and read the mate-1 records (stride 2)
-        k_pack<<<grid_for(2 * nc * g.W2f, 256), 256>>>(dB.as<unsigned char>(), dOff.as<uint64_t>(), dB.as<unsigned char>(), dOff.as<uint64_t>(),
+        k_pack<<<pack_grid(2 * nc, g), PACK_THREADS>>>(dB.as<unsigned char>(), dOff.as<uint64_t>(), dB.as<unsigned char>(), dOff.as<uint64_t>(),
                                                        nc, g, (int)mx, dPk.as<uint64_t>(), dLens.as<uint16_t>(), dSt.as<int>());
         CG_CUDA(cudaGetLastError());
         CollectOut o;
@@ -340,6 +340,46 @@ int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, 
     CG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *gbps = (double)threads * per_thread * iters * 32.0 / (ms * 1e-3) / 1e9;
+    return CG_OK;
+}
+
+int cg_pack_reads(int device, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2, uint64_t n_pairs,
+                  int max_len, int general, int iters, uint64_t* packed, uint16_t* lens, int* status, double* ms_per_launch) {
+    if (!off1 || !off2 || !packed || !lens || !status || max_len < 1 || max_len > 256 || iters < 1) CG_FAIL(CG_ERR_ARG, "bad argument");
+    CG_CUDA(cudaSetDevice(device));
+    PackGeom g = PackGeom::make(max_len);
+    uint64_t nb1 = off1[n_pairs], nb2 = off2[n_pairs], n_reads = 2 * n_pairs;
+    DevBuf d1, d2, o1, o2, pk, ln, st;
+    CG_CUDA(d1.alloc(nb1 + 64)); CG_CUDA(d2.alloc(nb2 + 64));
+    CG_CUDA(o1.alloc((n_pairs + 1) * 8)); CG_CUDA(o2.alloc((n_pairs + 1) * 8));
+    CG_CUDA(pk.alloc(n_reads * g.WT * 8)); CG_CUDA(ln.alloc(n_reads * 2)); CG_CUDA(st.alloc(4));
+    if (nb1) CG_CUDA(cudaMemcpy(d1.p, r1, nb1, cudaMemcpyHostToDevice));
+    if (nb2) CG_CUDA(cudaMemcpy(d2.p, r2, nb2, cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMemcpy(o1.p, off1, (n_pairs + 1) * 8, cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMemcpy(o2.p, off2, (n_pairs + 1) * 8, cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMemset(st.p, 0, 4));
+    cudaEvent_t e0, e1;
+    CG_CUDA(cudaEventCreate(&e0)); CG_CUDA(cudaEventCreate(&e1));
+    auto kern = general ? k_pack_general : k_pack;
+    for (int it = 0; it <= iters && n_reads; ++it) {          // the first launch is the warm-up
+        if (it == 1) CG_CUDA(cudaEventRecord(e0));
+        kern<<<pack_grid(n_reads, g), PACK_THREADS>>>(d1.as<unsigned char>(), o1.as<uint64_t>(), d2.as<unsigned char>(), o2.as<uint64_t>(), n_pairs, g, max_len,
+                                                       pk.as<uint64_t>(), ln.as<uint16_t>(), st.as<int>());
+    }
+    CG_CUDA(cudaGetLastError());
+    float ms = 0;
+    if (n_reads) {
+        CG_CUDA(cudaEventRecord(e1));
+        CG_CUDA(cudaEventSynchronize(e1));
+        CG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_per_launch) *ms_per_launch = ms / iters;
+    if (n_reads) {
+        CG_CUDA(cudaMemcpy(packed, pk.p, n_reads * g.WT * 8, cudaMemcpyDeviceToHost));
+        CG_CUDA(cudaMemcpy(lens, ln.p, n_reads * 2, cudaMemcpyDeviceToHost));
+    }
+    CG_CUDA(cudaMemcpy(status, st.p, 4, cudaMemcpyDeviceToHost));
     return CG_OK;
 }
 

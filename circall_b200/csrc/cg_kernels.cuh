@@ -3,6 +3,7 @@
 #pragma once
 #include "cg_common.h"
 #include "cg_pipeline.cuh"
+#include "cg_pack_swar.h"
 
 namespace cgk {
 using namespace cg;
@@ -37,18 +38,62 @@ __device__ __forceinline__ void pack4(uint32_t w, uint32_t& code8, uint32_t& n4,
     bad4 = (ob | (ob >> 7) | (ob >> 14) | (ob >> 21)) & 0xFu;
 }
 
+// the general formulation of one 32-base word: any character, N flags, partial words
+constexpr int PACK_THREADS = 256;
+static inline unsigned pack_grid(uint64_t n_reads, const PackGeom& g) {
+    uint64_t rpb = PACK_THREADS / g.W2f;
+    return (unsigned)((n_reads + rpb - 1) / rpb);
+}
+struct Word8 { uint32_t v[8]; };
+struct PackedWord { uint64_t code; uint32_t nmask, bad; };
+static __device__ __noinline__ PackedWord pack_word_general(Word8 in, int nb) {
+    uint64_t code = 0; uint32_t nmask = 0, bad = 0;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        uint32_t c8, n4, b4;
+        pack4(in.v[x], c8, n4, b4);
+        code |= (uint64_t)c8 << (8 * x);
+        nmask |= n4 << (4 * x);
+        bad |= b4 << (4 * x);
+    }
+    if (nb < 32) {
+        uint32_t keep = (1u << nb) - 1;
+        code &= (1ULL << (2 * nb)) - 1;
+        nmask = (nmask & keep) | ~keep;
+        bad &= keep;
+    }
+    // an N position carries code 0: spread the 32 mask bits to both bits of each 2-bit field
+    uint64_t x = nmask;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x << 2)) & 0x3333333333333333ULL;
+    x = (x | (x << 1)) & 0x5555555555555555ULL;
+    code &= ~(x | (x << 1));
+    return PackedWord{code, nmask, bad};
+}
+
 // K1: one thread per (read, 32-base word).  Consecutive threads read consecutive 32-byte pieces of
 // the concatenated ASCII buffer (aligned 4-byte loads + funnel shift) and write consecutive words
 // of the read-major packed records, so both sides are coalesced.
 //   reads r = 2 * pair + mate;  status bit0: character outside ACGTNacgtn, bit1: read longer than maxLen
-static __global__ void k_pack(const unsigned char* __restrict__ b1, const uint64_t* __restrict__ off1,
+// The kernel is bound by its instruction count, so a word takes the short way when all of its characters are
+// bases (ACGTacgt): four codes per 32-bit word with SWAR arithmetic, the characters the codes stand for rebuilt and
+// compared with the input (one test per thread), the codes gathered by a multiply.  A word with any other character
+// (N, or a character the reference rejects) goes through pack_word_general.  GENERAL = true: that way for every word
+// (what cg_pack_reads' check compares the short way with).
+template <bool GENERAL>
+__device__ __forceinline__ void pack_body(const unsigned char* __restrict__ b1, const uint64_t* __restrict__ off1,
                        const unsigned char* __restrict__ b2, const uint64_t* __restrict__ off2,
                        uint64_t n_pairs, PackGeom g, int maxLen, uint64_t* __restrict__ pk,
                        uint16_t* __restrict__ lens, int* status) {
-    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint64_t r = t / (uint64_t)g.W2f;
-    int j = (int)(t - r * (uint64_t)g.W2f);
-    if (r >= 2 * n_pairs) return;
+    // a block of PACK_THREADS threads takes PACK_THREADS / W2f whole reads (launch with pack_grid): no 64-bit division
+    float inv = __fdividef(1.0f, (float)g.W2f);
+    int rl = (int)(((float)threadIdx.x + 0.5f) * inv);                         // threadIdx.x / W2f: the half keeps the quotient
+    int rpb = (int)(((float)PACK_THREADS + 0.5f) * inv);                       // away from an integer, so the approximation is exact
+    int j = (int)threadIdx.x - rl * g.W2f;
+    uint64_t r = blockIdx.x * (uint64_t)rpb + rl;
+    if (rl >= rpb || r >= 2 * n_pairs) return;
     uint64_t i = r >> 1;
     const unsigned char* base = (r & 1) ? b2 : b1;
     const uint64_t* off = (r & 1) ? off2 : off1;
@@ -66,36 +111,36 @@ static __global__ void k_pack(const unsigned char* __restrict__ b1, const uint64
         int sh = (int)(a & 3) * 8;
         int need = (int)(a & 3) + nb;                 // bytes from q that hold data
         uint32_t w[9];
+        Word8 in;
+        uint32_t (&v)[8] = in.v;
 #pragma unroll
         for (int x = 0; x < 9; ++x) w[x] = (4 * x < need) ? __ldg(q + x) : 0u;
-        nmask = 0;
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            uint32_t v = __funnelshift_r(w[x], w[x + 1], sh);
-            uint32_t c8, n4, b4;
-            pack4(v, c8, n4, b4);
-            code |= (uint64_t)c8 << (8 * x);
-            nmask |= n4 << (4 * x);
-            bad |= b4 << (4 * x);
+        for (int x = 0; x < 8; ++x) v[x] = __funnelshift_r(w[x], w[x + 1], sh);
+        bool general = GENERAL;
+        if (!GENERAL) {
+            uint32_t diff = 0, m[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                uint32_t c = (4 * x + 4 <= nb) ? v[x] : 0x41414141u;     // words past the end (and a partial one) count as "AAAA"
+                m[x] = cg_pack4_bases(c, diff);                                // the four codes side by side in the top byte
+            }
+            uint32_t lo = __byte_perm(__byte_perm(m[0], m[1], 0x0073), __byte_perm(m[2], m[3], 0x0073), 0x5410);
+            uint32_t hi = __byte_perm(__byte_perm(m[4], m[5], 0x0073), __byte_perm(m[6], m[7], 0x0073), 0x5410);
+            code = (uint64_t)lo | ((uint64_t)hi << 32);
+            nmask = nb < 32 ? ~((1u << nb) - 1) : 0u;
+            general = diff != 0;
+            if (!general && (nb & 3)) {                                    // the bases of a partial word, one by one
+                int b0 = nb & ~3;
+                for (int y = b0; y < nb; ++y) {
+                    uint32_t c = __ldg(p + y);
+                    uint32_t t2 = ((c >> 1) ^ (c >> 2)) & 3u;
+                    if (((0x54474341u >> (8 * t2)) & 0xFFu) != (c & 0xDFu)) general = true;
+                    code |= (uint64_t)t2 << (2 * y);
+                }
+            }
         }
-        if (nb < 32) {
-            uint32_t keep = (1u << nb) - 1;
-            code &= (1ULL << (2 * nb)) - 1;
-            nmask = (nmask & keep) | ~keep;
-            bad &= keep;
-        }
-        // an N position carries code 0
-        uint64_t nm2 = 0;
-        {   // spread the 32 mask bits to the even bit positions of a 64-bit word
-            uint64_t x = nmask;
-            x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
-            x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
-            x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
-            x = (x | (x << 2)) & 0x3333333333333333ULL;
-            x = (x | (x << 1)) & 0x5555555555555555ULL;
-            nm2 = x | (x << 1);
-        }
-        code &= ~nm2;
+        if (general) { PackedWord o = pack_word_general(in, nb); code = o.code; nmask = o.nmask; bad = o.bad; }
     }
     if (bad) atomicOr(status, 1);
     uint64_t* rec = pk + r * (uint64_t)g.WT;
@@ -103,6 +148,18 @@ static __global__ void k_pack(const unsigned char* __restrict__ b1, const uint64
     uint32_t* mw = (uint32_t*)(rec + g.W2f + (j >> 1));
     mw[j & 1] = nmask;
     if ((g.W2f & 1) && j == g.W2f - 1) mw[1] = 0xFFFFFFFFu;
+}
+static __global__ void k_pack(const unsigned char* __restrict__ b1, const uint64_t* __restrict__ off1,
+                       const unsigned char* __restrict__ b2, const uint64_t* __restrict__ off2,
+                       uint64_t n_pairs, PackGeom g, int maxLen, uint64_t* __restrict__ pk,
+                       uint16_t* __restrict__ lens, int* status) {
+    pack_body<false>(b1, off1, b2, off2, n_pairs, g, maxLen, pk, lens, status);
+}
+static __global__ void k_pack_general(const unsigned char* __restrict__ b1, const uint64_t* __restrict__ off1,
+                       const unsigned char* __restrict__ b2, const uint64_t* __restrict__ off2,
+                       uint64_t n_pairs, PackGeom g, int maxLen, uint64_t* __restrict__ pk,
+                       uint16_t* __restrict__ lens, int* status) {
+    pack_body<true>(b1, off1, b2, off2, n_pairs, g, maxLen, pk, lens, status);
 }
 
 // set up this thread's read view in shared memory

@@ -1055,7 +1055,7 @@ int run_batch(cg_session* s) {
     CG_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
     // K1
-    rc = launch(s, k_pack, dim3(grid_for(n_reads * g.W2f, 256)), dim3(256), 0, s->in_r1, s->in_off1, s->in_r2, s->in_off2, n_pairs, g,
+    rc = launch(s, k_pack, dim3(pack_grid(n_reads, g)), dim3(PACK_THREADS), 0, s->in_r1, s->in_off1, s->in_r2, s->in_off2, n_pairs, g,
                 s->max_len, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), &s->d_hdr.as<BatchHdr>()->status);
     if (rc) return rc;
     CG_CUDA(cudaEventRecord(s->evp, s->stream));

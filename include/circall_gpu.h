@@ -190,6 +190,16 @@ int cg_device_flush_l2(int device);
  * Returns achieved GB/s of useful sectors. */
 int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, double* gbps);
 
+/* The read-packing kernel (K1) on its own, host buffers in and out: what a session does to a batch before the
+ * collectors run (2-bit codes as the collector reads them, SACollectorCircall.hpp:117-128,243-260: base j of a
+ * 32-base word at bits 2j, A 0 C 1 G 2 T 3, any other character code 0 with its bit set in the N mask).
+ * packed: 2 * n_pairs records (mate 1 then mate 2 of each pair) of W2 + WM 64-bit words, W2 = ceil(max_len / 32),
+ * WM = ceil(W2 / 2); lens: 2 * n_pairs; status bit 0: a character outside ACGTNacgtn, bit 1: a read longer than
+ * max_len (cut).  general != 0 runs the every-character formulation instead of the all-bases short cut (the two must
+ * agree bit for bit: tests/test_gpu_pipeline.py).  iters timed launches after one warm-up; ms_per_launch may be NULL. */
+int cg_pack_reads(int device, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2, uint64_t n_pairs,
+                  int max_len, int general, int iters, uint64_t* packed, uint16_t* lens, int* status, double* ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

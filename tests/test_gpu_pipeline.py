@@ -229,3 +229,78 @@ def test_merge_pairs_parity(gpu_world):
         assert np.array_equal(gj[:, [0, 1, 2, 6]], oj[:, [0, 1, 2, 6]]) and otm == bool(tm[i]), i
         paired = oj[:, 6] == 3
         assert np.array_equal(gj[paired], oj[paired])
+
+
+def _pack_numpy(bases, off, max_len):
+    """Numpy restatement of the packed-read record (include/circall_gpu.h: cg_pack_reads): 2-bit codes A 0 C 1 G 2 T 3
+    (either case), any other character code 0 + N-mask bit; positions past the read's end code 0 / mask 1."""
+    n = len(off) - 1
+    w2 = max(1, (max_len + 31) // 32)
+    wm = (w2 + 1) // 2
+    lut = np.full(256, 4, dtype=np.uint8)
+    for ch, c in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        lut[ch] = c
+    isn = np.zeros(256, dtype=bool)
+    isn[ord("N")] = isn[ord("n")] = True
+    rec = np.zeros((n, w2 + wm), dtype=np.uint64)
+    lens = np.zeros(n, dtype=np.uint16)
+    status = 0
+    for i in range(n):
+        s = bases[int(off[i]):int(off[i + 1])]
+        if len(s) > max_len:
+            status |= 2
+            s = s[:max_len]
+        lens[i] = len(s)
+        c = lut[s]
+        if np.any((c == 4) & ~isn[s]):
+            status |= 1
+        mask = np.ones(64 * wm, dtype=np.uint8)
+        mask[:len(s)] = (c == 4)
+        code = np.zeros(32 * w2, dtype=np.uint64)
+        code[:len(s)] = np.where(c == 4, 0, c)
+        sh = (2 * (np.arange(32 * w2) % 32)).astype(np.uint64)
+        rec[i, :w2] = np.bitwise_or.reduce((code << sh).reshape(w2, 32), axis=1)
+        rec[i, w2:] = np.bitwise_or.reduce((mask.astype(np.uint64) << (np.arange(64 * wm) % 64).astype(np.uint64)).reshape(wm, 64), axis=1)
+    return rec, lens, status
+
+
+@pytest.mark.parametrize("max_len,flavour", [(100, "bases"), (100, "mixed"), (75, "mixed"), (150, "mixed"), (250, "mixed"), (33, "mixed"), (64, "junk")])
+def test_pack_kernel_parity(max_len, flavour):
+    """K1 on its own: the all-bases short cut, the every-character formulation and the numpy restatement agree bit for bit
+    (read lengths 0 .. max_len + 3 at every byte alignment, lower case, N, characters the reference rejects)."""
+    import circall_b200 as cg
+    rng = np.random.default_rng(100 * max_len + len(flavour))
+    n = 3000
+    alpha = {"bases": b"ACGT", "mixed": b"ACGTacgtACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTNn", "junk": b"ACGTNacgtnX.*@ \x00\xff\x81\x61BDU"}[flavour]
+    alpha = np.frombuffer(alpha, dtype=np.uint8)
+    mates = []
+    for m in range(2):
+        ln = rng.integers(0, max_len + 1, size=n)
+        ln[rng.random(n) < 0.5] = max_len                       # half of them full length
+        if flavour != "bases":
+            ln[rng.random(n) < 0.02] = max_len + 3              # too long: cut, status bit 1
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(ln)
+        b = alpha[rng.integers(0, len(alpha), size=int(off[-1]))]
+        if flavour == "mixed":                                   # most reads clean, so that both ways run in every warp
+            clean = np.repeat(rng.random(n) < 0.7, ln)
+            b = np.where(clean, np.frombuffer(b"ACGT", dtype=np.uint8)[b & 3], b)
+        mates.append((np.ascontiguousarray(b), off))
+    (b1, o1), (b2, o2) = mates
+    fast, lf, sf, _ = cg.pack_reads(b1, o1, b2, o2, max_len, general=False)
+    gen, lg, sg, _ = cg.pack_reads(b1, o1, b2, o2, max_len, general=True)
+    assert np.array_equal(fast, gen) and np.array_equal(lf, lg) and sf == sg
+    r1, l1, s1 = _pack_numpy(b1, o1, max_len)
+    r2, l2, s2 = _pack_numpy(b2, o2, max_len)
+    assert np.array_equal(fast[0::2], r1) and np.array_equal(fast[1::2], r2)
+    assert np.array_equal(lf[0::2], l1) and np.array_equal(lf[1::2], l2)
+    assert sf == (s1 | s2)
+    if flavour == "bases":
+        assert sf == 0
+
+
+def test_pack_kernel_empty():
+    import circall_b200 as cg
+    z = np.zeros(1, dtype=np.uint64)
+    p, l, s, _ = cg.pack_reads(np.zeros(0, np.uint8), z, np.zeros(0, np.uint8), z, 100)
+    assert p.shape == (0, 6) and len(l) == 0 and s == 0
