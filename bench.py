@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="pairs per submit of the end-to-end leg (smaller than --batch: the copy of the first batch and the read-back of the last are not overlapped, so short batches shorten the step)")
+    ap.add_argument("--e2e-offsets", action="store_true", help="end-to-end leg through cg_session_submit (offset arrays copied with the reads) instead of cg_session_submit_fixed")
     ap.add_argument("--e2e-no-lists", action="store_true", help="experiment: the end-to-end leg without the per-record result lists (counts only)")
     ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
@@ -300,7 +301,7 @@ def main():
             ebatches.append((b0, nb))
             b0 += nb
             size = min(2 * size, ebatch)
-        h2d = 2 * n * L + 2 * sum(8 * (nb + 1) for _, nb in ebatches)
+        h2d = 2 * n * L + (2 * sum(8 * (nb + 1) for _, nb in ebatches) if args.e2e_offsets else 0)
         d2h = [0]
 
         def step_host():
@@ -311,7 +312,10 @@ def main():
                 if len(pend) == NS:
                     B = pend.pop(0).fetch(want_lists=not args.e2e_no_lists, materialize=False)
                     tot += 4 * B.n_export * 2 + B.n_export + 24 * B.n_junc + 40
-                s.submit_raw(pin1.ptr + b0 * L, pinoff.ptr, pin2.ptr + b0 * L, pinoff.ptr, nb)
+                if args.e2e_offsets:
+                    s.submit_raw(pin1.ptr + b0 * L, pinoff.ptr, pin2.ptr + b0 * L, pinoff.ptr, nb)
+                else:                           # every read of the workload has the same length: cg_session_submit_fixed, no offsets on PCIe
+                    s.submit_fixed_raw(pin1.ptr + b0 * L, pin2.ptr + b0 * L, nb, L)
                 pend.append(s)
             for s in pend:
                 B = s.fetch(want_lists=not args.e2e_no_lists, materialize=False)
@@ -324,7 +328,8 @@ def main():
             step_host()
         dte = bracket(step_host, args.steps)
         e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
-               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS, "batch_pairs": ebatch}
+               "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS, "batch_pairs": ebatch,
+               "call": "cg_session_submit" if args.e2e_offsets else "cg_session_submit_fixed"}
         for x in SS[1:]:
             x.close()
 

@@ -110,6 +110,7 @@ def lib():
     L.cg_session_destroy.restype = None
     L.cg_session_submit.argtypes = [vp, vp, vp, vp, vp, u64]
     L.cg_session_submit_device.argtypes = [vp, vp, vp, vp, vp, u64, u32]
+    L.cg_session_submit_fixed.argtypes = [vp, vp, vp, u64, u32]
     L.cg_session_fetch.argtypes = [vp, i32, ctypes.POINTER(_BatchResult)]
     L.cg_session_counters.argtypes = [vp, ctypes.POINTER(_Counters), vp, u64]
     L.cg_session_accumulator.argtypes = [vp, pp, ctypes.POINTER(u64)]
@@ -336,6 +337,10 @@ class Session:
     def submit_raw(self, p1, po1, p2, po2, n_pairs):
         """Host pointers (e.g. into pinned staging buffers) without any copy on the Python side."""
         _check(lib().cg_session_submit(self._h, p1, po1, p2, po2, n_pairs))
+
+    def submit_fixed_raw(self, p1, p2, n_pairs, read_len):
+        """host pointers to n_pairs * read_len characters per mate file (cg_session_submit_fixed)"""
+        _check(lib().cg_session_submit_fixed(self._h, p1, p2, n_pairs, read_len))
 
     def submit_device(self, d_r1, d_off1, d_r2, d_off2, n_pairs, max_read_len):
         _check(lib().cg_session_submit_device(self._h, d_r1, d_off1, d_r2, d_off2, n_pairs, max_read_len))

@@ -857,6 +857,12 @@ k_cand_flag(const uint32_t* __restrict__ nh, const uint8_t* __restrict__ sp, con
 
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// offsets of n reads of one length (cg_session_submit_fixed: the offsets are not worth their bytes on PCIe)
+__global__ void k_fixed_offsets(uint64_t* __restrict__ off, uint64_t n_plus_1, uint64_t len) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n_plus_1) off[i] = i * len;
+}
+
 } // namespace
 
 struct cg_session {
@@ -1255,6 +1261,28 @@ int cg_session_submit(cg_session* s, const char* r1, const uint64_t* off1, const
     s->in_off1 = s->d_off1.as<uint64_t>(); s->in_off2 = s->d_off2.as<uint64_t>();
     s->n_pairs = n_pairs; s->max_len = (int)mx; s->input_on_device = false;
     if (s->wt_read_len == 0 && n_pairs) s->wt_read_len = (uint32_t)(off1[1] - off1[0]);
+    return run_batch(s);
+}
+
+int cg_session_submit_fixed(cg_session* s, const char* r1, const char* r2, uint64_t n_pairs, uint32_t read_len) {
+    if (!s || (n_pairs && (!r1 || !r2))) CG_FAIL(CG_ERR_ARG, "null argument");
+    if (s->pending) CG_FAIL(CG_ERR_STATE, "previous batch not fetched");
+    if (n_pairs >= (1ULL << 30)) CG_FAIL(CG_ERR_ARG, "batch too large (limit 2^30 pairs)");
+    if (read_len == 0) CG_FAIL(CG_ERR_ARG, "read_len must be positive");
+    if (read_len > CG_MAX_READ_LEN) CG_FAIL(CG_ERR_LENGTH, "a read is longer than CG_MAX_READ_LEN");
+    CG_CUDA(cudaSetDevice(s->device));
+    uint64_t bytes = n_pairs * (uint64_t)read_len;
+    CG_CUDA(s->d_r1.reserve(bytes + 64)); CG_CUDA(s->d_r2.reserve(bytes + 64));
+    CG_CUDA(s->d_off1.reserve((n_pairs + 1) * 8));
+    if (bytes) CG_CUDA(cudaMemcpyAsync(s->d_r1.p, r1, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (bytes) CG_CUDA(cudaMemcpyAsync(s->d_r2.p, r2, bytes, cudaMemcpyHostToDevice, s->stream));
+    k_fixed_offsets<<<grid_for(n_pairs + 1, 256), 256, 0, s->stream>>>(s->d_off1.as<uint64_t>(), n_pairs + 1, read_len);
+    CG_CUDA(cudaGetLastError());
+    ++s->launches;
+    s->in_r1 = s->d_r1.as<unsigned char>(); s->in_r2 = s->d_r2.as<unsigned char>();
+    s->in_off1 = s->d_off1.as<uint64_t>(); s->in_off2 = s->d_off1.as<uint64_t>();
+    s->n_pairs = n_pairs; s->max_len = (int)read_len; s->input_on_device = false;
+    if (s->wt_read_len == 0 && n_pairs) s->wt_read_len = read_len;
     return run_batch(s);
 }
 

@@ -160,6 +160,10 @@ void cg_session_destroy(cg_session* s);
  * (the jobs pair_sequence_parser hands to processReadsQuasi, Circall_wt.cpp:237-241) */
 int cg_session_submit(cg_session* s, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2,
                       uint64_t n_pairs);
+/* same for a batch whose reads all have one length (what a sequencer writes): r1 / r2 hold n_pairs * read_len characters and
+ * the offsets are made on the device, so they do not cross PCIe (16 of the 216 bytes per 2x100 pair) and are not checked on
+ * the host.  Results are those of cg_session_submit with offsets i * read_len. */
+int cg_session_submit_fixed(cg_session* s, const char* r1, const char* r2, uint64_t n_pairs, uint32_t read_len);
 /* same, buffers already resident in this session's GPU memory (bench.py `value` leg); max_read_len bounds
  * every read of the batch (a longer read fails the batch with CG_ERR_LENGTH at fetch) */
 int cg_session_submit_device(cg_session* s, const char* d_r1, const uint64_t* d_off1, const char* d_r2,

@@ -304,3 +304,32 @@ def test_pack_kernel_empty():
     z = np.zeros(1, dtype=np.uint64)
     p, l, s, _ = cg.pack_reads(np.zeros(0, np.uint8), z, np.zeros(0, np.uint8), z, 100)
     assert p.shape == (0, 6) and len(l) == 0 and s == 0
+
+
+@pytest.mark.parametrize("L", [100, 75])
+def test_submit_fixed_equals_submit(gpu_world, L):
+    """cg_session_submit_fixed (offsets made on the device) gives what cg_session_submit gives for reads of one length."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 77 + L, 6000, L=L)
+    b1 = np.ascontiguousarray(r1).reshape(-1)
+    b2 = np.ascontiguousarray(r2).reshape(-1)
+    assert b1.size == 6000 * L and b2.size == 6000 * L
+    Sa = cg.Session(gtx, gbsj)
+    A = Sa.run(r1, r2)
+    Sb = cg.Session(gtx, gbsj)
+    Sb.submit_fixed_raw(b1.ctypes.data, b2.ctypes.data, 6000, L)
+    B = Sb.fetch()
+    ca, pa = Sa.counters()
+    cb, pb = Sb.counters()
+    assert ca == cb and np.array_equal(pa, pb)
+    assert (A.n_export, A.n_junc, A.n_cand, A.n_eq) == (B.n_export, B.n_junc, B.n_cand, B.n_eq)
+    assert sorted(zip(A.exp_pair.tolist(), A.exp_code.tolist())) == sorted(zip(B.exp_pair.tolist(), B.exp_code.tolist()))
+    assert sorted(A.junc.tolist()) == sorted(B.junc.tolist())
+    assert A.eq_classes() == B.eq_classes()
+    # an empty batch and the argument checks
+    Sb.submit_fixed_raw(None, None, 0, L)
+    assert Sb.fetch().n_pairs == 0
+    with pytest.raises(cg.CircallError):
+        Sb.submit_fixed_raw(b1.ctypes.data, b2.ctypes.data, 10, 0)
+    with pytest.raises(cg.CircallError):
+        Sb.submit_fixed_raw(b1.ctypes.data, b2.ctypes.data, 10, 100000)

@@ -163,7 +163,13 @@ int run_mapper(int stage, const Args& a) {
         for (;;) {
             if (pending[cur]) finish(cur);
             if (!in.fill(B[cur], a.batch)) break;
-            ck(cg_session_submit(S[cur], B[cur].b1, B[cur].off1.data(), B[cur].b2, B[cur].off2.data(), B[cur].n), "submitting a batch");
+            // reads of one length (the usual case): no offsets across PCIe
+            uint64_t len = B[cur].n ? B[cur].off1[1] : 0;
+            bool fixed = len > 0;
+            for (uint64_t i = 0; fixed && i < B[cur].n; ++i)
+                fixed = B[cur].off1[i + 1] - B[cur].off1[i] == len && B[cur].off2[i + 1] - B[cur].off2[i] == len;
+            if (fixed) ck(cg_session_submit_fixed(S[cur], B[cur].b1, B[cur].b2, B[cur].n, (uint32_t)len), "submitting a batch");
+            else ck(cg_session_submit(S[cur], B[cur].b1, B[cur].off1.data(), B[cur].b2, B[cur].off2.data(), B[cur].n), "submitting a batch");
             pending[cur] = true;
             pairs += B[cur].n;
             cur ^= 1;
