@@ -177,6 +177,24 @@ def oracle_indices(cg, oracle, T, cores, gtx=None, gbsj=None):
     return otx, obsj
 
 
+def _bind_to_gpu_socket(local):
+    """Experiment switch (--numa-affinity, off by default): run this rank on the CPUs NVML reports as local to
+    its GPU, so that the page-locked staging buffers it allocates afterwards sit on that socket.  Returns the CPU set or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception as e:                                   # an experiment: never fatal
+        sys.stderr.write("numa affinity not set: %r\n" % (e,))
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +211,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20, help="pairs per submit of the end-to-end leg (smaller than --batch: the copy of the first batch and the read-back of the last are not overlapped, so short batches shorten the step)")
     ap.add_argument("--e2e-offsets", action="store_true", help="end-to-end leg through cg_session_submit (offset arrays copied with the reads) instead of cg_session_submit_fixed")
+    ap.add_argument("--numa-affinity", action="store_true", help="experiment: bind the rank to the CPUs local to its GPU before the page-locked buffers are allocated")
     ap.add_argument("--e2e-no-lists", action="store_true", help="experiment: the end-to-end leg without the per-record result lists (counts only)")
     ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
@@ -208,6 +227,9 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    affinity, all_cpus = None, os.sched_getaffinity(0)
+    if args.numa_affinity:
+        affinity = _bind_to_gpu_socket(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import circall_b200 as cg
@@ -330,8 +352,12 @@ def main():
         e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS, "batch_pairs": ebatch,
                "call": "cg_session_submit" if args.e2e_offsets else "cg_session_submit_fixed"}
+        if affinity:
+            e2e["cpu_affinity"] = affinity
         for x in SS[1:]:
             x.close()
+    if affinity:
+        os.sched_setaffinity(0, all_cpus)                    # the cpu_baseline leg gets every host thread back
 
     # ---- cpu baseline + algorithmic bytes from the oracle's counters (rank 0, N = 1 only)
     cpu = None
