@@ -4,6 +4,7 @@
 #include "cg_kernels.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 using namespace cg;
 using namespace cgk;
@@ -16,6 +17,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")";
     cudaGetLastError();
     return CG_ERR_CUDA;
+}
+// Device-wide settings of the random-access path, applied whenever the library touches a device.  The k-mer table, suffix array and
+// text are read one 32-byte sector at a time at random addresses: the L2's default DRAM fetch granularity pulls in whole 128-byte
+// lines for them (110 B of DRAM traffic per missed sector).  CG_L2_FETCH = 32 / 64 / 128 overrides the default below.
+void device_tuning(int device) {
+    static int applied[64] = {0};
+    if (device < 0 || device >= 64 || applied[device]) return;
+    applied[device] = 1;
+    size_t want = CG_L2_FETCH_DEFAULT;
+    if (const char* e = getenv("CG_L2_FETCH")) want = (size_t)atoi(e);
+    if (want == 32 || want == 64 || want == 128) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) != cudaSuccess) cudaGetLastError();   // a hint: never fatal
+    }
 }
 }
 
@@ -321,6 +335,7 @@ int cg_merge_pairs(int device, uint64_t n_pairs, const uint64_t* left_off, const
 int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, double* gbps) {
     if (!gbps || bytes < (1u << 20) || per_thread == 0 || iters <= 0) CG_FAIL(CG_ERR_ARG, "bad argument");
     CG_CUDA(cudaSetDevice(device));
+    cgi::device_tuning(device);
     uint64_t ns = 1;
     while (ns * 2 * 32 <= bytes) ns *= 2;       // power-of-two number of 32-B sectors
     DevBuf buf, sink;

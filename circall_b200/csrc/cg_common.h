@@ -36,6 +36,10 @@ struct cg_index {
 namespace cgi {
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#ifndef CG_L2_FETCH_DEFAULT
+#define CG_L2_FETCH_DEFAULT 0          // 0 = leave the driver's default; set by measurement (profiles/r2_experiments.md)
+#endif
+void device_tuning(int device);        // cg_api.cu
 
 // RAII device buffer used for temporaries inside one API call
 struct DevBuf {

@@ -241,6 +241,7 @@ int check_device(int device) {
     if (e != cudaSuccess || nd == 0) { cudaGetLastError(); CG_FAIL(CG_ERR_CUDA, "no CUDA device available (libcircall_gpu has no CPU fallback)"); }
     if (device < 0 || device >= nd) CG_FAIL(CG_ERR_ARG, "device ordinal out of range");
     CG_CUDA(cudaSetDevice(device));
+    cgi::device_tuning(device);
     return CG_OK;
 }
 

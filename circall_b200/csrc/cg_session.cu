@@ -1182,6 +1182,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
     int nd = 0;
     if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) { cudaGetLastError(); CG_FAIL(CG_ERR_CUDA, "no CUDA device available (libcircall_gpu has no CPU fallback)"); }
     CG_CUDA(cudaSetDevice(device));
+    cgi::device_tuning(device);
     cg_session* s = new cg_session();
     s->tx = tx; s->bsj = bsj; s->opts = o; s->device = device;
     s->n_bsj = (o.stage != 1 && bsj) ? bsj->n_tx : 0;
