@@ -124,6 +124,7 @@ def lib():
     L.cg_host_free.argtypes = [vp]
     L.cg_device_flush_l2.argtypes = [i32]
     L.cg_bench_gather.argtypes = [i32, u64, u32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.cg_bench_gather_mode.argtypes = [i32, u64, u32, i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.cg_pack_reads.argtypes = [i32, vp, vp, vp, vp, u64, i32, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_double)]
     _LIB = L
     return L
@@ -443,7 +444,7 @@ def pack_reads(r1, off1, r2, off2, max_len, general=False, iters=1, device=0):
     return packed, lens, st.value, ms.value
 
 
-def bench_gather(nbytes, per_thread=64, iters=5, device=0):
+def bench_gather(nbytes, per_thread=64, iters=5, device=0, mode=0):
     g = ctypes.c_double()
-    _check(lib().cg_bench_gather(device, nbytes, per_thread, iters, ctypes.byref(g)))
+    _check(lib().cg_bench_gather_mode(device, nbytes, per_thread, iters, mode, ctypes.byref(g)))
     return g.value

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 
 using namespace cg;
 using namespace cgk;
@@ -29,6 +30,11 @@ void device_tuning(int device) {
     if (const char* e = getenv("CG_L2_FETCH")) want = (size_t)atoi(e);
     if (want == 32 || want == 64 || want == 128) {
         if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) != cudaSuccess) cudaGetLastError();   // a hint: never fatal
+    }
+    if (getenv("CG_DEBUG")) {
+        size_t got = 0;
+        cudaError_t e = cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "circall_gpu: device %d cudaLimitMaxL2FetchGranularity asked %zu, now %zu (%s)\n", device, want, got, cudaGetErrorString(e));
     }
 }
 }
@@ -136,6 +142,25 @@ k_merge(MergeIn in, uint64_t n_pairs, uint32_t readLen, uint32_t maxNumHits, int
 }
 
 // ---- random-sector gather microbenchmark ------------------------------------------------------------
+// MODE picks the load instruction: what the L2 fetches from DRAM for a missing 32-byte sector depends on it (profiles/r2_experiments.md)
+//   0 ld.global.nc (what __ldg compiles to)   1 .nc.L2::64B   2 .nc.L2::128B   3 .nc.L2::256B   4 .nc.L1::no_allocate
+//   5 ld.global.cg   6 ld.global (L1-allocating)   7 .nc.L1::no_allocate.L2::64B   8 ld.global.cv   9 both halves of the sector (2 x 16 B)
+template <int MODE>
+__device__ __forceinline__ uint4 gather_load(const uint4* p) {
+    uint4 v;
+    if (MODE == 1) asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 2) asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 3) asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 4) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 5) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 6) asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 7) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 8) asm volatile("ld.global.cv.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (MODE == 9) { uint4 a = __ldg(p), b = __ldg(p + 1); v.x = a.x ^ b.x; v.y = a.y; v.z = b.z; v.w = a.w ^ b.w; }
+    else v = __ldg(p);
+    return v;
+}
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_gather(const uint4* __restrict__ buf, uint64_t n_sectors_mask, uint32_t per_thread, uint64_t seed, uint32_t* sink) {
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -147,12 +172,19 @@ k_gather(const uint4* __restrict__ buf, uint64_t n_sectors_mask, uint32_t per_th
         for (int j = 0; j < 4; ++j) {
             x = x * 6364136223846793005ULL + 1442695040888963407ULL;
             uint64_t s = (x >> 20) & n_sectors_mask;
-            v[j] = __ldg(&buf[2 * s]);               // first 16 B of a 32-B sector
+            v[j] = gather_load<MODE>(&buf[2 * s]);   // first 16 B of a 32-B sector
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc += v[j].x ^ v[j].w;
     }
     if (acc == 0x12345678u) *sink = acc;
+}
+typedef void (*gather_fn)(const uint4*, uint64_t, uint32_t, uint64_t, uint32_t*);
+static gather_fn gather_kernel(int mode) {
+    switch (mode) {
+        case 1: return k_gather<1>; case 2: return k_gather<2>; case 3: return k_gather<3>; case 4: return k_gather<4>; case 5: return k_gather<5>;
+        case 6: return k_gather<6>; case 7: return k_gather<7>; case 8: return k_gather<8>; case 9: return k_gather<9>; default: return k_gather<0>;
+    }
 }
 
 } // namespace
@@ -333,6 +365,11 @@ int cg_merge_pairs(int device, uint64_t n_pairs, const uint64_t* left_off, const
 }
 
 int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, double* gbps) {
+    return cg_bench_gather_mode(device, bytes, per_thread, iters, 0, gbps);
+}
+
+int cg_bench_gather_mode(int device, uint64_t bytes, uint32_t per_thread, int iters, int mode, double* gbps) {
+    if (mode < 0 || mode > 9) CG_FAIL(CG_ERR_ARG, "gather mode must be 0..9");
     if (!gbps || bytes < (1u << 20) || per_thread == 0 || iters <= 0) CG_FAIL(CG_ERR_ARG, "bad argument");
     CG_CUDA(cudaSetDevice(device));
     cgi::device_tuning(device);
@@ -345,10 +382,11 @@ int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, 
     const uint64_t threads = 148ull * 2048 * 4;
     cudaEvent_t e0, e1;
     CG_CUDA(cudaEventCreate(&e0)); CG_CUDA(cudaEventCreate(&e1));
-    k_gather<<<grid_for(threads, 256), 256>>>(buf.as<uint4>(), ns - 1, per_thread, 1, sink.as<uint32_t>());
+    const gather_fn kern = gather_kernel(mode);
+    kern<<<grid_for(threads, 256), 256>>>(buf.as<uint4>(), ns - 1, per_thread, 1, sink.as<uint32_t>());
     CG_CUDA(cudaDeviceSynchronize());
     CG_CUDA(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) k_gather<<<grid_for(threads, 256), 256>>>(buf.as<uint4>(), ns - 1, per_thread, 2 + i, sink.as<uint32_t>());
+    for (int i = 0; i < iters; ++i) kern<<<grid_for(threads, 256), 256>>>(buf.as<uint4>(), ns - 1, per_thread, 2 + i, sink.as<uint32_t>());
     CG_CUDA(cudaEventRecord(e1));
     CG_CUDA(cudaEventSynchronize(e1));
     float ms = 0;

@@ -193,6 +193,10 @@ int cg_device_flush_l2(int device);
  * issues `per_thread` dependent-free 32-B loads at hashed addresses inside a `bytes`-sized buffer.
  * Returns achieved GB/s of useful sectors. */
 int cg_bench_gather(int device, uint64_t bytes, uint32_t per_thread, int iters, double* gbps);
+/* the same with another load instruction (mode 0 = cg_bench_gather's ld.global.nc; 1-3 L2::64B/128B/256B prefetch size, 4 L1::no_allocate,
+ * 5 .cg, 6 plain ld.global, 7 no_allocate + L2::64B, 8 .cv, 9 both 16-byte halves of the sector): what one missing sector costs in DRAM
+ * bytes depends on it, and that cost is the ceiling of the whole random-access path */
+int cg_bench_gather_mode(int device, uint64_t bytes, uint32_t per_thread, int iters, int mode, double* gbps);
 
 /* The read-packing kernel (K1) on its own, host buffers in and out: what a session does to a batch before the
  * collectors run (2-bit codes as the collector reads them, SACollectorCircall.hpp:117-128,243-260: base j of a

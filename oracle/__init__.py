@@ -36,6 +36,8 @@ def _lib():
     L.orc_index_from_text.argtypes = [vp, u64, i32, i32]
     L.orc_index_from_text_sa.restype = vp
     L.orc_index_from_text_sa.argtypes = [vp, u64, i32, vp, i32]
+    L.orc_suffix_array.restype = i32
+    L.orc_suffix_array.argtypes = [vp, u64, i32, i32, vp]
     L.orc_index_from_records.restype = vp
     L.orc_index_from_records.argtypes = [ctypes.POINTER(cp), ctypes.POINTER(cp), u32, i32, i32]
     L.orc_index_free.argtypes = [vp]
@@ -291,6 +293,15 @@ def merge_fuzzy(left, right, left_matches, right_matches, read_len=100, max_num_
                                len(left), rt.ctypes.data, rp.ctypes.data, rf.ctypes.data, len(right), read_len,
                                max_num_hits, out.ctypes.data, cap, ctypes.byref(tm))
     return out[:n].copy(), bool(tm.value)
+
+
+def suffix_array(text, algo=0, nthreads=None):
+    """Suffix array of a '$'-joined text: algo 0 = induced sorting (the index builder's), 1 = bucketed comparison sort."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    out = np.zeros(text.size, np.int32)
+    if _lib().orc_suffix_array(text.ctypes.data, text.size, algo, nthreads or os.cpu_count() or 1, out.ctypes.data) != 0:
+        raise RuntimeError("oracle suffix array: " + _err())
+    return out
 
 
 def stdsort(a):

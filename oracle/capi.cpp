@@ -12,6 +12,8 @@ void extendSearchBrute(const Searcher&, OffsetT, OffsetT, OffsetT, const Query&,
 int lce(const Searcher&, OffsetT, OffsetT, OffsetT, OffsetT);
 bool collect(const Searcher&, const char*, int, std::vector<QuasiAlignment>&,
              std::vector<SAIntervalHit>&, std::vector<SAIntervalHit>&, MateStatus, bool);
+void build_sa_sais(const std::string&, std::vector<OffsetT>&);
+void build_sa_compare(const std::string&, std::vector<OffsetT>&, int);
 void mergeLeftRightHitsFuzzy(bool, bool, std::vector<QuasiAlignment>&, std::vector<QuasiAlignment>&,
                              std::vector<QuasiAlignment>&, uint32_t, uint32_t, bool&);
 }
@@ -39,6 +41,16 @@ void* orc_index_from_text_sa(const char* seq, uint64_t n, int k, const int32_t* 
     try { index_from_text_with_sa(*ix, seq, n, k, sa, nthreads); } catch (...) { delete ix; throw; }
     return ix;
     ORC_CATCH(nullptr)
+}
+// the suffix array alone: algo 0 = induced sorting (u_sais.cpp, what the index builder uses), 1 = bucketed comparison sort
+int orc_suffix_array(const char* seq, uint64_t n, int algo, int nthreads, int32_t* out) {
+    ORC_TRY
+    std::string s(seq, n);
+    std::vector<OffsetT> SA;
+    if (algo == 0) build_sa_sais(s, SA); else build_sa_compare(s, SA, nthreads);
+    std::memcpy(out, SA.data(), n * sizeof(int32_t));
+    return 0;
+    ORC_CATCH(-1)
 }
 // FASTA records (names, sequences as NUL-terminated strings) with SURVEY B6 normalisation
 void* orc_index_from_records(const char** names, const char** seqs, uint32_t nrec, int k, int nthreads) {

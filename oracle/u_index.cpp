@@ -5,8 +5,9 @@
 //
 // The suffix array is the true suffix array of the whole '$'-joined text (what
 // libdivsufsort returns; it is unique, so any correct sorter gives the same array).
-// Built here by a bucketed comparison sort — deliberately a different algorithm
-// from the product's GPU prefix-doubling builder so the two check each other.
+// Built by induced sorting (u_sais.cpp); the bucketed comparison sort below is its cross-check
+// at test sizes — both deliberately different algorithms from the product's GPU
+// prefix-doubling builder so that they check each other.
 #include "oracle_types.hpp"
 #include "u_mer.hpp"
 #include <algorithm>
@@ -53,7 +54,10 @@ static inline int sa_code(char c) {   // order-preserving: '$' < A < C < G < T, 
     throw std::runtime_error("index text holds a character outside {A,C,G,T,$}");
 }
 
-static void build_sa(const std::string& seq, std::vector<OffsetT>& SA, int nthreads) {
+void build_sa_sais(const std::string& seq, std::vector<OffsetT>& SA);     // u_sais.cpp
+
+// the bucketed comparison sort: quadratic-ish on repetitive text, kept as the cross-check of u_sais.cpp at test sizes
+void build_sa_compare(const std::string& seq, std::vector<OffsetT>& SA, int nthreads) {
     const size_t n = seq.size();
     if (n >= (1ULL << 31)) throw std::runtime_error("text >= 2^31: 64-bit index not supported by the oracle");
     SA.resize(n);
@@ -162,7 +166,7 @@ static void build_khash(Index& ix, int nthreads) {
 
 void finish_index(Index& ix, int nthreads) {
     ix.rankDict.build(ix.seq);
-    build_sa(ix.seq, ix.SA, nthreads);
+    build_sa_sais(ix.seq, ix.SA);
     build_khash(ix, nthreads);
 }
 
