@@ -32,8 +32,35 @@
 #define CG_HDN inline
 #endif
 
+// Loads from the index (k-mer table, suffix array, text blocks, offsets): random addresses, read-only.  What the L2 pulls from DRAM
+// for a missing 32-byte sector is set by the load's prefetch-size qualifier: a plain ld.global.nc fills the whole 128-byte line
+// (130 B of DRAM traffic per load in the gather microbenchmark), .L2::64B fills 64 (65 B) at the same request rate
+// (profiles/r2_experiments.md).  CG_LTC = 0 / 64 / 128 / 256 picks the qualifier at build time.
+#ifndef CG_LTC
+#define CG_LTC 64
+#endif
 #if defined(__CUDA_ARCH__)
-#define CG_LDG(p) __ldg(p)
+#if CG_LTC == 64
+#define CG_LTC_Q ".L2::64B"
+#elif CG_LTC == 128
+#define CG_LTC_Q ".L2::128B"
+#elif CG_LTC == 256
+#define CG_LTC_Q ".L2::256B"
+#else
+#define CG_LTC_Q ""
+#endif
+namespace cg {
+__device__ __forceinline__ uint4 ldg_ix(const uint4* p) {
+    uint4 v; asm("ld.global.nc" CG_LTC_Q ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint2 ldg_ix(const uint2* p) {
+    uint2 v; asm("ld.global.nc" CG_LTC_Q ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint32_t ldg_ix(const uint32_t* p) {
+    uint32_t v; asm("ld.global.nc" CG_LTC_Q ".u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+}
+#define CG_LDG(p) cg::ldg_ix(p)
 #else
 #define CG_LDG(p) (*(p))
 #endif

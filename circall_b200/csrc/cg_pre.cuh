@@ -23,7 +23,7 @@
 //
 // CG_HD: tests/emu runs the same function on the host in front of the emulated tiers.
 #pragma once
-#include "cg_tsm.cuh"
+#include "cg_thrmem.cuh"
 
 namespace cgp {
 using namespace cg;
@@ -78,7 +78,7 @@ CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pair
     else return false;
     const uint32_t w = e - b;
     if (b == 0 || w == 0 || w > (uint32_t)PRE_WMAX) return false;
-    if (s == 1) cgt::tsm_make_rc(m, L);
+    if (s == 1) cgt::make_rc(m, L);
     // extendSearchNaive(b - 1, e) (:143 / :393): every suffix of the interval; all of their SA entries first
     uint32_t p[PRE_WMAX];
 #pragma unroll

@@ -10,7 +10,6 @@
 // Nothing here falls back to the host: without a CUDA device session creation fails.
 #include "cg_kernels.cuh"
 #include "cg_warp.cuh"
-#include "cg_tsm.cuh"
 #include "cg_pre.cuh"
 #include "cg_thr.cuh"
 #include <algorithm>
@@ -50,7 +49,7 @@ struct BatchHdr {
     int status;
     uint32_t n_ovf_wt;             // mates / records the fast path handed to the general kernels
     uint32_t n_ovf_bsj;
-    uint32_t n_t2_wt;              // mates the front kernel (or the state machine) declined / records the state machine declined
+    uint32_t n_t2_wt;              // mates the front kernel declined / records handed to the lockstep tier
     uint32_t n_t2_bsj;
     uint32_t n_t3_wt;              // mates / records the lockstep thread tier handed to the warp kernels
     uint32_t n_t3_bsj;
@@ -347,7 +346,7 @@ k_bsj_cls(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
         const uint64_t mer0 = __ldg(w) & ix.km, merL = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & ix.km;
         const uint64_t rc0 = revcomp(mer0, k), rcL = revcomp(merL, k);
         const uint64_t h0 = home_slot(ix, mer0), h1 = home_slot(ix, rc0), h2 = home_slot(ix, merL), h3 = home_slot(ix, rcL);
-        const u32x4 s0 = __ldg(&ix.hslots[h0]), s1 = __ldg(&ix.hslots[h1]), s2 = __ldg(&ix.hslots[h2]), s3 = __ldg(&ix.hslots[h3]);
+        const u32x4 s0 = CG_LDG(&ix.hslots[h0]), s1 = CG_LDG(&ix.hslots[h1]), s2 = CG_LDG(&ix.hslots[h2]), s3 = CG_LDG(&ix.hslots[h3]);
         uint32_t b, e;
         c = (uint8_t)(1 + (resolve(ix, mer0, h0, s0, b, e) ? 1 : 0) + (resolve(ix, rc0, h1, s1, b, e) ? 2 : 0)
                         + (resolve(ix, merL, h2, s2, b, e) ? 4 : 0) + (resolve(ix, rcL, h3, s3, b, e) ? 8 : 0));
@@ -454,9 +453,9 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
                     for (uint32_t c0 = it.begin; c0 < it.end; c0 += 32) {         // :326 / :355, 32 positions per round
                         bool pred = false; uint32_t tid = 0; int hitPos = 0;
                         if (c0 + lane < it.end) {
-                            uint32_t p = __ldg(&ix.sa[c0 + lane]), local;
+                            uint32_t p = CG_LDG(&ix.sa[c0 + lane]), local;
                             tid_of(ix, p, tid, local);
-                            uint32_t refLen = __ldg(&ix.offsets[tid + 1]) - __ldg(&ix.offsets[tid]) - 1;
+                            uint32_t refLen = CG_LDG(&ix.offsets[tid + 1]) - CG_LDG(&ix.offsets[tid]) - 1;
                             hitPos = (int)local;
                             int junctPos = (int)(refLen / 2);                     // :333
                             pred = hitPos < junctPos - 5 && hitPos + (int)it.len > junctPos + 5;   // :336 / :364
@@ -507,200 +506,6 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
         if (mapped) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)mapped);
         if (hits) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)hits);
         if (upper) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)upper);
-    }
-}
-
-// ---- first tier: block-sorted state machine (cg_tsm.cuh) ------------------------------------------------------
-// A block owns BSM_NC read contexts in shared memory (collector state, packed read, interval list, the landing
-// zone of its loads).  Every round: wait for the loads of the previous round (cp.async), SORT the contexts by state,
-// and let thread t advance the t-th context of that order by one step of cgt::tsm_complete / control / issue.  A warp
-// therefore runs 32 reads that are at the same place of the algorithm — the instruction stream is shared by all
-// 32 lanes instead of the 3 or 4 that happen to agree when every thread keeps its own read — and each context has
-// its next loads in flight while the block goes on to other contexts.  A read that bails (or holds an N) is flagged
-// in ovf[] and emits nothing here; the warp kernels redo it.
-#ifndef CG_BSM_NC
-#define CG_BSM_NC 256
-#endif
-static const int BSM_NC = CG_BSM_NC;
-#ifndef CG_BSM_MINB
-#define CG_BSM_MINB 1
-#endif
-static const int BSM_NCW = (int)(offsetof(cgt::Ctx, d) / 4);       // saved context words
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
-
-// scratch + landing zone of one context; the engines' loads become asynchronous copies into the landing zone
-struct BMem : cgt::TMem {
-    uint4* land;          // land[slot * BSM_NC]: 16-byte landing slots of this context
-    uint32_t* sal;        // sal[slot * BSM_NC]: its suffix-array entries
-    __device__ __forceinline__ void ld16(u32x4&, int slot, const u32x4* p) const { cp_async16(land + slot * BSM_NC, p); }
-    __device__ __forceinline__ void ld8(uint32_t&, uint32_t&, int slot, int half, const cgt::u32x2* p) const { cp_async8(reinterpret_cast<char*>(land + slot * BSM_NC) + 8 * half, p); }
-    __device__ __forceinline__ void ld4(uint32_t&, int slot, const uint32_t* p) const { cp_async4(sal + slot * BSM_NC, p); }
-    __device__ __forceinline__ void ld4w(uint32_t&, int slot, int word, const uint32_t* p) const { cp_async4(reinterpret_cast<uint32_t*>(land + slot * BSM_NC) + word, p); }
-};
-__host__ __device__ inline size_t bsm_smem_bytes(const PackGeom& g) {
-    return (size_t)BSM_NC * (4 * 16 + BSM_NCW * 4 + cgt::TMem::words(g.W2f + 1) * 4 + 4 * 4 + 4) + 2 * 32 * 4;
-}
-
-template <bool BSJ>
-__global__ void __launch_bounds__(BSM_NC, CG_BSM_MINB)
-k_bsm(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_fixed,
-      const uint32_t* __restrict__ exp_mate, int lceMode,
-      uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,      // wt outputs
-      BsjOut o, int do_counts,                                       // bsj outputs
-      uint8_t* __restrict__ ovf, int zero) {
-    extern __shared__ uint4 bsm_smem[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int W2 = g.W2f + 1, SW = cgt::TMem::words(W2);
-    uint4* land = bsm_smem;                                                    // [4][NC]
-    uint32_t* cxw = reinterpret_cast<uint32_t*>(land + 4 * BSM_NC);            // [NCW][NC]
-    uint32_t* scr = cxw + BSM_NCW * BSM_NC;                                    // [SW][NC]
-    uint32_t* sal = scr + SW * BSM_NC;                                         // [4][NC]
-    uint32_t* order = sal + 4 * BSM_NC;                                        // [NC]
-    uint32_t* hist = order + BSM_NC;                                           // [32]
-    uint32_t* start = hist + 32;                                               // [32]
-    const IndexView& ix = cgw::c_ix[BSJ ? 1 : 0];
-    const uint32_t n = (uint32_t)(BSJ ? (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed) : n_fixed);
-    const uint32_t stride = gridDim.x * BSM_NC;
-    uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
-    JSink sink; sink.buf = nullptr; sink.cursor = nullptr; sink.cap = 0; sink.rec = 0;
-    if (BSJ) { sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; }
-
-    auto accessor = [&](int i) {
-        BMem m; m.base = scr + i; m.stride = BSM_NC; m.W2 = W2; m.land = land + i; m.sal = sal + i;
-        return m;
-    };
-    // the packed words of mate c.r -> forward strand area (codes) and reverse-complement area (N masks, checked and
-    // then overwritten); both mates' lengths -> sa1
-    auto issue_record = [&](cgt::Ctx& c, const BMem& m) {
-        const uint32_t* rec = reinterpret_cast<const uint32_t*>(pk + (uint64_t)c.r * g.WT);
-        for (int j = 0; j < 2 * g.W2f; ++j) cp_async4(m.base + (size_t)j * BSM_NC, rec + j);
-        for (int j = 0; j < 2 * g.WMf; ++j) cp_async4(m.base + (size_t)(2 * W2 + j) * BSM_NC, rec + 2 * g.W2f + j);
-        cp_async4(m.sal + 1 * BSM_NC, reinterpret_cast<const uint32_t*>(lens + (c.r & ~1u)));
-        c.req = cgt::RQ_FETCH_W;
-    };
-    auto start_read = [&](cgt::Ctx& c, const BMem& m) {
-        if (c.x >= n) { c.req = cgt::RQ_DEAD; return; }
-        if (BSJ && exp_mate) { cp_async4(m.sal, exp_mate + c.x); c.req = cgt::RQ_FETCH_R; }
-        else { c.r = BSJ ? 2 * c.x : c.x; issue_record(c, m); }
-    };
-    auto save = [&](const cgt::Ctx& c, int i) {
-#pragma unroll
-        for (int w = 0; w < BSM_NCW; ++w) { uint32_t v; memcpy(&v, reinterpret_cast<const char*>(&c) + 4 * w, 4); cxw[w * BSM_NC + i] = v; }
-    };
-
-    {   // context tid starts on work item blockIdx.x * NC + tid
-        cgt::Ctx c;
-        memset(&c, 0, sizeof c);
-        c.zero = zero; c.pc = cgt::PC_START; c.x = blockIdx.x * BSM_NC + tid;
-        start_read(c, accessor(tid));
-        save(c, tid);
-    }
-    for (;;) {
-        cp_async_wait_all();
-        if (tid < 32) hist[tid] = 0;
-        __syncthreads();
-        // ---- sort the contexts by state: table look-up state, else the control resume point
-        {
-            const int req = (int)cxw[(offsetof(cgt::Ctx, req) / 4) * BSM_NC + tid], pc = (int)cxw[(offsetof(cgt::Ctx, pc) / 4) * BSM_NC + tid];
-            const int key = req ? req : 16 + pc;
-            const unsigned mm = __match_any_sync(0xffffffffu, key);
-            const int leader = __ffs(mm) - 1;
-            uint32_t wb = 0;
-            if (lane == leader) wb = atomicAdd(&hist[key], (uint32_t)__popc(mm));
-            wb = __shfl_sync(0xffffffffu, wb, leader);
-            __syncthreads();
-            if (tid < 32) {
-                uint32_t v = hist[tid], xs = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, xs, d); if (lane >= d) xs += y; }
-                start[tid] = xs - v;
-            }
-            __syncthreads();
-            order[start[key] + wb + __popc(mm & ((1u << lane) - 1))] = tid;
-        }
-        __syncthreads();
-        if (hist[cgt::RQ_DEAD] == BSM_NC) break;
-        const int i = (int)order[tid];
-        const BMem m = accessor(i);
-        cgt::Ctx c;
-#pragma unroll
-        for (int w = 0; w < BSM_NCW; ++w) { uint32_t v = cxw[w * BSM_NC + i]; memcpy(reinterpret_cast<char*>(&c) + 4 * w, &v, 4); }
-        c.d.s0 = land[0 * BSM_NC + i]; c.d.s1 = land[1 * BSM_NC + i]; c.d.s2 = land[2 * BSM_NC + i]; c.d.s3 = land[3 * BSM_NC + i];
-        c.d.sa0 = sal[0 * BSM_NC + i]; c.d.sa1 = sal[1 * BSM_NC + i]; c.d.sa2 = sal[2 * BSM_NC + i]; c.d.sa3 = sal[3 * BSM_NC + i];
-
-        if (c.req == cgt::RQ_FETCH_R) { c.r = c.d.sa0; issue_record(c, m); }
-        else if (c.req == cgt::RQ_FETCH_W) {
-            const uint32_t lw = c.d.sa1;
-            const int L = (int)((c.r & 1u) ? lw >> 16 : lw & 0xffffu);
-            bool anyN = false;                    // the mask words were staged in the reverse-complement area
-            for (int j = 0; j < g.WMf; ++j) {
-                int lo = 64 * j;
-                if (lo >= L) break;
-                uint64_t mk = (uint64_t)m.ld(2 * W2 + 2 * j) | ((uint64_t)m.ld(2 * W2 + 2 * j + 1) << 32);
-                if (L - lo < 64) mk &= (1ULL << (L - lo)) - 1;
-                anyN |= mk != 0;
-            }
-            if (anyN || L < 1) { ovf[c.x] = 1; c.x += stride; start_read(c, m); }
-            else {
-                m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
-                cgt::tsm_make_rc(m, L);
-                c.L = L; c.pairLen = BSJ ? L : (int)(lw & 0xffffu);        // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
-                c.pc = cgt::PC_START; c.req = cgt::RQ_NONE;
-            }
-        }
-        // one step of the state machine; its three phases are separated by meeting points of the warp
-        const bool stepping = c.req < cgt::RQ_FETCH_R;
-        bool ctl = false;
-        if (stepping) ctl = cgt::tsm_complete(c, ix, m, lceMode);
-        __syncwarp();
-        if (ctl) { sink.rec = c.x; cgt::tsm_control<BSJ>(c, ix, m, sink); }
-        __syncwarp();
-        if (stepping) {
-            cgt::tsm_issue(c, ix, m);
-            if (c.pc == cgt::PC_DONE) {
-                if (!BSJ) { flags[c.r] = c.flags; nhits[c.r] = c.nh; }
-                else {
-                    // commit (Circall_bsj.cpp:383-491)
-                    o.rec_nhits[c.x] = c.nh; o.rec_split[c.x] = c.split ? 1 : 0;
-                    upper += c.nh > 0;                                                    // :383
-                    const uint32_t cc = c.nh > (uint32_t)MAX_READ_OCCS ? 0 : c.nh;        // :385
-                    const bool cand = cc > 0 && c.split;                                  // :390
-                    obs += 1; mapped += cand; hits += cc;                                 // :488-491
-                    if (cand) {
-                        if (cc == 1) { if (do_counts & 1) atomicAdd(&o.per_bsj[m.ld(m.cb())], 1ULL); }   // EquivalenceClassBuilder.hpp:112-130
-                        else if (do_counts & 2) {
-                            unsigned long long e = atomicAdd(&o.hdr->n_eq, 1ULL), sidx = atomicAdd(&o.hdr->n_eq_tids, (unsigned long long)cc);
-                            if (e < o.eq_cap && sidx + cc <= o.eq_tids_cap) {
-                                o.eq_ent[e] = make_uint4(c.x, (uint32_t)sidx, cc, 0u);
-                                for (uint32_t t = 0; t < cc; ++t) o.eq_tids[sidx + t] = m.ld(m.cb() + t);
-                            }
-                        }
-                    }
-                }
-                c.pc = cgt::PC_START; c.x += stride; start_read(c, m);
-            } else if (c.pc == cgt::PC_BAIL) { ovf[c.x] = 1; c.pc = cgt::PC_START; c.x += stride; start_read(c, m); }
-        }
-        save(c, i);
-    }
-    if (BSJ && (do_counts & 1)) {
-        __shared__ uint32_t sh[BSM_NC / 32];
-        uint32_t t;
-        t = block_sum(obs, sh);    if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_OBS], (unsigned long long)t);
-        t = block_sum(mapped, sh); if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_MAP], (unsigned long long)t);
-        t = block_sum(hits, sh);   if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_HITS], (unsigned long long)t);
-        t = block_sum(upper, sh);  if (threadIdx.x == 0 && t) atomicAdd(&o.ctr[C_BSJ_UPPER], (unsigned long long)t);
     }
 }
 
@@ -756,7 +561,7 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
     if (anyN) return false;
     for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
     m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
-    cgt::tsm_make_rc(m, L);
+    cgt::make_rc(m, L);
     return true;
 }
 
@@ -878,7 +683,6 @@ struct cg_session {
     int sms = 0;
     bool use_pre = true;                         // Circall_wt front kernel for clean full-length matches (CG_NO_PRE=1 switches it off)
     bool use_thr = true;                         // lockstep thread tier in front of the warp kernels (CG_NO_THR=1 switches it off)
-    bool use_tsm = false;                        // first tier = thread state machine (CG_TSM=1 switches it on; experimental: parity-green, not yet faster)
     unsigned char* d_gscratch = nullptr;
     bool pending = false;
     // batch state
@@ -939,18 +743,6 @@ int compact_classes(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, 
     return launch(s, k_cls_write, dim3(nb), dim3(CP_THREADS), 0, f, n, (const uint32_t*)s->d_bc.as<uint32_t>(), nb, out);
 }
 
-// launch the block-sorted state machine over n_fixed mates (wt) / the exported records (bsj); persistent grid
-template <bool BSJ>
-int launch_tsm(cg_session* s, uint64_t n_fixed, const uint32_t* em, const BsjOut& o, int do_counts) {
-    const size_t smem = bsm_smem_bytes(s->geom);
-    if (smem > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(k_bsm<BSJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bsm<BSJ>, BSM_NC, smem));
-    if (nb < 1) nb = 1;
-    return launch(s, k_bsm<BSJ>, dim3(s->sms * nb), dim3(BSM_NC), smem, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, n_fixed, em,
-                  s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), o, do_counts, s->d_ovf.as<uint8_t>(), 0);
-}
-
 int run_bsj_stage(cg_session* s, int do_counts) {
     const uint64_t n_reads = 2 * s->n_pairs;
     const bool stage2 = s->opts.stage == 2;
@@ -970,16 +762,10 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     const dim3 blk(WARPS_PER_BLOCK * 32);
     const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, false, true), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(s->geom, true, true);
     int rc;
-    // tiers: (experimental state machine,) lockstep thread tier, fast warp kernel, general warp kernel — each over the records
+    // tiers: lockstep thread tier, fast warp kernel, general warp kernel — each over the records
     // the one before it declined
     const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;            // records still to map (null: all of them)
-    if (s->use_tsm) {
-        rc = launch_tsm<true>(s, s->n_pairs, em, o, do_counts);
-        if (rc) return rc;
-        rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
-        if (rc) return rc;
-        cur_list = s->d_list.as<uint32_t>(); cur_n = &dh->n_t2_bsj;
-    } else if (s->use_thr) {
+    if (s->use_thr) {
         // classify the records by their end k-mers, group them by class, map them one per thread
         CG_CUDA(cudaMemsetAsync(s->d_ovf3.p, 0, worst, s->stream));
         rc = launch(s, k_bsj_cls, dim3(grid_for(worst, 256)), dim3(256), 0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs,
@@ -1072,21 +858,15 @@ int run_batch(cg_session* s) {
         const dim3 blk(WARPS_PER_BLOCK * 32);
         const size_t smf = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false), smg = (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, true, false);
         // the tiers, each over the mates the one before it declined: front kernel (clean full-length matches, one thread
-        // per mate; or the experimental state machine), lockstep thread tier (single-strand reads with mismatches), fast
+        // per mate), lockstep thread tier (single-strand reads with mismatches), fast
         // warp kernel, general warp kernel
         const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;        // mates still to map (null: all of them)
-        if (s->use_tsm || s->use_pre) {
-            if (s->use_tsm) {
-                BsjOut none; memset(&none, 0, sizeof none);
-                CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, n_reads, s->stream));
-                rc = launch_tsm<false>(s, n_reads, (const uint32_t*)nullptr, none, 0);
-            } else {
-                rc = launch(s, k_wt_pre, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
-                            s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>());
-            }
+        if (s->use_pre) {
+            rc = launch(s, k_wt_pre, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>());
             if (rc) return rc;
             // the front kernel leaves a look-up class per declined mate: the lockstep tier wants its work grouped by it
-            rc = (s->use_thr && !s->use_tsm) ? compact_classes(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt)
+            rc = s->use_thr ? compact_classes(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt)
                                              : compact_flags(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt);
             if (rc) return rc;
             cur_list = s->d_list.as<uint32_t>(); cur_n = &dh->n_t2_wt;
@@ -1095,7 +875,7 @@ int run_batch(cg_session* s) {
             CG_CUDA(cudaMemsetAsync(s->d_ovf3.p, 0, n_reads, s->stream));
             // the class-sorted list has its two-strand classes at the end (compact_classes): lean instantiation over the head,
             // two-strand instantiation over the tail; an unsorted list (or none) goes through the lean one alone
-            const bool sorted = cur_list && s->use_pre && !s->use_tsm;
+            const bool sorted = cur_list && s->use_pre;
             const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
             rc = launch(s, k_wt_thr<false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
@@ -1202,7 +982,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         PackGeom g = PackGeom::make(160);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bw, k_wt_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, false));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_bsj_warp<false, false>, WARPS_PER_BLOCK * 32, (size_t)WARPS_PER_BLOCK * warp_smem_bytes(g, false, true));
-        s->sms = sms; s->use_tsm = getenv("CG_TSM") != nullptr && atoi(getenv("CG_TSM")) != 0;
+        s->sms = sms;
         s->use_pre = getenv("CG_NO_PRE") == nullptr;
         s->use_thr = getenv("CG_NO_THR") == nullptr;
         // the lockstep tier keeps table slot numbers in 32 bits (cg_thr.cuh::q_walk)
@@ -1343,7 +1123,7 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     out->n_fallback_wt = hdr.n_ovf_wt;
     out->n_fallback_bsj = hdr.n_ovf_bsj;
     out->n_tier2_wt = s->use_thr ? hdr.n_t3_wt : hdr.n_t2_wt;          // reads that reached the warp kernels
-    out->n_tier2_bsj = s->use_thr && !s->use_tsm ? hdr.n_t3_bsj : hdr.n_t2_bsj;
+    out->n_tier2_bsj = s->use_thr ? hdr.n_t3_bsj : hdr.n_t2_bsj;
     if (s->input_on_device && s->wt_read_len == 0 && s->n_pairs) {
         uint16_t l0 = 0;
         CG_CUDA(cudaMemcpy(&l0, s->d_lens.p, 2, cudaMemcpyDeviceToHost));

@@ -10,9 +10,9 @@
 //     for each segment of the read:   LOOK (table look-ups, QW per round)   ->  EXTEND (extendSearchNaive, 4 suffixes
 //                                     in flight)  ->  LCE  ->  next position
 //
-// — and the lanes of a warp meet at each of them whatever segment of whatever strand they are on.  (The resumable /
-// sequential state machines of cg_tsm.cuh failed on exactly this: every control state carried its own copy of the
-// engines and the lanes ran them one after the other.)
+// — and the lanes of a warp meet at each of them whatever segment of whatever strand they are on.  (Round 1's resumable /
+// sequential state-machine tiers failed on exactly this: every control state carried its own copy of the engines and
+// the lanes ran them one after the other; they are gone from the tree, profiles/r1_experiments.md keeps their numbers.)
 //
 // What makes the single loop possible, following the reference statement by statement (k = 31, read without N):
 //   * Phase A (:112-200) looks up the k-mer at 0 and its reverse complement; Phase B's / C's "expected present"
@@ -35,7 +35,7 @@
 //
 // CG_HD throughout: tests/emu runs the same functions on the host in front of the emulated warp tiers.
 #pragma once
-#include "cg_tsm.cuh"
+#include "cg_thrmem.cuh"
 
 #ifndef CG_THR_WALK
 #define CG_THR_WALK 4      // table look-ups per thread in a walk round.  Measured (k_wt_thr / k_bsj_thr, ms per 4 M pairs): 8 -> 4.93 / 9.28,

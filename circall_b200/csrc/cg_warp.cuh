@@ -84,7 +84,7 @@ __device__ __noinline__ Hit w_probe(uint64_t key, bool active) {
     bool pend = active;
     while (__any_sync(FULL, pend)) {
         if (pend) {
-            u32x4 s = __ldg(&ix.hslots[h]);
+            u32x4 s = CG_LDG(&ix.hslots[h]);
             uint64_t kk = (uint64_t)s.x | ((uint64_t)s.y << 32);
             if (kk == key) { r.b = s.z; r.e = s.w; r.found = true; pend = false; }
             else if (kk == ~0ULL) pend = false;
@@ -108,8 +108,8 @@ __device__ __noinline__ int w_match(RV r, int s, int qstart, uint32_t p, int i, 
         if (b != curb) {
             if (b == nxb) { c0 = n0; c1 = n1; tmk = nmk; }
             else {
-                u32x4 a = __ldg(&ix.text[2 * (uint64_t)b]);
-                u32x4 c = __ldg(&ix.text[2 * (uint64_t)b + 1]);
+                u32x4 a = CG_LDG(&ix.text[2 * (uint64_t)b]);
+                u32x4 c = CG_LDG(&ix.text[2 * (uint64_t)b + 1]);
                 c0 = (uint64_t)a.x | ((uint64_t)a.y << 32); c1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
                 tmk = (uint64_t)c.x | ((uint64_t)c.y << 32);
             }
@@ -118,8 +118,8 @@ __device__ __noinline__ int w_match(RV r, int s, int qstart, uint32_t p, int i, 
             // overlaps this block's load / comparison instead of following it
             nxb = 0xffffffffu;
             if (CG_OPT_TWOBLOCK && (int)(tp & 63) + (lim - i) > 64) {
-                u32x4 a = __ldg(&ix.text[2 * (uint64_t)b + 2]);
-                u32x4 c = __ldg(&ix.text[2 * (uint64_t)b + 3]);
+                u32x4 a = CG_LDG(&ix.text[2 * (uint64_t)b + 2]);
+                u32x4 c = CG_LDG(&ix.text[2 * (uint64_t)b + 3]);
                 n0 = (uint64_t)a.x | ((uint64_t)a.y << 32); n1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
                 nmk = (uint64_t)c.x | ((uint64_t)c.y << 32);
                 nxb = b + 1;
@@ -172,7 +172,7 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
         for (uint32_t c0 = 0; c0 < w; c0 += 32) {
             int l = -1;
             if (c0 + (uint32_t)lane < w) {
-                const uint32_t p = __ldg(&ix.sa[lbIn + 1 + c0 + lane]);
+                const uint32_t p = CG_LDG(&ix.sa[lbIn + 1 + c0 + lane]);
                 if ((CG_OPT_PF & 1) && w <= 32) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);   // transcript-id half of the block of p, for the hit enumeration
                 l = w_match<X>(r, s, qstart, p, startAt, m) >> 2;
             }
@@ -191,7 +191,7 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
     int prevLow = startAt, prevHigh = startAt, maxI = startAt;
     while (ub - lb > 1) {
         uint32_t c = lb + (ub - lb) / 2;
-        int v = w_match<X>(r, s, qstart, __ldg(&ix.sa[c]), cmin(prevLow, prevHigh), m);
+        int v = w_match<X>(r, s, qstart, CG_LDG(&ix.sa[c]), cmin(prevLow, prevHigh), m);
         int i = v >> 2, ord = (v & 3) - 1;
         if (i > maxI) maxI = i;
         if (i >= m || ord < 0) { ub = c; prevHigh = i; } else { lb = c; prevLow = i; }
@@ -202,7 +202,7 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
     for (int pass = 0; pass < 2; ++pass) {
         while (hi - lo > 1) {
             uint32_t c = lo + (hi - lo) / 2;
-            int v = w_match<X>(r, s, qstart, __ldg(&ix.sa[c]), startAt, maxI);
+            int v = w_match<X>(r, s, qstart, CG_LDG(&ix.sa[c]), startAt, maxI);
             int i = v >> 2, ord = (v & 3) - 1;
             bool goLeft = pass == 0 ? (i >= maxI || ord < 0) : (i < maxI && ord < 0);
             if (goLeft) hi = c; else lo = c;
@@ -453,7 +453,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
 // transcriptAtPosition(p) alone (no offset look-up)
 template <int X>
 __device__ __forceinline__ uint32_t tid_at(uint32_t p) {
-    u32x4 c = __ldg(&c_ix[X].text[2 * (uint64_t)(p >> 6) + 1]);
+    u32x4 c = CG_LDG(&c_ix[X].text[2 * (uint64_t)(p >> 6) + 1]);
     uint64_t mask = (uint64_t)c.x | ((uint64_t)c.y << 32);
     uint32_t o = p & 63;
     return c.z + (uint32_t)__popcll(o ? (mask & ((1ULL << o) - 1)) : 0ULL);
@@ -493,7 +493,7 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
     if (msp > 32) { H.ok = false; return H; }       // the candidates (narrowest interval) must fit the lanes; the others may be wider
     const uint32_t mb = ints[mi].begin, me = ints[mi].end;
     bool have = (uint32_t)lane < msp;
-    if (have) H.tid = tid_at<X>(__ldg(&ix.sa[mb + lane]));
+    if (have) H.tid = tid_at<X>(CG_LDG(&ix.sa[mb + lane]));
     // one lane per distinct transcript
     unsigned same = __match_any_sync(FULL, have ? H.tid : (0x80000000u | (uint32_t)lane));
     H.alive = have && (__ffs(same) - 1 == lane);
@@ -511,7 +511,7 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
 #pragma unroll 1
         for (uint32_t c0 = ib; c0 < ie; c0 += 32) {
             uint32_t t = 0xffffffffu;
-            if (c0 + (uint32_t)lane < ie) t = tid_at<X>(__ldg(&ix.sa[c0 + lane]));
+            if (c0 + (uint32_t)lane < ie) t = tid_at<X>(CG_LDG(&ix.sa[c0 + lane]));
 #pragma unroll 1
             for (unsigned m = aB & ~seenB; m; m &= m - 1) {
                 int a = __ffs(m) - 1;
@@ -544,7 +544,7 @@ __device__ __noinline__ uint32_t w_hits_list(int lane, const Interval* ints, int
     __syncwarp();
     uint32_t N = 32;
     while (N < msp) N <<= 1;
-    for (uint32_t c = lane; c < N; c += 32) scr[c] = c < msp ? tid_at<X>(__ldg(&ix.sa[mb + c])) : 0xffffffffu;
+    for (uint32_t c = lane; c < N; c += 32) scr[c] = c < msp ? tid_at<X>(CG_LDG(&ix.sa[mb + c])) : 0xffffffffu;
     __syncwarp();
     for (uint32_t k2 = 2; k2 <= N; k2 <<= 1)
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
@@ -579,7 +579,7 @@ __device__ __noinline__ uint32_t w_hits_list(int lane, const Interval* ints, int
         if (dup) continue;
         // mark the candidates that occur among this interval's positions (binary search in the sorted list)
         for (uint32_t c = ib + lane; c < ie; c += 32) {
-            uint32_t t = tid_at<X>(__ldg(&ix.sa[c]));
+            uint32_t t = tid_at<X>(CG_LDG(&ix.sa[c]));
             uint32_t lo = 0, hi = cnt;
             while (lo < hi) { uint32_t md = (lo + hi) >> 1; if (scr[md] < t) lo = md + 1; else hi = md; }
             if (lo < cnt && scr[lo] == t && act[lo] == counter) act[lo] = (uint8_t)(counter + 1);

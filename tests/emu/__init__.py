@@ -14,10 +14,9 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "emu.cpp"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_core.cuh"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pipeline.cuh"),
-            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm.cuh"),
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_thrmem.cuh"),
             os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_pre.cuh"),
-            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_thr.cuh"),
-            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_tsm_control.inc")]
+            os.path.join(_HERE, "..", "..", "circall_b200", "csrc", "cg_thr.cuh")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     return so
@@ -42,7 +41,7 @@ def _lib():
         L.emu_run_err.argtypes = [vp]
         L.emu_run_sizes.argtypes = [vp, vp]
         L.emu_run_fallbacks.argtypes = [vp, vp]
-        L.emu_run_tsm.argtypes = [vp, vp]
+        L.emu_run_tiers.argtypes = [vp, vp]
         L.emu_run_fill.argtypes = [vp] * 12
         L.emu_stdsort.argtypes = [vp, i32]
         _LIB = L
@@ -102,9 +101,9 @@ def run(tx, bsj, r1, off1, r2, off2, lce_mode=0):
         fb = np.zeros(2, np.uint64)
         L.emu_run_fallbacks(h, fb.ctypes.data)
         out["fallbacks"] = fb
-        ts = np.zeros(3 + 32 + 3, np.uint64)
-        L.emu_run_tsm(h, ts.ctypes.data)
-        out["tsm"] = ts          # [wt mates done by the state machine, bsj records done by it, steps, bail reasons wt[16], bsj[16], front kernel, lockstep tier wt, bsj]
+        ts = np.zeros(3, np.uint64)
+        L.emu_run_tiers(h, ts.ctypes.data)
+        out["tiers"] = ts        # [wt mates answered by the front kernel's function, wt mates / bsj records answered by the lockstep thread tier]
         L.emu_run_fill(h, *[out[k].ctypes.data for k in ("mate_flags", "mate_nhits", "exp_pair", "exp_code", "junc",
                                                          "cand", "rec_nhits", "rec_split", "eq_lens", "eq_tids", "ctr")])
         return out

@@ -10,7 +10,6 @@
 // kernels use (make_block / text_kmer / hmix); the suffix array is passed in by the test.
 #define CG_HOST_EMU 1
 #include "../../circall_b200/csrc/cg_pipeline.cuh"
-#include "../../circall_b200/csrc/cg_tsm.cuh"
 #include "../../circall_b200/csrc/cg_pre.cuh"
 #include "../../circall_b200/csrc/cg_thr.cuh"
 #include <algorithm>
@@ -28,25 +27,6 @@ struct EmuIndex {
     uint64_t n_kmers = 0;
 };
 
-
-// first tier, as in the kernels: the thread state machine stepped to completion on the host.  Returns false
-// when it bails (the caller then runs the next tier); rows it emitted before are discarded with `tmp`.
-template <bool BSJ, class Sink>
-static bool tsm_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, cgt::Ctx& c,
-                     std::vector<uint32_t>& scratch, Sink& sink, uint64_t& steps) {
-    int W2f = std::max(1, (L + 31) / 32), WMf = (W2f + 1) / 2;
-    cgt::TMem m; m.stride = 1; m.W2 = W2f + 1;
-    scratch.assign(cgt::TMem::words(m.W2), 0xdeadbeefu);
-    m.base = scratch.data();
-    if (!cgt::tsm_begin(c, m, pk.data(), W2f, WMf, L, pairLen)) return false;
-    if (getenv("CG_EMU_TSM_STEP")) {             // the resumable form, one scheduling round at a time
-        while (c.pc != cgt::PC_DONE && c.pc != cgt::PC_BAIL) { cgt::tsm_step<BSJ>(c, ix, m, lceMode, sink); ++steps; }
-    } else {                                     // the sequential form (what the thread-per-mate chain kernels run)
-        cgt::tsm_mate_sync<BSJ>(c, ix, m, lceMode, sink);
-        ++steps;
-    }
-    return c.pc == cgt::PC_DONE;
-}
 
 // the front kernel's per-mate function on the host (false: declined)
 static bool pre_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
@@ -85,7 +65,7 @@ static bool thr_stage(const std::vector<uint64_t>& pk, int L, std::vector<uint32
     m.base = scratch.data();
     for (int j = 0; j < W2f; ++j) { m.st(2 * j, (uint32_t)pk[j]); m.st(2 * j + 1, (uint32_t)(pk[j] >> 32)); }
     m.st(2 * W2f, 0); m.st(2 * W2f + 1, 0);
-    cgt::tsm_make_rc(m, L);
+    cgt::make_rc(m, L);
     return true;
 }
 // look-up class of a read as k_wt_pre / k_bsj_cls compute it: bit 0 / 1 = read[0,k) / its reverse complement in the table
@@ -249,11 +229,8 @@ struct EmuRun {
     std::vector<uint32_t> eqLens, eqTids;     // one entry per candidate record
     uint64_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t fallbacks[2] = {0, 0};      // reads the fast path handed to the general path (wt mates, bsj records)
-    uint64_t tsm_done[2] = {0, 0};       // reads finished by the thread state machine (first tier), wt mates / bsj records
-    uint64_t tsm_steps = 0;
     uint64_t pre_done = 0;               // wt mates resolved by the thread-per-mate front kernel's function
     uint64_t thr_done[2] = {0, 0};       // wt mates / bsj records resolved by the lockstep thread tier
-    uint64_t tsm_why[2][16] = {};        // bail reasons (cgt::BAIL_*) per tool
     int err = 0;
 };
 
@@ -275,7 +252,6 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
     auto* fs = new FastScratch<EFI, EFK, EHC>();
     std::vector<uint64_t> pk, strands;
     std::vector<uint32_t> tscr;
-    const bool use_tsm = getenv("CG_EMU_NO_TSM") == nullptr;
     const bool use_pre = getenv("CG_EMU_NO_PRE") == nullptr;
     const bool use_thr = getenv("CG_EMU_NO_THR") == nullptr;
     for (uint64_t i = 0; i < n; ++i) {
@@ -284,14 +260,10 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
         for (int m = 0; m < 2; ++m) {
             ReadView rv;
             if (!view_of(m ? r2 + off2[i] : r1 + off1[i], m ? l2 : l1, pk, strands, rv)) R->err = -4;
-            // same tiers as the kernels: thread state machine, small-capacity fast path, general path on overflow
-            cgt::Ctx tc; cgt::NoSink ns;
-            tc.why = 0;
+            // same tiers as the kernels: clean-match front function, lockstep thread tier, small-capacity fast path, general path on overflow
             if (use_pre && pre_host(TX->v, pk, m ? l2 : l1, l1, tscr, fl[m], nh[m])) ++R->pre_done;
             else if (use_thr && thr_wt_host(TX->v, pk, m ? l2 : l1, l1, lceMode, tscr, fl[m], nh[m])) ++R->thr_done[0];
-            else if (use_tsm && tsm_host<false>(TX->v, pk, m ? l2 : l1, l1, lceMode, tc, tscr, ns, R->tsm_steps)) {
-                ++R->tsm_done[0]; fl[m] = tc.flags; nh[m] = tc.nh;
-            } else if ((use_tsm ? ++R->tsm_why[0][tc.why & 15] : 0), !wt_mate_fast<EFI, EFK, EHC>(TX->v, rv, l1, lceMode, *fs, fl[m], nh[m])) {
+            else if (!wt_mate_fast<EFI, EFK, EHC>(TX->v, rv, l1, lceMode, *fs, fl[m], nh[m])) {
                 ++R->fallbacks[0];
                 wt_mate<EMAXINT, EMAXKS>(TX->v, rv, l1, lceMode, *sc, fl[m], nh[m]);
             }
@@ -316,18 +288,12 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
             view_of(m ? r2 + off2[i] : r1 + off1[i], (int)(m ? off2[i + 1] - off2[i] : off1[i + 1] - off1[i]), pk, strands, rv);
             VecSink sink{&R->junc, rec};
             uint32_t nh; bool split; uint8_t err = 0;
-            cgt::Ctx tc;
             std::vector<int64_t> tmpj; VecSink tsink{&tmpj, rec};
             int Lr = (int)(m ? off2[i + 1] - off2[i] : off1[i + 1] - off1[i]);
             if (use_thr && thr_bsj_host(BS->v, pk, Lr, lceMode, tscr, tsink, nh, split, tids)) {
                 ++R->thr_done[1];
                 R->junc.insert(R->junc.end(), tmpj.begin(), tmpj.end());
-            } else if ((tmpj.clear(), use_tsm) && tsm_host<true>(BS->v, pk, Lr, Lr, lceMode, tc, tscr, tsink, R->tsm_steps)) {
-                ++R->tsm_done[1]; nh = tc.nh; split = tc.split;
-                R->junc.insert(R->junc.end(), tmpj.begin(), tmpj.end());
-                cgt::TMem tm; tm.base = tscr.data(); tm.stride = 1; tm.W2 = std::max(1, (Lr + 31) / 32) + 1;
-                for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = tm.ld(tm.cb() + t);
-            } else if ((use_tsm ? ++R->tsm_why[1][tc.why & 15] : 0), bsj_record_fast<EFI, EFK, EHC>(BS->v, rv, lceMode, *fs, sink, nh, split)) {
+            } else if (bsj_record_fast<EFI, EFK, EHC>(BS->v, rv, lceMode, *fs, sink, nh, split)) {
                 for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = fs->tid[t];
             } else {
                 ++R->fallbacks[1];
@@ -348,7 +314,8 @@ void* emu_run(void* txh, void* bsjh, const char* r1, const uint64_t* off1, const
 void emu_run_free(void* r) { delete (EmuRun*)r; }
 int emu_run_err(void* r) { return ((EmuRun*)r)->err; }
 void emu_run_fallbacks(void* r, uint64_t* out) { out[0] = ((EmuRun*)r)->fallbacks[0]; out[1] = ((EmuRun*)r)->fallbacks[1]; }
-void emu_run_tsm(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->tsm_done[0]; out[1] = R->tsm_done[1]; out[2] = R->tsm_steps; out[35] = R->pre_done; out[36] = R->thr_done[0]; out[37] = R->thr_done[1]; for (int t = 0; t < 2; ++t) for (int w = 0; w < 16; ++w) out[3 + 16 * t + w] = R->tsm_why[t][w]; }
+// which tier answered: [0] wt mates by the clean-match front function, [1] wt mates / [2] bsj records by the lockstep thread tier
+void emu_run_tiers(void* r, uint64_t* out) { EmuRun* R = (EmuRun*)r; out[0] = R->pre_done; out[1] = R->thr_done[0]; out[2] = R->thr_done[1]; }
 void emu_run_sizes(void* r, uint64_t* out) {
     EmuRun* R = (EmuRun*)r;
     out[0] = R->expPair.size(); out[1] = R->junc.size() / 6; out[2] = R->cand.size(); out[3] = R->eqTids.size();

@@ -69,26 +69,14 @@ def test_pipeline_lockstep_tier_coverage(world, L, monkeypatch):
     T = world[0]
     r1, r2 = make_reads(T, 900 + L, 4000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
     R = _pipeline(world, r1, r2, 0)
-    ts = R.emu["tsm"]
-    pre, thr_wt, thr_bsj = int(ts[35]), int(ts[36]), int(ts[37])
+    ts = R.emu["tiers"]
+    pre, thr_wt, thr_bsj = int(ts[0]), int(ts[1]), int(ts[2])
     n_mates, n_rec = 2 * r1.shape[0], len(R.emu["exp_pair"])
     assert thr_wt > 0.4 * (n_mates - pre), (pre, thr_wt, n_mates)       # the test reads are N-rich (18 % of them hold one)
     assert thr_bsj > 0.4 * n_rec, (thr_bsj, n_rec)
     monkeypatch.setenv("CG_EMU_NO_PRE", "1")
     R = _pipeline(world, r1, r2, 1)
-    assert int(R.emu["tsm"][36]) > 0.6 * n_mates
-
-
-@pytest.mark.parametrize("step", [False, True])
-def test_pipeline_state_machine_forms(world, step, monkeypatch):
-    """The state-machine tier in its two expansions: sequential (chain kernels) and resumable, one round at a time."""
-    if step:
-        monkeypatch.setenv("CG_EMU_TSM_STEP", "1")
-    monkeypatch.setenv("CG_EMU_NO_PRE", "1")          # let every mate reach it
-    monkeypatch.setenv("CG_EMU_NO_THR", "1")
-    T = world[0]
-    r1, r2 = make_reads(T, 411, 4000)
-    _pipeline(world, r1, r2, 0)
+    assert int(R.emu["tiers"][1]) > 0.6 * n_mates
 
 
 @pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0), (250, 0), (33, 0)])

@@ -111,20 +111,6 @@ def test_pipeline_parity_tier_subsets(gpu_world, off, monkeypatch):
         assert 0 < B.n_tier2_wt < 0.3 * 2 * r1.shape[0] and 0 < B.n_tier2_bsj < 0.4 * B.n_export
 
 
-@pytest.mark.parametrize("L", [100, 150])
-def test_pipeline_parity_state_machine_tier(gpu_world, L, monkeypatch):
-    """The experimental first tier (block-sorted state machine, cg_tsm.cuh; CG_TSM=1) in front of the warp kernels:
-    same outputs, and it must actually have handled most reads."""
-    cg, T, otx, obsj, gtx, gbsj = gpu_world
-    monkeypatch.setenv("CG_TSM", "1")
-    r1, r2 = make_reads(T, 300 + L, 20000, L=L, frag_mean=2.4 * L, frag_sd=0.3 * L)
-    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, 0)
-    assert 0 < B.n_tier2_wt < 0.5 * 2 * r1.shape[0] and 0 < B.n_tier2_bsj < 0.6 * B.n_export
-    r1, r2 = make_reads(T, 78, 6000, n_rate=0.01)
-    a, b = ragged(r1, r2, 4)
-    _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, a, b)
-
-
 def test_pipeline_ragged_and_edge_reads(gpu_world):
     cg, T, otx, obsj, gtx, gbsj = gpu_world
     r1, r2 = make_reads(T, 77, 6000, n_rate=0.01)
