@@ -124,6 +124,12 @@ struct IndexView {
     int k;
     uint64_t km;              // kmask(k)
     uint64_t km3;             // kmask(k) / 3: a homopolymer word is (w & 3) * km3
+    // Seed filter (null / 0 = none): one bit per fm-mer code, set when the fm-mer or its reverse complement occurs '$'-free
+    // in the text.  Every k-mer of the table is a '$'-free substring of the text, so a read window that contains an fm-mer
+    // whose bit is clear — and its reverse complement, the set being closed under it — is certainly not in the table: one
+    // random access settles the k - fm + 1 windows that contain the probed fm-mer (cg_thr.cuh::q_walk).
+    const uint32_t* fbits;
+    int fm;
 };
 
 struct TB { uint64_t c0, c1, mask; uint32_t tid0, start0; };
@@ -309,9 +315,8 @@ CG_HD void make_block(const unsigned char* s, int nv, uint64_t& c0, uint64_t& c1
         else { mask |= 1ULL << i; if (c != 5) bad = true; }
     }
 }
-// k-mer word of text[p, p+k); false when the window holds a '$' or runs past the text
-CG_HD bool text_kmer(const IndexView& ix, uint32_t p, uint64_t& w) {
-    const int k = ix.k;
+// word of text[p, p+k); false when the window holds a '$' or runs past the text
+CG_HD bool text_word(const IndexView& ix, uint32_t p, int k, uint64_t& w) {
     if ((uint64_t)p + (uint64_t)k > (uint64_t)ix.n) return false;
     w = 0;
     int i = 0;
@@ -329,6 +334,19 @@ CG_HD bool text_kmer(const IndexView& ix, uint32_t p, uint64_t& w) {
     }
     return true;
 }
+
+CG_HD bool text_kmer(const IndexView& ix, uint32_t p, uint64_t& w) { return text_word(ix, p, ix.k, w); }
+
+// seed filter: m-mer codes are 2 m bits (m <= 16), base j at bits 2j like the k-mer words
+CG_HD uint32_t fm_mask(int m) { return m >= 16 ? 0xffffffffu : ((1u << (2 * m)) - 1u); }
+CG_HD uint32_t fm_revcomp(uint32_t x, int m) {
+    uint32_t r = brev32(x);
+    r = ~(((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1));
+    return r >> (32 - 2 * m);
+}
+CG_HD bool fm_homopolymer(uint32_t x, int m) { return x == (x & 3u) * (fm_mask(m) / 3u); }
+// m of an index with k-mers of k bases: 16 (a 512 MB bit set) when that leaves the 3-probe stage of the walk inside 64 windows
+CG_HD int fm_for_k(int k, int want) { return (want >= 8 && want <= 16 && want < k && 3 * (k - want) + 1 < 64) ? want : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // k-mer table probe

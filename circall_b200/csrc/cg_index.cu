@@ -22,6 +22,8 @@
 #include <fstream>
 #include <random>
 #include <sys/stat.h>
+#include <cerrno>
+#include <stdexcept>
 
 using namespace cg;
 using cgi::DevBuf;
@@ -235,6 +237,32 @@ int build_khash(cg_index* idx) {
     return CG_OK;
 }
 
+// seed filter (cg_core.cuh: IndexView::fbits): one thread per text position
+__global__ void __launch_bounds__(256)
+k_fbits(IndexView ix, int fm, uint32_t* __restrict__ bits) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= ix.n) return;
+    uint64_t w;
+    if (!text_word(ix, (uint32_t)p, fm, w)) return;
+    const uint32_t x = (uint32_t)w, y = fm_revcomp(x, fm);
+    if (!((bits[x >> 5] >> (x & 31)) & 1u)) atomicOr(&bits[x >> 5], 1u << (x & 31));
+    if (!((bits[y >> 5] >> (y & 31)) & 1u)) atomicOr(&bits[y >> 5], 1u << (y & 31));
+}
+int build_fbits(cg_index* idx) {
+    int want = 16;
+    if (const char* e = getenv("CG_FM")) want = atoi(e);
+    idx->fm = fm_for_k(idx->k, want);
+    if (!idx->fm) return CG_OK;
+    const uint64_t words = (1ULL << (2 * idx->fm)) / 32;
+    CG_CUDA(cudaMalloc((void**)&idx->d_fbits, words * 4));
+    CG_CUDA(cudaMemset(idx->d_fbits, 0, words * 4));
+    IndexView v = idx->view();
+    k_fbits<<<grid_for(idx->n, 256), 256>>>(v, idx->fm, idx->d_fbits);
+    CG_CUDA(cudaGetLastError());
+    CG_CUDA(cudaDeviceSynchronize());
+    return CG_OK;
+}
+
 int check_device(int device) {
     int nd = 0;
     cudaError_t e = cudaGetDeviceCount(&nd);
@@ -250,11 +278,13 @@ void free_index_device(cg_index* idx) {
     if (idx->d_sa) cudaFree(idx->d_sa);
     if (idx->d_hslots) cudaFree(idx->d_hslots);
     if (idx->d_offsets) cudaFree(idx->d_offsets);
+    if (idx->d_fbits) cudaFree(idx->d_fbits);
+    idx->d_fbits = nullptr;
     idx->d_text = nullptr; idx->d_sa = nullptr; idx->d_hslots = nullptr; idx->d_offsets = nullptr;
 }
 
 void finish_sizes(cg_index* idx) {
-    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4;
+    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4 + (idx->d_fbits ? (1ULL << (2 * idx->fm)) / 8 : 0);
 }
 
 int build_impl(int device, const char* text, uint64_t n, int k, const std::vector<std::string>* names, cg_index** out) {
@@ -317,6 +347,8 @@ int build_impl(int device, const char* text, uint64_t n, int k, const std::vecto
     ascii.alloc(0);
     rc = build_khash(idx);
     if (rc) return fail(rc);
+    rc = build_fbits(idx);
+    if (rc) return fail(rc);
 #undef CG_TRY
     finish_sizes(idx);
     idx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -361,11 +393,12 @@ int load_dev(const std::string& path, void** d, uint64_t bytes) {
 extern "C" {
 
 int cg_index_build(int device, const char* text, uint64_t n, int k, cg_index** out) {
-    return build_impl(device, text, n, k, nullptr, out);
+    try { return build_impl(device, text, n, k, nullptr, out); }
+    catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index build failed: ") + e.what()); }
+    catch (...) { CG_FAIL(CG_ERR_IO, "index build failed"); }
 }
 
-int cg_index_build_fasta(int device, const char* fasta_path, int k, cg_index** out) {
-    if (!fasta_path || !out) CG_FAIL(CG_ERR_ARG, "null argument");
+static int index_build_fasta_impl(int device, const char* fasta_path, int k, cg_index** out) {
     std::ifstream in(fasta_path);
     if (!in) CG_FAIL(CG_ERR_IO, std::string("cannot open ") + fasta_path);
     // RapMap record normalisation: name up to the first whitespace, upper case, non-ACGT ->
@@ -406,12 +439,24 @@ int cg_index_build_fasta(int device, const char* fasta_path, int k, cg_index** o
     if (text.empty()) CG_FAIL(CG_ERR_IO, "no usable record in FASTA file");
     return build_impl(device, text.data(), text.size(), k, &names, out);
 }
+int cg_index_build_fasta(int device, const char* fasta_path, int k, cg_index** out) {
+    if (!fasta_path || !out) CG_FAIL(CG_ERR_ARG, "null argument");
+    try { return index_build_fasta_impl(device, fasta_path, k, out); }
+    catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index build failed: ") + e.what()); }
+    catch (...) { CG_FAIL(CG_ERR_IO, "index build failed"); }
+}
 
+static int index_save_impl(const cg_index* idx, const char* dir);
 int cg_index_save(const cg_index* idx, const char* dir) {
     if (!idx || !dir) CG_FAIL(CG_ERR_ARG, "null argument");
+    try { return index_save_impl(idx, dir); }
+    catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index save failed: ") + e.what()); }
+    catch (...) { CG_FAIL(CG_ERR_IO, "index save failed"); }
+}
+static int index_save_impl(const cg_index* idx, const char* dir) {
     CG_CUDA(cudaSetDevice(idx->device));
     std::string d(dir);
-    mkdir(d.c_str(), 0777);
+    if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) CG_FAIL(CG_ERR_IO, "cannot create directory " + d);
     uint64_t meta[8] = {0x3130305844494743ULL /* "CGIDX001" */, (uint64_t)idx->k, idx->n, idx->n_tx, idx->n_kmers, idx->hcap, idx->n_blocks, 0};
     if (!write_file(d + "/meta.bin", meta, sizeof meta)) CG_FAIL(CG_ERR_IO, "cannot write " + d + "/meta.bin");
     if (!write_file(d + "/offsets.bin", idx->offsets.data(), idx->offsets.size() * 4)) CG_FAIL(CG_ERR_IO, "cannot write offsets.bin");
@@ -434,20 +479,39 @@ int cg_index_save(const cg_index* idx, const char* dir) {
     return CG_OK;
 }
 
-int cg_index_open(const char* dir, int device, cg_index** out) {
-    if (!dir || !out) CG_FAIL(CG_ERR_ARG, "null argument");
+static bool file_size_is(const std::string& path, uint64_t bytes) {
+    struct stat st;
+    return stat(path.c_str(), &st) == 0 && (uint64_t)st.st_size == bytes;
+}
+
+static int index_open_impl(const char* dir, int device, cg_index** out) {
     std::string d(dir);
     uint64_t meta[8];
-    if (!read_file(d + "/meta.bin", meta, sizeof meta) || meta[0] != 0x3130305844494743ULL)
+    if (!file_size_is(d + "/meta.bin", sizeof meta) || !read_file(d + "/meta.bin", meta, sizeof meta) || meta[0] != 0x3130305844494743ULL)
         CG_FAIL(CG_ERR_IO, "not a circall_b200 index directory: " + d);
+    // nothing in meta.bin is trusted: every field is checked against the others and against the files' sizes before anything is
+    // allocated or indexed with it
+    const uint64_t k = meta[1], n = meta[2], n_tx = meta[3], n_kmers = meta[4], hcap = meta[5], n_blocks = meta[6];
+    if (k < 3 || k > 31 || (k & 1) == 0) CG_FAIL(CG_ERR_IO, "meta.bin: k must be odd and <= 31");
+    if (n == 0 || n >= (1ULL << 31) - 128) CG_FAIL(CG_ERR_IO, "meta.bin: text length out of range");
+    if (n_tx == 0 || n_tx > n) CG_FAIL(CG_ERR_IO, "meta.bin: transcript count out of range");
+    if (n_blocks != (n + 63) / 64 + 1) CG_FAIL(CG_ERR_IO, "meta.bin: text block count does not match the text length");
+    if (hcap < 16 || (hcap & (hcap - 1)) != 0 || hcap > (1ULL << 36) || n_kmers >= hcap) CG_FAIL(CG_ERR_IO, "meta.bin: table capacity must be a power of two above the k-mer count");
+    if (!file_size_is(d + "/offsets.bin", (n_tx + 1) * 4)) CG_FAIL(CG_ERR_IO, "offsets.bin has the wrong size");
+    if (!file_size_is(d + "/text.bin", n_blocks * 32)) CG_FAIL(CG_ERR_IO, "text.bin has the wrong size");
+    if (!file_size_is(d + "/sa.bin", n * 4)) CG_FAIL(CG_ERR_IO, "sa.bin has the wrong size");
+    if (!file_size_is(d + "/hash.bin", hcap * 16)) CG_FAIL(CG_ERR_IO, "hash.bin has the wrong size");
     int rc = check_device(device);
     if (rc) return rc;
     cg_index* idx = new cg_index();
-    idx->device = device; idx->k = (int)meta[1]; idx->n = meta[2]; idx->n_tx = (uint32_t)meta[3];
-    idx->n_kmers = meta[4]; idx->hcap = meta[5]; idx->n_blocks = meta[6];
-    idx->offsets.resize((size_t)idx->n_tx + 1);
+    idx->device = device; idx->k = (int)k; idx->n = n; idx->n_tx = (uint32_t)n_tx;
+    idx->n_kmers = n_kmers; idx->hcap = hcap; idx->n_blocks = n_blocks;
     auto fail = [&](int code) { free_index_device(idx); delete idx; return code; };
+    idx->offsets.resize((size_t)idx->n_tx + 1);
     if (!read_file(d + "/offsets.bin", idx->offsets.data(), idx->offsets.size() * 4)) { cgi::set_error("cannot read offsets.bin"); return fail(CG_ERR_IO); }
+    if (idx->offsets[0] != 0 || idx->offsets[idx->n_tx] != n) { cgi::set_error("offsets.bin: first / last offset do not match the text"); return fail(CG_ERR_IO); }
+    for (uint32_t t = 0; t < idx->n_tx; ++t)
+        if (idx->offsets[t + 1] <= idx->offsets[t]) { cgi::set_error("offsets.bin: offsets must increase"); return fail(CG_ERR_IO); }
     {
         std::ifstream in(d + "/names.txt");
         std::string s;
@@ -460,9 +524,17 @@ int cg_index_open(const char* dir, int device, cg_index** out) {
     cudaError_t e = cudaMalloc((void**)&idx->d_offsets, idx->offsets.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(idx->d_offsets, idx->offsets.data(), idx->offsets.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(cgi::cuda_fail(e, "upload offsets", __FILE__, __LINE__));
+    if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter is derived from the text: not part of the directory
     finish_sizes(idx);
     *out = idx;
     return CG_OK;
+}
+
+int cg_index_open(const char* dir, int device, cg_index** out) {
+    if (!dir || !out) CG_FAIL(CG_ERR_ARG, "null argument");
+    try { return index_open_impl(dir, device, out); }
+    catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index open failed: ") + e.what()); }
+    catch (...) { CG_FAIL(CG_ERR_IO, "index open failed"); }
 }
 
 void cg_index_close(cg_index* idx) {

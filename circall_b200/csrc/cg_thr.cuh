@@ -157,62 +157,91 @@ CG_HDN u32x4 q_resolve_from(const u32x4* hslots, uint64_t hmask, uint64_t key, u
 }
 
 // The position walk (:112-132 with both = true: k-mer and reverse complement, a position counts when either is there;
-// :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s, QW look-ups per round.
+// :234-261 / :341-372 after a mismatch with both = false): positions o .. lim of strand s.
 // Returns the first position that hits (F: the k-mer's own look-up, hasR: its reverse complement's, both only) or -1;
 // homo is set when a looked-up window is a homopolymer (the caller declines).
+//
+// A walk runs over windows that are NOT in the table — the 31 windows that cover a substitution, the stretch of a read that
+// lies outside every BSJ reference — and each of them used to cost one random DRAM access (the table slot) to learn that.
+// With the index's seed filter (IndexView::fbits: which fm-mers occur in the text, fm = 16) a stage of the walk first looks up
+// Q_NP fm-mers of the read, S = k - fm positions apart, all in flight together: an fm-mer the text does not hold settles the
+// S + 1 windows that contain it (no k-mer of the table can contain it, nor can a reverse complement: the bit set is closed
+// under it), so three accesses answer 46 windows.  Only the windows left alive are looked up in the table, QW per round as
+// before.  Exactness: the filter only ever removes windows that are absent from the table, and a window it removes is not a
+// homopolymer (a homopolymer fm-mer is never used as evidence), so the positions visited, the first hit and the homopolymer
+// decline are those of the unfiltered walk.
+#if defined(CG_HOST_EMU)
+struct WalkStats { uint64_t filter_loads = 0, table_loads = 0, dead_windows = 0; };     // tests/emu: what the walks of a run cost
+static WalkStats g_walk;
+#define CG_WALK_STAT(f, n) (g_walk.f += (uint64_t)(n))
+#else
+#define CG_WALK_STAT(f, n) ((void)0)
+#endif
+static const int Q_NP = 3;        // seed-filter look-ups per stage (cg::fm_for_k keeps Q_NP * S + 1 below 64 windows)
 template <class M>
-CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
+CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
     const int k = ix.k;
     const int sh = both ? 1 : 0, per = QW >> sh;
+    const int fm = ix.fm, S = k - fm;
     F.f = false; F.b = F.e = 0; hasR = false;
     while (o <= lim) {
-        uint64_t key[QW]; u32x4 sl[QW]; uint32_t hs[QW];
-        // the (at most) QW windows of this round start within QW bases of each other: they are cut out of four words of the
-        // strand read once, instead of three scratch loads per window
-        const int wb = (s ? 2 * m.W2 : 0) + (o >> 4), sh0 = (o & 15) * 2;
-        const uint32_t w0 = m.ld(wb), w1 = m.ld(wb + 1), w2 = m.ld(wb + 2), w3 = m.ld(wb + 3);
+        // ---- filter stage: dead bit j = window o0 + j is certainly not in the table
+        const int o0 = o;
+        uint64_t dead = 0;
+        int hi = lim;
+        if (fm) {
+            const uint32_t fmk = fm_mask(fm);
+            uint32_t x[Q_NP], wv[Q_NP];
 #pragma unroll
-        for (int i = 0; i < QW; ++i) {
-            const int j = i >> sh;                                             // position o + j
-            const bool in = o + j <= lim;
-            const int bit = sh0 + 2 * j, hi = bit >> 5, sf = bit & 31;         // bit < 46: the window starts in word 0 or 1
-            const uint32_t a = hi ? w1 : w0, b = hi ? w2 : w1, c = hi ? w3 : w2;
-            const uint64_t mer = ((uint64_t)cgt::fsr(a, b, sf) | ((uint64_t)cgt::fsr(b, c, sf) << 32)) & ix.km;
-            if (!(both && (i & 1))) homo |= in && homopolymer_ix(mer, ix);
-            key[i] = (both && (i & 1)) ? revcomp(mer, k) : mer;
-            hs[i] = (uint32_t)home_slot(ix, key[i]);                           // (a table has fewer than 2^32 slots)
-            sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;            // an empty slot: not found
-            if (in) sl[i] = CG_LDG(&ix.hslots[hs[i]]);
-        }
-        if (homo) return -1;
-        // Resolve all of them together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
-        // of the look-ups; the odd slot of the same sector (an L1 hit) settles almost all of those.  Both steps are
-        // straight-line code for the whole warp; only what is still open afterwards takes the generic probe loop.
-        uint32_t fb = 0, pend = 0;
-#pragma unroll
-        for (int i = 0; i < QW; ++i) {
-            const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
-            if (kk == key[i]) fb |= 1u << i;
-            else if (kk != ~0ULL) pend |= 1u << i;
-        }
-        if (pend) {
-#pragma unroll
-            for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
-#pragma unroll
-            for (int i = 0; i < QW; ++i) {
-                if ((pend >> i) & 1u) {
-                    const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
-                    if (kk == key[i]) { fb |= 1u << i; pend &= ~(1u << i); }
-                    else if (kk == ~0ULL) pend &= ~(1u << i);
+            for (int j = 0; j < Q_NP; ++j) {
+                const int p = o0 + S * (j + 1);                                // this fm-mer lies inside the windows o0 + S j .. p
+                x[j] = 0; wv[j] = 0xffffffffu;
+                if (p + fm <= L && o0 + S * j <= lim) {
+                    const int wb = (s ? 2 * m.W2 : 0) + (p >> 4);
+                    x[j] = cgt::fsr(m.ld(wb), m.ld(wb + 1), (p & 15) * 2) & fmk;
+                    if (!fm_homopolymer(x[j], fm)) { wv[j] = CG_LDG(&ix.fbits[x[j] >> 5]); CG_WALK_STAT(filter_loads, 1); }
                 }
             }
-            // both slots of the home sector taken by other k-mers (up to 9 % of the look-ups at this table's load): the two slots
-            // of the next sector, again for all look-ups together — one lane at a time in the probe loop this was 16 % of the
-            // kernel's time — and the loop only for what is left after that
-#pragma unroll 1
-            for (int step = 2; step < 4 && pend; ++step) {
 #pragma unroll
-                for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[((uint64_t)hs[i] + step) & ix.hmask]);
+            for (int j = 0; j < Q_NP; ++j) if (!((wv[j] >> (x[j] & 31)) & 1u)) dead |= ((2ULL << S) - 1ULL) << (S * j);
+            hi = cmin(lim, o0 + Q_NP * S);
+        }
+        // ---- table stage over the windows of [o0, hi] that are still alive
+        while (o <= hi) {
+            const uint64_t dm = dead >> (o - o0);
+            if (dm & 1ULL) { const int sk = ctz64(~dm); CG_WALK_STAT(dead_windows, cmin(sk, hi - o + 1)); o += sk; continue; }
+            uint64_t key[QW]; u32x4 sl[QW]; uint32_t hs[QW];
+            // the (at most) QW windows of this round start within QW bases of each other: they are cut out of four words of the
+            // strand read once, instead of three scratch loads per window
+            const int wb = (s ? 2 * m.W2 : 0) + (o >> 4), sh0 = (o & 15) * 2;
+            const uint32_t w0 = m.ld(wb), w1 = m.ld(wb + 1), w2 = m.ld(wb + 2), w3 = m.ld(wb + 3);
+#pragma unroll
+            for (int i = 0; i < QW; ++i) {
+                const int j = i >> sh;                                             // position o + j
+                const bool in = o + j <= lim && !((dm >> j) & 1ULL);
+                const int bit = sh0 + 2 * j, hi5 = bit >> 5, sf = bit & 31;        // bit < 46: the window starts in word 0 or 1
+                const uint32_t a = hi5 ? w1 : w0, b = hi5 ? w2 : w1, c = hi5 ? w3 : w2;
+                const uint64_t mer = ((uint64_t)cgt::fsr(a, b, sf) | ((uint64_t)cgt::fsr(b, c, sf) << 32)) & ix.km;
+                if (!(both && (i & 1))) homo |= in && homopolymer_ix(mer, ix);
+                key[i] = (both && (i & 1)) ? revcomp(mer, k) : mer;
+                hs[i] = (uint32_t)home_slot(ix, key[i]);                           // (a table has fewer than 2^32 slots)
+                sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;            // an empty slot: not found
+                if (in) { sl[i] = CG_LDG(&ix.hslots[hs[i]]); CG_WALK_STAT(table_loads, 1); }
+            }
+            if (homo) return -1;
+            // Resolve all of them together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
+            // of the look-ups; the odd slot of the same sector (an L1 hit) settles almost all of those.  Both steps are
+            // straight-line code for the whole warp; only what is still open afterwards takes the generic probe loop.
+            uint32_t fb = 0, pend = 0;
+#pragma unroll
+            for (int i = 0; i < QW; ++i) {
+                const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
+                if (kk == key[i]) fb |= 1u << i;
+                else if (kk != ~0ULL) pend |= 1u << i;
+            }
+            if (pend) {
+#pragma unroll
+                for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
 #pragma unroll
                 for (int i = 0; i < QW; ++i) {
                     if ((pend >> i) & 1u) {
@@ -221,27 +250,43 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int s, int o, int lim, bool bo
                         else if (kk == ~0ULL) pend &= ~(1u << i);
                     }
                 }
-            }
-            if (pend) {
+                // both slots of the home sector taken by other k-mers (up to 9 % of the look-ups at this table's load): the two slots
+                // of the next sector, again for all look-ups together — one lane at a time in the probe loop this was 16 % of the
+                // kernel's time — and the loop only for what is left after that
+#pragma unroll 1
+                for (int step = 2; step < 4 && pend; ++step) {
 #pragma unroll
-                for (int i = 0; i < QW; ++i) {
-                    if ((pend >> i) & 1u) {
-                        const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 4) & ix.hmask);
-                        if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
+                    for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[((uint64_t)hs[i] + step) & ix.hmask]);
+#pragma unroll
+                    for (int i = 0; i < QW; ++i) {
+                        if ((pend >> i) & 1u) {
+                            const uint64_t kk = (uint64_t)sl[i].x | ((uint64_t)sl[i].y << 32);
+                            if (kk == key[i]) { fb |= 1u << i; pend &= ~(1u << i); }
+                            else if (kk == ~0ULL) pend &= ~(1u << i);
+                        }
+                    }
+                }
+                if (pend) {
+#pragma unroll
+                    for (int i = 0; i < QW; ++i) {
+                        if ((pend >> i) & 1u) {
+                            const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 4) & ix.hmask);
+                            if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
+                        }
                     }
                 }
             }
-        }
-        // the first position that hits; sl[i].z / .w are the interval of look-up i when it was found
-        int pos = -1;
+            // the first position that hits; sl[i].z / .w are the interval of look-up i when it was found
+            int pos = -1;
 #pragma unroll
-        for (int i = QW - 1; i >= 0; --i) {
-            if (both) {
-                if (!(i & 1) && ((fb >> i) & 3u)) { pos = o + (i >> 1); F.f = (fb >> i) & 1u; F.b = sl[i].z; F.e = sl[i].w; hasR = (fb >> (i + 1)) & 1u; }
-            } else if ((fb >> i) & 1u) { pos = o + i; F.f = true; F.b = sl[i].z; F.e = sl[i].w; }
+            for (int i = QW - 1; i >= 0; --i) {
+                if (both) {
+                    if (!(i & 1) && ((fb >> i) & 3u)) { pos = o + (i >> 1); F.f = (fb >> i) & 1u; F.b = sl[i].z; F.e = sl[i].w; hasR = (fb >> (i + 1)) & 1u; }
+                } else if ((fb >> i) & 1u) { pos = o + i; F.f = true; F.b = sl[i].z; F.e = sl[i].w; }
+            }
+            if (pos >= 0) return pos;
+            o += per;
         }
-        if (pos >= 0) return pos;
-        o += per;
     }
     return -1;
 }
@@ -298,7 +343,7 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
         }
         if (walk) {
             bool hasR = false;
-            pos = q_walk(ix, m, s, o, wlim, phaseA, hit, hasR, homo);
+            pos = q_walk(ix, m, L, s, o, wlim, phaseA, hit, hasR, homo);
             if (homo) return QD_HOMO;
             if (pos >= 0) {
                 if (phaseA) other = hasR;

@@ -44,6 +44,9 @@ def _lib():
         L.emu_run_tiers.argtypes = [vp, vp]
         L.emu_run_fill.argtypes = [vp] * 12
         L.emu_stdsort.argtypes = [vp, i32]
+        L.emu_index_fm.restype = i32
+        L.emu_index_fm.argtypes = [vp]
+        L.emu_walk_stats.argtypes = [vp, i32]
         _LIB = L
     return _LIB
 
@@ -54,6 +57,7 @@ class EmuIndex:
         sa = np.ascontiguousarray(sa, np.int32)
         self._h = _lib().emu_index_create(text.ctypes.data, text.size, sa.ctypes.data, k)
         self.n_kmers = _lib().emu_index_num_kmers(self._h)
+        self.fm = _lib().emu_index_fm(self._h)
 
     def __del__(self):
         try:
@@ -109,6 +113,13 @@ def run(tx, bsj, r1, off1, r2, off2, lce_mode=0):
         return out
     finally:
         L.emu_run_free(h)
+
+
+def walk_stats(reset=True):
+    """(seed-filter look-ups, table look-ups, windows the filter settled) of the lockstep tier's walks since the last reset."""
+    a = np.zeros(3, np.uint64)
+    _lib().emu_walk_stats(a.ctypes.data, int(reset))
+    return tuple(int(x) for x in a)
 
 
 def stdsort(a):

@@ -22,7 +22,7 @@ using namespace cg;
 
 struct EmuIndex {
     std::vector<u32x4> text, hslots;
-    std::vector<uint32_t> sa, offsets;
+    std::vector<uint32_t> sa, offsets, fbits;
     IndexView v;
     uint64_t n_kmers = 0;
 };
@@ -135,6 +135,22 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
     E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
     E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0; E->v.hshift = 0;
     E->v.km = kmask(k); E->v.km3 = E->v.km / 3;
+    E->v.fbits = nullptr; E->v.fm = 0;
+    {   // seed filter, as cg_index.cu::build_fbits makes it: every '$'-free fm-mer of the text and its reverse complement
+        int want = 16;
+        if (const char* e = getenv("CG_FM")) want = atoi(e);
+        const int fm = fm_for_k(k, want);
+        if (fm) {
+            E->fbits.assign((size_t)((1ULL << (2 * fm)) / 32), 0u);
+            for (uint64_t p = 0; p < n; ++p) {
+                uint64_t w;
+                if (!text_word(E->v, (uint32_t)p, fm, w)) continue;
+                const uint32_t x = (uint32_t)w, y = fm_revcomp(x, fm);
+                E->fbits[x >> 5] |= 1u << (x & 31); E->fbits[y >> 5] |= 1u << (y & 31);
+            }
+            E->v.fbits = E->fbits.data(); E->v.fm = fm;
+        }
+    }
     // k-mer table: heads of runs of equal valid k-mers in SA order
     std::vector<uint64_t> keys; std::vector<uint32_t> begins, endsI;
     bool have = false; uint64_t prev = 0;
@@ -334,6 +350,10 @@ void emu_run_fill(void* r, uint8_t* mateFlags, uint16_t* mateNHits, uint64_t* ex
 }
 
 void emu_thr_why(uint64_t* out, int reset) { memcpy(out, g_thr_why, sizeof g_thr_why); out[15] = g_thr_vote[0]; out[31] = g_thr_vote[1]; if (reset) { memset(g_thr_why, 0, sizeof g_thr_why); memset(g_thr_vote, 0, sizeof g_thr_vote); } }
+
+// seed filter of an index (0 = none) and what the lockstep tier's walks cost since the last reset: filter look-ups, table look-ups, windows the filter settled
+int emu_index_fm(void* h) { return ((EmuIndex*)h)->v.fm; }
+void emu_walk_stats(uint64_t* out, int reset) { out[0] = cgq::g_walk.filter_loads; out[1] = cgq::g_walk.table_loads; out[2] = cgq::g_walk.dead_windows; if (reset) cgq::g_walk = cgq::WalkStats(); }
 
 // std::sort replica check: sorts packed kmerScores entries with cg::StdSort
 void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort<true>(n); }

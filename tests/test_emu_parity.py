@@ -111,3 +111,26 @@ def test_pipeline_shipped_style_reads(world):
         off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
         out.append((np.concatenate([r[i, :lens[i]] for i in range(n)]), off))
     _pipeline(world, out[0], out[1])
+
+
+def test_seed_filter_exact_and_cheaper(small_world, monkeypatch):
+    """The lockstep tier's walks with the index's seed filter (cg_thr.cuh::q_walk; which fm-mers occur in the text) against the
+    same walks without it: the outputs are those of the oracle either way — the filter may only remove windows that are not in
+    the table — and with the filter the walks look up far fewer table slots (each one a random DRAM access on the device).
+    fm = 12 sets a sixth of its bits on this text instead of a few in ten thousand at 16: the "present" side of every branch runs too."""
+    T, otx, obsj = small_world
+    r1, r2 = T.reads(77, 6000, L=100, circ_frac=0.05)           # no N: every read reaches the thread tiers
+    cost = {}
+    for fm in (0, 12, 16):
+        monkeypatch.setenv("CG_FM", str(fm))
+        etx, ebsj = emu.EmuIndex(T.tx_text, otx.sa), emu.EmuIndex(T.bsj_text, obsj.sa)
+        assert etx.fm == fm and ebsj.fm == fm
+        emu.walk_stats()
+        _pipeline((T, otx, obsj, etx, ebsj), r1, r2, 0)
+        cost[fm] = emu.walk_stats()
+    assert cost[0][0] == 0 and cost[0][2] == 0
+    for fm in (12, 16):
+        filt, table, dead = cost[fm]
+        assert dead > 0 and filt > 0
+        assert filt + table < 0.5 * cost[0][1], cost              # random accesses of the walks: at least halved
+    assert cost[16][1] < 0.35 * cost[0][1], cost
