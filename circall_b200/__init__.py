@@ -49,7 +49,7 @@ class _CollectResult(ctypes.Structure):
 
 class _Opts(ctypes.Structure):
     _fields_ = [("lce_mode", ctypes.c_int), ("max_batch_pairs", ctypes.c_uint32), ("stage", ctypes.c_int),
-                ("keep_mate_detail", ctypes.c_int)]
+                ("keep_mate_detail", ctypes.c_int), ("dump_intervals", ctypes.c_int)]
 
 
 class _BatchResult(ctypes.Structure):
@@ -62,7 +62,9 @@ class _BatchResult(ctypes.Structure):
                 ("rec_nhits", ctypes.c_void_p), ("rec_split", ctypes.c_void_p),
                 ("device_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double * 4),
                 ("n_fallback_wt", ctypes.c_uint64), ("n_fallback_bsj", ctypes.c_uint64),
-                ("n_tier2_wt", ctypes.c_uint64), ("n_tier2_bsj", ctypes.c_uint64)]
+                ("n_tier2_wt", ctypes.c_uint64), ("n_tier2_bsj", ctypes.c_uint64),
+                ("wt_iv_head", ctypes.c_void_p), ("wt_iv_off", ctypes.c_void_p), ("wt_iv", ctypes.c_void_p), ("n_wt_iv", ctypes.c_uint64),
+                ("bsj_iv_head", ctypes.c_void_p), ("bsj_iv_off", ctypes.c_void_p), ("bsj_iv", ctypes.c_void_p), ("n_bsj_iv", ctypes.c_uint64)]
 
 
 class _Counters(ctypes.Structure):
@@ -293,6 +295,22 @@ class BatchResult:
         if detail:
             self.mate_flags = _view(r.mate_flags, np.uint8, 2 * r.n_pairs)
             self.mate_nhits = _view(r.mate_nhits, np.uint16, 2 * r.n_pairs)
+        # cg_opts::dump_intervals: (head, off, intervals[n, 4]) per Circall_wt mate / per Circall_bsj record
+        self.wt_iv = self.bsj_iv = None
+        if r.wt_iv_head:
+            self.wt_iv = (_view(r.wt_iv_head, np.uint32, 2 * r.n_pairs), _view(r.wt_iv_off, np.uint32, 2 * r.n_pairs),
+                          _view(r.wt_iv, np.int32, 4 * r.n_wt_iv).reshape(-1, 4))
+        if r.bsj_iv_head:
+            self.bsj_iv = (_view(r.bsj_iv_head, np.uint32, r.n_export), _view(r.bsj_iv_off, np.uint32, r.n_export),
+                           _view(r.bsj_iv, np.int32, 4 * r.n_bsj_iv).reshape(-1, 4))
+
+    @staticmethod
+    def intervals_of(iv, i):
+        """(found, tier, fwd[nF, 4], rc[nR, 4]) of item i of a dump_intervals triple; tier 0 = no tier recorded it."""
+        head, off, pool = iv
+        h, o = int(head[i]), int(off[i])
+        nF, nR, tier, found = h & 0xfff, (h >> 12) & 0xfff, (h >> 24) & 0xf, bool((h >> 28) & 1)
+        return found, tier, pool[o:o + nF], pool[o + nF:o + nF + nR]
 
     def eq_classes(self):
         """{sorted tid tuple -> count} of the multi-transcript classes of this batch."""
@@ -306,9 +324,9 @@ class BatchResult:
 class Session:
     """Circall_wt + Circall_bsj on batches of read pairs.  stage: 0 fused, 1 wt only, 2 bsj only."""
 
-    def __init__(self, tx, bsj, stage=0, lce_mode=0, keep_mate_detail=False):
+    def __init__(self, tx, bsj, stage=0, lce_mode=0, keep_mate_detail=False, dump_intervals=False):
         self.tx, self.bsj, self.stage, self.detail = tx, bsj, stage, keep_mate_detail
-        o = _Opts(lce_mode, 0, stage, int(keep_mate_detail))
+        o = _Opts(lce_mode, 0, stage, int(keep_mate_detail), int(dump_intervals))
         h = ctypes.c_void_p()
         _check(lib().cg_session_create(tx._h if tx else None, bsj._h if bsj else None, ctypes.byref(o), ctypes.byref(h)))
         self._h = h

@@ -87,6 +87,13 @@ CG_HD int ctz32(uint32_t x) {
     return __builtin_ctz(x);
 #endif
 }
+CG_HD int clz32(uint32_t x) {        // x != 0
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
+#endif
+}
 CG_HD int popc64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
     return __popcll(x);

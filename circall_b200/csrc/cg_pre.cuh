@@ -58,7 +58,10 @@ CG_HD int pre_match(const IndexView& ix, const cgt::TMem& m, int s, uint32_t p, 
 // m holds the forward strand; the reverse-complement strand is derived here when it is needed
 // cls (1..16) classifies a declined mate by which of the four k-mers are in the table (1 + f0 + 2 f1 + 4 f2 + 8 f3; 1 when it
 // never got to the look-ups): the lockstep tier sorts its work by it so that a warp holds reads that take the same path
-CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pairLen, uint8_t& flags, uint32_t& nh, uint8_t& cls) {
+// what the clean-match path implies for the collector's interval list (debug surface of the session, row A3): strand, the
+// full-length interval, the k-mer interval of the forced last position
+struct PreIv { int s; uint32_t lb, ub, bl, el; };
+CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pairLen, uint8_t& flags, uint32_t& nh, uint8_t& cls, PreIv* iv = nullptr) {
     const int k = ix.k;
     cls = 1;
     if (L < k + 1 || L > 0xffff) return false;
@@ -106,6 +109,9 @@ CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pair
     const bool full = L == pairLen || (pairLen == k && bl > 0 && el > bl && el - bl < 1000u);
     flags = (uint8_t)(MATE_SEEDED | (full ? MATE_FULL : 0));            // Circall_wt.cpp:311
     nh = n;
+    if (iv) {                                                           // the suffixes that share the longest prefix are contiguous
+        iv->s = s; iv->lb = b + (uint32_t)ctz32(fullB); iv->ub = b + 32u - (uint32_t)clz32(fullB); iv->bl = bl; iv->el = el;
+    }
     return true;
 }
 

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <cstddef>
 #include <cstdlib>
+#include <cstdio>
 
 using namespace cg;
 using namespace cgk;
@@ -55,6 +56,37 @@ struct BatchHdr {
     uint32_t n_t3_bsj;
     uint32_t n_cand;               // BSJ candidate records (Circall_bsj.cpp:390)
 };
+
+// ---- debug surface (cg_opts::dump_intervals): the post-vote interval lists of every collector call, as the tier that answered it
+// computed them — the row-A3 parity surface of the PRODUCTION tiers (tests compare them with the oracle's fwdSAInts / rcSAInts).
+// head[item] = nF | nR << 12 | tier << 24 | found << 28 (0 = never written), off[item] = first entry in the pool.
+struct IvDump { uint32_t* head; uint32_t* off; int4* pool; uint32_t* cursor; uint32_t cap; };
+enum { TIER_PRE = 1, TIER_THR = 2, TIER_THR_VOTE = 3, TIER_WARP = 4, TIER_GEN = 5 };
+__device__ __forceinline__ uint32_t iv_head(int nF, int nR, int tier, bool found) { return (uint32_t)nF | ((uint32_t)nR << 12) | ((uint32_t)tier << 24) | (found ? 1u << 28 : 0u); }
+// one thread writes the lists it keeps in its scratch
+template <class M>
+__device__ __noinline__ void iv_dump_thread(IvDump d, uint64_t item, int tier, bool found, M m, int nF, int nR) {
+    const uint32_t n = (uint32_t)(nF + nR), o = n ? atomicAdd(d.cursor, n) : 0u;
+    d.head[item] = iv_head(nF, nR, tier, found); d.off[item] = o;
+    if (o + n > d.cap) return;
+    for (int sx = 0; sx < 2; ++sx)
+        for (int i = 0; i < (sx ? nR : nF); ++i) {
+            const uint32_t lq = m.ld(m.iv(sx, i) + 2);
+            d.pool[o + (sx ? nF : 0) + i] = make_int4((int)m.ld(m.iv(sx, i)), (int)m.ld(m.iv(sx, i) + 1), (int)(lq & 0xffffu), (int)(lq >> 16));
+        }
+}
+// one warp writes the lists of its collector state
+__device__ __noinline__ void iv_dump_warp(IvDump d, uint64_t item, int tier, bool found, const Interval* fwd, int nF, const Interval* rc, int nR, int lane) {
+    const uint32_t n = (uint32_t)(nF + nR);
+    uint32_t o = 0;
+    if (lane == 0) { o = n ? atomicAdd(d.cursor, n) : 0u; d.head[item] = iv_head(nF, nR, tier, found); d.off[item] = o; }
+    o = __shfl_sync(0xffffffffu, o, 0);
+    if (o + n > d.cap) return;
+    for (int i = lane; i < (int)n; i += 32) {
+        const Interval& I = i < nF ? fwd[i] : rc[i - nF];
+        d.pool[o + i] = make_int4((int)I.begin, (int)I.end, (int)I.len, (int)I.qpos);
+    }
+}
 
 // ---- warp-per-read kernels --------------------------------------------------------------------------
 static const int WARPS_PER_BLOCK = 8;
@@ -131,7 +163,7 @@ template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
-          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
+          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump) {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, false) / 8);
@@ -144,6 +176,9 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
         int L = lens[r];
         int pairLen = lens[r & ~1ULL];             // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
         if ((CG_OPT_PF & 4) && !LIST && x + nwarps < n && lane * 4 < g.WT) cgw::prefetch_l2(pk + (x + nwarps) * (uint64_t)g.WT + lane * 4);   // this warp's next read
+#ifdef CG_WARP_PROF
+        const long long wp_read0 = clock64();
+#endif
         cgw::RV rv = warp_view(pk + r * (uint64_t)g.WT, g, L, mine, lane);
         bool found, ok; int nF, nR;
         const Interval* fwd; const Interval* rc;
@@ -164,6 +199,7 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
 #pragma unroll 1
             for (int i = lane; i < nR; i += 32) full |= ((int)rc[i].len == pairLen);
             if (__any_sync(cgw::FULL, full)) fl |= MATE_FULL;
+            WPROF_T0();
             if (GEN) {
                 uint32_t a = cgw::w_hits_list<0>(lane, fwd, nF, gp.scrA, gp.actA);
                 uint32_t b = cgw::w_hits_list<0>(lane, rc, nR, gp.scrB, gp.actB);
@@ -173,8 +209,16 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
                 ok = hF.ok && hR.ok;
                 if (ok) nh = warp_union_count(hF.tid, hF.alive, hR.tid, hR.alive);
             }
+            WPROF_ADD(cgw::WP_HITS, lane);
         }
+#ifdef CG_WARP_PROF
+        if (lane == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - wp_read0);
+            atomicAdd(&cgw::g_wprof[7], dt); atomicAdd(&cgw::g_wprof[8 + (GEN ? 1 : 0)], 1ULL); atomicAdd(&cgw::g_wprof[16 + (GEN ? 24 : 0) + (63 - __clzll(dt | 1ULL))], 1ULL);
+        }
+#endif
         if (lane == 0) { flags[r] = ok ? fl : MATE_ERR; nhits[r] = ok ? nh : 0; if (!GEN) ovf[r] = ok ? 0 : 1; }
+        if (dump.head && ok) iv_dump_warp(dump, r, GEN ? TIER_GEN : TIER_WARP, found, fwd, found ? nF : 0, rc, found ? nR : 0, lane);
     }
 }
 
@@ -383,7 +427,7 @@ template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
            const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
-           int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch) {
+           int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump) {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, true) / 8);
@@ -439,7 +483,13 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
                 }
             }
         }
-        if (!ok) { if (lane == 0) ovf[rec] = 1; continue; }
+        if (!ok) {
+            if (GEN) {          // the general collector ran out of its worst-case capacities: reported, never dropped (as k_wt_warp / k_wt_commit do)
+                if (lane == 0) { atomicOr(&o.hdr->status, ST_CAPACITY); o.rec_nhits[rec] = 0; o.rec_split[rec] = 0; }
+            } else if (lane == 0) ovf[rec] = 1;
+            continue;
+        }
+        if (dump.head) iv_dump_warp(dump, rec, GEN ? TIER_GEN : TIER_WARP, found, fwd, found ? nF : 0, rc, found ? nR : 0, lane);
         bool split = false;
         if (nh > 0) {                                                             // Circall_bsj.cpp:319
 #pragma unroll 1
@@ -516,7 +566,7 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
 static const int PRE_THREADS = CG_PRE_THREADS;
 __global__ void __launch_bounds__(PRE_THREADS)
 k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
-         uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf) {
+         uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, IvDump dump) {
     extern __shared__ uint32_t pre_smem[];
     const uint64_t r = (uint64_t)blockIdx.x * PRE_THREADS + threadIdx.x;
     if (r >= n_reads) return;
@@ -536,7 +586,21 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
     if (!anyN) {
         for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
         m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
-        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh, cls);
+        cgp::PreIv piv;
+        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh, cls, dump.head ? &piv : (cgp::PreIv*)nullptr);
+        if (done && dump.head) {
+            // the list this path stands for (cg_pre.cuh): the full-length interval, then the k-mer interval of the forced last position —
+            // twice on the forward strand (Phase B re-runs it after setting lastSearch, :300-321), once on the other (:412)
+            const int k = cgw::c_ix[0].k;
+            const bool lastOk = piv.el > piv.bl && piv.el - piv.bl < 1000u;
+            const int n = 1 + (lastOk ? (piv.s == 0 ? 2 : 1) : 0);
+            const uint32_t o = atomicAdd(dump.cursor, (uint32_t)n);
+            dump.head[r] = iv_head(piv.s == 0 ? n : 0, piv.s == 0 ? 0 : n, TIER_PRE, true); dump.off[r] = o;
+            if (o + n <= dump.cap) {
+                dump.pool[o] = make_int4((int)piv.lb, (int)piv.ub, L, 0);
+                for (int i = 1; i < n; ++i) dump.pool[o + i] = make_int4((int)piv.bl, (int)piv.el, k, L - k);
+            }
+        }
     }
     if (done) { flags[r] = fl; nhits[r] = nh; }
     ovf[r] = done ? 0 : cls;          // declined: the look-up class (1..16), see k_cls_*
@@ -572,7 +636,7 @@ template <bool VOTE>
 __global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
          const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
-         uint8_t* __restrict__ ovf) {
+         uint8_t* __restrict__ ovf, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : n_reads;
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -581,10 +645,11 @@ k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
     const uint64_t r = list ? (uint64_t)list[x] : x;
     const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
     cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
-    uint8_t fl = 0; uint32_t nh = 0; int why = 0;
-    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why);
+    uint8_t fl = 0; uint32_t nh = 0; int why = 0, nF = 0, nR = 0;
+    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why, nF, nR);
     if (done) { flags[r] = fl; nhits[r] = nh; }
     else ovf[r] = 1;
+    if (dump.head && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
 }
 
 // Circall_bsj: over the records list[..] (every exported record when list is null); ovf[rec] = 1 hands record rec to the warp
@@ -593,7 +658,7 @@ template <bool VOTE>
 __global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, BsjOut o, int do_counts,
-          uint8_t* __restrict__ ovf) {
+          uint8_t* __restrict__ ovf, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -606,8 +671,9 @@ k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
         const int L = lens[r];
         cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
         JSink sink; sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; sink.rec = (uint32_t)rec;
-        uint32_t nh = 0; bool split = false; int why = 0, at = 0;
-        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why);
+        uint32_t nh = 0; bool split = false; int why = 0, at = 0, nF = 0, nR = 0;
+        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why, nF, nR);
+        if (dump.head && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
         if (!done) ovf[rec] = 1;
         else {
             // commit (Circall_bsj.cpp:383-491)
@@ -695,6 +761,10 @@ struct cg_session {
     // device buffers
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
         d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3, d_exppair, d_expcode, d_cand;
+    GrowBuf d_ivhead_wt, d_ivoff_wt, d_ivpool_wt, d_ivhead_bsj, d_ivoff_bsj, d_ivpool_bsj, d_ivcur;   // cg_opts::dump_intervals
+    uint32_t iv_cap = 0;
+    PinVec<uint32_t> h_ivhead_wt, h_ivoff_wt, h_ivhead_bsj, h_ivoff_bsj;
+    PinVec<int4> h_ivpool_wt, h_ivpool_bsj;
     unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
@@ -755,6 +825,12 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     o.rec_nhits = s->d_recnh.as<uint32_t>(); o.rec_split = s->d_recsp.as<uint8_t>();
     o.per_bsj = s->d_acc; o.ctr = s->d_acc + s->n_bsj; o.hdr = s->d_hdr.as<BatchHdr>();
     const uint32_t* em = stage2 ? nullptr : s->d_exp.as<uint32_t>();
+    IvDump dbs; memset(&dbs, 0, sizeof dbs);
+    if (s->opts.dump_intervals && do_counts == 3) {          // (not on the redo pass of a batch whose row buffers were too small)
+        dbs.head = s->d_ivhead_bsj.as<uint32_t>(); dbs.off = s->d_ivoff_bsj.as<uint32_t>(); dbs.pool = s->d_ivpool_bsj.as<int4>();
+        dbs.cursor = s->d_ivcur.as<uint32_t>() + 1; dbs.cap = s->iv_cap;
+        CG_CUDA(cudaMemsetAsync(dbs.head, 0, worst * 4, s->stream));
+    }
     IndexView v = s->bsj->view();
     BatchHdr* dh = s->d_hdr.as<BatchHdr>();
     CG_CUDA(cudaMemsetAsync(s->d_ovf.p, 0, worst, s->stream));
@@ -776,11 +852,11 @@ int run_bsj_stage(cg_session* s, int do_counts) {
         const uint32_t* seg = (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(worst, CP_TILE));
         rc = launch(s, k_bsj_thr<false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>());
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
         if (rc) return rc;
         rc = launch(s, k_bsj_thr<true>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>());
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
         if (rc) return rc;
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
         if (rc) return rc;
@@ -791,17 +867,17 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     if (cur_list)
         rc = launch(s, k_bsj_warp<false, true>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, cur_list, cur_n,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs);
     else
         rc = launch(s, k_bsj_warp<false, false>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs);
     if (rc) return rc;
     rc = compact_flags(s, ovf_fast, worst, s->d_list2.as<uint32_t>(), &dh->n_ovf_bsj);
     if (rc) return rc;
     rc = launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
                 s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list2.as<uint32_t>(),
-                (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch);
+                (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch, dbs);
     if (rc) return rc;
     // the candidate list (records with a junction row and 1 .. maxReadOccs hits), in record order; d_ovf2 is free again
     rc = launch(s, k_cand_flag, dim3(grid_for(worst, 256)), dim3(256), 0, (const uint32_t*)o.rec_nhits, (const uint8_t*)o.rec_split,
@@ -844,6 +920,19 @@ int run_batch(cg_session* s) {
         if (s->eq_tids_cap < want_t) { CG_CUDA(s->d_eqtids.reserve(want_t * 4)); s->eq_tids_cap = want_t; }
     }
     CG_CUDA(cudaMemsetAsync(s->d_hdr.p, 0, sizeof(BatchHdr), s->stream));
+    IvDump dwt; memset(&dwt, 0, sizeof dwt);
+    if (s->opts.dump_intervals) {
+        s->iv_cap = (uint32_t)std::min<uint64_t>(0xfffffff0ull, 24 * n_reads + 4096);
+        CG_CUDA(s->d_ivcur.reserve(8));
+        CG_CUDA(cudaMemsetAsync(s->d_ivcur.p, 0, 8, s->stream));
+        if (stage != 2) {
+            CG_CUDA(s->d_ivhead_wt.reserve(n_reads * 4 + 4)); CG_CUDA(s->d_ivoff_wt.reserve(n_reads * 4 + 4)); CG_CUDA(s->d_ivpool_wt.reserve((uint64_t)s->iv_cap * 16));
+            dwt.head = s->d_ivhead_wt.as<uint32_t>(); dwt.off = s->d_ivoff_wt.as<uint32_t>(); dwt.pool = s->d_ivpool_wt.as<int4>();
+            dwt.cursor = s->d_ivcur.as<uint32_t>(); dwt.cap = s->iv_cap;
+            CG_CUDA(cudaMemsetAsync(dwt.head, 0, n_reads * 4 + 4, s->stream));
+        }
+        if (stage != 1) { CG_CUDA(s->d_ivhead_bsj.reserve(n_reads * 4 + 4)); CG_CUDA(s->d_ivoff_bsj.reserve(n_reads * 4 + 4)); CG_CUDA(s->d_ivpool_bsj.reserve((uint64_t)s->iv_cap * 16)); }
+    }
     CG_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
     // K1
@@ -863,7 +952,7 @@ int run_batch(cg_session* s) {
         const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;        // mates still to map (null: all of them)
         if (s->use_pre) {
             rc = launch(s, k_wt_pre, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
-                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>());
+                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), dwt);
             if (rc) return rc;
             // the front kernel leaves a look-up class per declined mate: the lockstep tier wants its work grouped by it
             rc = s->use_thr ? compact_classes(s, s->d_ovf.as<uint8_t>(), n_reads, s->d_list.as<uint32_t>(), &dh->n_t2_wt)
@@ -879,12 +968,12 @@ int run_batch(cg_session* s) {
             const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
             rc = launch(s, k_wt_thr<false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>());
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
             if (rc) return rc;
             if (sorted) {
                 rc = launch(s, k_wt_thr<true>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4,
                             s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>());
+                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
                 if (rc) return rc;
             }
             rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
@@ -896,17 +985,17 @@ int run_batch(cg_session* s) {
         if (cur_list)
             rc = launch(s, k_wt_warp<false, true>, dim3(s->warp_grid_wt), blk, smf,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt);
         else
             rc = launch(s, k_wt_warp<false, false>, dim3(s->warp_grid_wt), blk, smf,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr);
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt);
         if (rc) return rc;
         rc = compact_flags(s, ovf_fast, n_reads, s->d_list2.as<uint32_t>(), &dh->n_ovf_wt);
         if (rc) return rc;
         rc = launch(s, k_wt_warp<true, true>, dim3(s->gen_grid), blk, smg,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list2.as<uint32_t>(), (const uint32_t*)&dh->n_ovf_wt,
-                    s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch);
+                    s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch, dwt);
         if (rc) return rc;
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
         rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
@@ -1001,13 +1090,31 @@ void cg_session_destroy(cg_session* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+#ifdef CG_WARP_PROF
+    {
+        unsigned long long h[64];
+        if (cudaMemcpyFromSymbol(h, cgw::g_wprof, sizeof h) == cudaSuccess) {
+            fprintf(stderr, "WPROF (k_wt_warp, cycles of lane 0 summed over warps): look %llu extend %llu lce %llu vote %llu hits %llu | per-read total %llu reads fast %llu gen %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[7], h[8], h[9]);
+            fprintf(stderr, "WPROF reads by log2(cycles), fast kernel:");
+            for (int b = 8; b < 24; ++b) fprintf(stderr, " %d:%llu", b, h[16 + b]);
+            fprintf(stderr, "\nWPROF reads by log2(cycles), general kernel:");
+            for (int b = 8; b < 24; ++b) fprintf(stderr, " %d:%llu", b, h[40 + b]);
+            fprintf(stderr, "\n");
+            memset(h, 0, sizeof h);
+            cudaMemcpyToSymbol(cgw::g_wprof, h, sizeof h);
+        }
+    }
+#endif
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
-                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3, &s->d_exppair, &s->d_expcode, &s->d_cand})
+                       &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3, &s->d_exppair, &s->d_expcode, &s->d_cand,
+                       &s->d_ivhead_wt, &s->d_ivoff_wt, &s->d_ivpool_wt, &s->d_ivhead_bsj, &s->d_ivoff_bsj, &s->d_ivpool_bsj, &s->d_ivcur})
         b->release();
     s->h_hdr.release();
     s->h_exp_pair.release(); s->h_exp_code.release(); s->h_cand.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();
     s->h_mnhits.release(); s->h_junc.release(); s->h_eqent.release();
+    s->h_ivhead_wt.release(); s->h_ivoff_wt.release(); s->h_ivhead_bsj.release(); s->h_ivoff_bsj.release(); s->h_ivpool_wt.release(); s->h_ivpool_bsj.release();
     if (s->d_acc) cudaFree(s->d_acc);
     if (s->d_gscratch) cudaFree(s->d_gscratch);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1151,7 +1258,27 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
         if ((rc = d2h(s, s->h_eqent, s->d_eqent.p, hdr.n_eq))) return rc;
         if ((rc = d2h(s, s->h_eq_tids_raw, s->d_eqtids.p, hdr.n_eq_tids))) return rc;
     }
+    uint32_t ivn[2] = {0, 0};
+    if (s->opts.dump_intervals) {
+        CG_CUDA(cudaMemcpyAsync(ivn, s->d_ivcur.p, 8, cudaMemcpyDeviceToHost, s->stream));
+        CG_CUDA(cudaStreamSynchronize(s->stream));
+        if (ivn[0] > s->iv_cap || ivn[1] > s->iv_cap) CG_FAIL(CG_ERR_CAPACITY, "interval dump buffer too small for this batch");
+        if (stage != 2) {
+            if ((rc = d2h(s, s->h_ivhead_wt, s->d_ivhead_wt.p, 2 * s->n_pairs))) return rc;
+            if ((rc = d2h(s, s->h_ivoff_wt, s->d_ivoff_wt.p, 2 * s->n_pairs))) return rc;
+            if ((rc = d2h(s, s->h_ivpool_wt, s->d_ivpool_wt.p, ivn[0]))) return rc;
+        }
+        if (stage != 1) {
+            if ((rc = d2h(s, s->h_ivhead_bsj, s->d_ivhead_bsj.p, n_exp))) return rc;
+            if ((rc = d2h(s, s->h_ivoff_bsj, s->d_ivoff_bsj.p, n_exp))) return rc;
+            if ((rc = d2h(s, s->h_ivpool_bsj, s->d_ivpool_bsj.p, ivn[1]))) return rc;
+        }
+    }
     CG_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->opts.dump_intervals) {
+        if (stage != 2) { out->wt_iv_head = s->h_ivhead_wt.data(); out->wt_iv_off = s->h_ivoff_wt.data(); out->wt_iv = (const int32_t*)s->h_ivpool_wt.data(); out->n_wt_iv = ivn[0]; }
+        if (stage != 1) { out->bsj_iv_head = s->h_ivhead_bsj.data(); out->bsj_iv_off = s->h_ivoff_bsj.data(); out->bsj_iv = (const int32_t*)s->h_ivpool_bsj.data(); out->n_bsj_iv = ivn[1]; }
+    }
     out->exp_pair = s->h_exp_pair.data(); out->exp_code = s->h_exp_code.data();
     if (s->opts.keep_mate_detail && stage != 2) { out->mate_flags = s->h_mflags.data(); out->mate_nhits = s->h_mnhits.data(); }
     if (stage != 1) {

@@ -589,8 +589,7 @@ CG_HD int q_hits2(const IndexView& ix, const QMemT<VOTE>& m, int nF, int nR, int
 
 // one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517): false = declined
 template <bool VOTE>
-CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why) {
-    int nF, nR;
+CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why, int& nF, int& nR) {
     const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
     why = r;
     if (r < 0) return false;
@@ -611,8 +610,7 @@ CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairL
 // one record of Circall_bsj (src/Circall_bsj.cpp:300-399): false = declined (nothing was emitted).  On success the
 // hit transcripts are left in ascending order at tids_at (word index in the scratch), nh of them.
 template <bool VOTE, class Sink>
-CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why) {
-    int nF, nR;
+CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why, int& nF, int& nR) {
     const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
     why = r;
     tids_at = m.cb(0);

@@ -44,6 +44,18 @@ static const int W_LINEAR = CG_W_LINEAR;     // widest open interval the extensi
 
 __constant__ IndexView c_ix[2];          // [0] txIdx, [1] bsjIdx — written by the session before each stage
 
+// -DCG_WARP_PROF: cycles the warp-per-read kernels spend per phase (lane 0 of every warp adds its clock64() deltas), and a log2
+// histogram of the cycles per read; printed by cg_session_destroy.  Measurement build only (profiles/r2_experiments.md).
+#ifdef CG_WARP_PROF
+__device__ unsigned long long g_wprof[64];       // [0..7] phase cycles, [8] reads, [16 + b] reads whose cycles have bit length b
+enum { WP_LOOK = 0, WP_EXTEND, WP_LCE, WP_VOTE, WP_HITS, WP_REST };
+#define WPROF_T0() const long long _wp0 = clock64()
+#define WPROF_ADD(ph, lane) do { if ((lane) == 0) atomicAdd(&cgw::g_wprof[ph], (unsigned long long)(clock64() - _wp0)); } while (0)
+#else
+#define WPROF_T0() do {} while (0)
+#define WPROF_ADD(ph, lane) do {} while (0)
+#endif
+
 template <int FI, int FK>
 struct WStateT {
     Interval fwd[FI];
@@ -317,14 +329,14 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
     int rb = 0, q0 = 0;
     bool first = true;
     while (rb + k < L) {
-        Look lk = w_look<X>(rv, lane, 0, rb, L - k - 1, k1bits, true, first, true);  // :117-132
+        Look lk; { WPROF_T0(); lk = w_look<X>(rv, lane, 0, rb, L - k - 1, k1bits, true, first, true); WPROF_ADD(WP_LOOK, lane); }  // :117-132
         first = false;
         if (lk.pos < 0) { rb = lk.o_end; continue; }
         rb = lk.pos;
         const bool hasF = (lk.fb >> lk.jl) & 1, hasR = (lk.fb >> (lk.jl + 1)) & 1;
         if (hasF) {
             uint32_t b = __shfl_sync(FULL, lk.b, lk.jl), e = __shfl_sync(FULL, lk.e, lk.jl);
-            Ext x = w_extend<X>(rv, lane, 0, rb, b > 0 ? b - 1 : 0, e, k);           // :140-143
+            Ext x; { WPROF_T0(); x = w_extend<X>(rv, lane, 0, rb, b > 0 ? b - 1 : 0, e, k); WPROF_ADD(WP_EXTEND, lane); }           // :140-143
             lbF = x.lb; ubF = x.ub; matched = x.len;
             if (ubF > lbF && ubF - lbF < maxInterval) {                              // :149
                 W_PUSH_INT(st.fwd, nF, lbF, ubF, matched, rb);
@@ -351,7 +363,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
         if (s == 0) {
             if (!fwdHit) continue;
             int remaining = L - (q0 + matched);                                      // :219
-            int l = w_lce<X>(lbF, ubF - 1, matched, remaining, lceMode);             // :220
+            int l; { WPROF_T0(); l = w_lce<X>(lbF, ubF - 1, matched, remaining, lceMode); WPROF_ADD(WP_LCE, lane); }             // :220
             int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
             o = cmin(cmax(0, L - k), q0 + fwdSkip);                                  // :224-228
             expectAbsent = remaining > 0 && o < L - k;    // the match stopped on a mismatch: the next windows cover it
@@ -366,7 +378,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
             else {
                 // expected present: this k-mer and its reverse complement on lanes 0/1 (:261+:268 / :372+:379);
                 // after a mismatch: up to 32 positions at once
-                Look lk = w_look<X>(rv, lane, s, o, L - k, kbits, !expectAbsent, !expectAbsent, false);
+                Look lk; { WPROF_T0(); lk = w_look<X>(rv, lane, s, o, L - k, kbits, !expectAbsent, !expectAbsent, false); WPROF_ADD(WP_LOOK, lane); }
                 if (lk.pos < 0) { o = lk.o_end; expectAbsent = true; continue; }     // :324 / :436
                 o = lk.pos;
                 b = __shfl_sync(FULL, lk.b, lk.jl); e = __shfl_sync(FULL, lk.e, lk.jl);
@@ -378,7 +390,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
             int fpos = s == 0 ? o : L - (o + k);                                     // :366
             if (s == 0) { ++fwdHit; if (other) ++rcHit; W_PUSH_KS(fpos, 1, other ? 1 : 0); }
             else { ++rcHit; if (other) ++fwdHit; W_PUSH_KS(fpos, other ? 1 : 0, 1); }
-            Ext x = w_extend<X>(rv, lane, s, o, b > 0 ? b - 1 : 0, e, k);            // :279-280 / :392-393
+            Ext x; { WPROF_T0(); x = w_extend<X>(rv, lane, s, o, b > 0 ? b - 1 : 0, e, k); WPROF_ADD(WP_EXTEND, lane); }            // :279-280 / :392-393
             matched = x.len;
             if (x.ub > x.lb && x.ub - x.lb < maxInterval) {                          // :285 / :398
                 if (s == 0) W_PUSH_INT(st.fwd, nF, x.lb, x.ub, matched, o);
@@ -391,7 +403,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
             if (lastSearch) break;                                                   // :300 / :412
             int mismatch = o + matched;
             if (mismatch < L) {
-                int l = w_lce<X>(x.lb, x.ub - 1, matched, L - mismatch, lceMode);    // :304 / :416
+                int l; { WPROF_T0(); l = w_lce<X>(x.lb, x.ub - 1, matched, L - mismatch, lceMode); WPROF_ADD(WP_LCE, lane); }    // :304 / :416
                 o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
                 if (o > L - k) { o = L - k; lastSearch = true; }
                 else expectAbsent = true;
@@ -404,6 +416,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
     __syncwarp();
 
     // ---- strand vote (:442-490)
+    WPROF_T0();
     if (fwdHit > 0 && rcHit == 0) nR = 0;
     else if (rcHit > 0 && fwdHit == 0) nF = 0;
     else {
@@ -445,6 +458,7 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
         }
         if (fs > rs) nR = 0; else if (rs > fs) nF = 0;                               // :482-488
     }
+    WPROF_ADD(WP_VOTE, lane);
 #undef W_PUSH_KS
 #undef W_PUSH_INT
     return true;

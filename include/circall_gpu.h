@@ -118,6 +118,9 @@ typedef struct {
     int stage;                   /* 0 = wt then bsj (fused), 1 = wt only (bsj index may be NULL),
                                     2 = bsj only: mate 1 of every submitted pair is the record's read 1 */
     int keep_mate_detail;        /* also return per-mate flags / hit counts (parity tests) */
+    int dump_intervals;          /* debug surface of row A3: also return, for every collector call of the batch, the post-vote
+                                    fwdSAInts / rcSAInts (SACollectorCircall.hpp:442-490) as the tier that answered the read
+                                    computed them, and which tier that was (parity tests; costs time and memory) */
 } cg_opts;
 
 typedef struct { uint32_t rec; uint32_t dir; uint32_t query_pos; uint32_t len; int32_t hit_pos; uint32_t tid; } cg_junction;
@@ -143,6 +146,12 @@ typedef struct {
     double kernel_ms[4];         /* of which: read packing, wt collector, wt commit + export compaction, bsj collector + span filter */
     uint64_t n_fallback_wt, n_fallback_bsj;   /* mates / records that needed the large-capacity general kernels */
     uint64_t n_tier2_wt, n_tier2_bsj;         /* mates / records the thread-per-read first tier handed to the warp-per-read kernels */
+    /* cg_opts::dump_intervals (fetch with want_lists): per Circall_wt mate (2 per pair) / per Circall_bsj record
+     * head = nF | nR << 12 | tier << 24 | found << 28 (tier 1 clean-match kernel, 2 / 3 lockstep thread tier lean / two-strand,
+     * 4 / 5 warp kernels fast / general), off = index of the item's first interval in *_iv (4 int32 each: begin, end, len,
+     * queryPos; the nF forward ones first) */
+    const uint32_t* wt_iv_head; const uint32_t* wt_iv_off; const int32_t* wt_iv; uint64_t n_wt_iv;
+    const uint32_t* bsj_iv_head; const uint32_t* bsj_iv_off; const int32_t* bsj_iv; uint64_t n_bsj_iv;
 } cg_batch_result;
 
 /* scalar counters (ReadExperiment.hpp:265-270) for the two tools */

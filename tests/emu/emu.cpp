@@ -77,30 +77,30 @@ static bool both_class(const IndexView& ix, const std::vector<uint64_t>& pk, int
 static uint64_t g_thr_why[2][16];
 static uint64_t g_thr_vote[2];
 static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
-    int why = cgq::QD_N;
+    int why = cgq::QD_N, nF = 0, nR = 0;
     bool ok;
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
-        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why);
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR);
         if (ok) ++g_thr_vote[0];
     } else {
         cgq::QMemT<false> m;
-        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_wt_mate<false>(ix, m, L, pairLen, lceMode, fl, nh, why);
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_wt_mate<false>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR);
     }
     if (!ok) ++g_thr_why[0][(-why) & 15];
     return ok;
 }
 template <class Sink>
 static bool thr_bsj_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int lceMode, std::vector<uint32_t>& scratch, Sink& sink, uint32_t& nh, bool& split, uint32_t* tids) {
-    int why = cgq::QD_N, at = 0;
+    int why = cgq::QD_N, at = 0, nF = 0, nR = 0;
     bool ok;
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
-        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why);
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR);
         if (ok) { ++g_thr_vote[1]; for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t); }
     } else {
         cgq::QMemT<false> m;
-        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_bsj_record<false>(ix, m, L, lceMode, sink, nh, split, at, why);
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_bsj_record<false>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR);
         if (ok) for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t);
     }
     if (!ok) ++g_thr_why[1][(-why) & 15];

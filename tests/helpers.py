@@ -22,3 +22,39 @@ def ragged(r1, r2, seed):
         b = np.concatenate([r[i, :lens[i]] for i in range(n)]) if n else np.zeros(0, np.uint8)
         out.append((b, off))
     return out[0], out[1]
+
+
+def compare_tier_intervals(B, oidx_tx, oidx_bsj, r1, r2, lce_mode=0, wt_items=None, bsj_items=None):
+    """Row A3 on the PRODUCTION tiers: the post-vote fwdSAInts / rcSAInts (SACollectorCircall.hpp:442-490) of collector calls of a
+    batch run with dump_intervals — as the tier that answered the read computed them — against the oracle's collector on the same
+    read.  r1 / r2: (n, L) arrays or (bases, offsets).  wt_items: mate indices (2 * pair + mate) to check, default all; bsj_items:
+    export records, default all.  Returns {tier: number of collector calls checked}."""
+    import numpy as np
+
+    def read_of(reads, i):
+        if isinstance(reads, tuple):
+            b, o = reads
+            return bytes(b[int(o[i]):int(o[i + 1])])
+        return reads[i].tobytes()
+
+    seen = {}
+    n_mates = B.wt_iv[0].size if B.wt_iv is not None else 0
+    for r in (range(n_mates) if wt_items is None else wt_items):
+        found, tier, gf, gr = B.intervals_of(B.wt_iv, int(r))
+        assert tier != 0, ("no tier recorded mate", r)
+        ofound, f, rc, _ = oidx_tx.collect(read_of(r2 if r & 1 else r1, int(r) >> 1), strict=True, lce_mode=lce_mode, cap_hits=1 << 15)
+        assert found == ofound, (r, tier, found, ofound)
+        if found:
+            assert np.array_equal(gf, f) and np.array_equal(gr, rc), (r, tier, gf, f, gr, rc)
+        seen[("wt", tier)] = seen.get(("wt", tier), 0) + 1
+    if B.bsj_iv is not None:
+        for rec in (range(B.n_export) if bsj_items is None else bsj_items):
+            found, tier, gf, gr = B.intervals_of(B.bsj_iv, int(rec))
+            assert tier != 0, ("no tier recorded record", rec)
+            pair, code = int(B.exp_pair[rec]), int(B.exp_code[rec])
+            ofound, f, rc, _ = oidx_bsj.collect(read_of(r2 if code == 2 else r1, pair), strict=True, lce_mode=lce_mode, cap_hits=1 << 15)
+            assert found == ofound, (rec, tier, found, ofound)
+            if found:
+                assert np.array_equal(gf, f) and np.array_equal(gr, rc), (rec, tier, gf, f, gr, rc)
+            seen[("bsj", tier)] = seen.get(("bsj", tier), 0) + 1
+    return seen

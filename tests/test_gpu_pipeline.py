@@ -5,7 +5,7 @@ nondeterministic, SURVEY.md §8 c)."""
 import numpy as np
 import pytest
 
-from tests.helpers import make_reads, ragged
+from tests.helpers import compare_tier_intervals, make_reads, ragged
 
 pytestmark = pytest.mark.gpu
 
@@ -56,10 +56,10 @@ def test_collect_parity(gpu_world, lce_mode):
     _cmp_collect(cg, obsj, gbsj, r2, lce_mode)
 
 
-def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0):
+def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0, dump_intervals=False):
     import oracle
     R = oracle.Run(otx, obsj, 2, r1, r2, lce_mode=lce_mode)
-    S = cg.Session(gtx, gbsj, stage=0, lce_mode=lce_mode, keep_mate_detail=True)
+    S = cg.Session(gtx, gbsj, stage=0, lce_mode=lce_mode, keep_mate_detail=True, dump_intervals=dump_intervals)
     B = S.run(r1, r2)
     p, c = R.wt_export()
     assert np.array_equal(B.exp_pair, p.astype(np.uint32)) and np.array_equal(B.exp_code, c)
@@ -85,6 +85,24 @@ def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0):
     assert geq == oeq
     S.close()
     return B, R
+
+
+@pytest.mark.parametrize("lce_mode", [0, 1])
+def test_production_tier_intervals(gpu_world, lce_mode):
+    """Row A3 through the kernels the pipeline really runs: every collector call of a batch (both mates on txIdx, every exported
+    record on bsjIdx) hands out its post-vote interval lists together with the tier that answered it — clean-match kernel, lockstep
+    thread tier (lean / two-strand), warp kernel (fast / general) — and each list equals the oracle collector's on the same read.
+    (`cg_collect` / test_collect_parity checks the same surface through the stand-alone reference kernel.)"""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 31, 6000)                       # N-rich: those reads go to the warp kernels
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode, dump_intervals=True)
+    seen = compare_tier_intervals(B, otx, obsj, r1, r2, lce_mode)
+    for tool, tiers in (("wt", (1, 2, 3, 4)), ("bsj", (2, 3, 4))):
+        for t in tiers:
+            assert seen.get((tool, t), 0) > 0, (tool, t, seen)
+    a, b = ragged(r1[:2000], r2[:2000], 5)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, a, b, lce_mode, dump_intervals=True)
+    compare_tier_intervals(B, otx, obsj, a, b, lce_mode)
 
 
 @pytest.mark.parametrize("L,lce_mode", [(100, 0), (100, 1), (75, 0), (150, 0), (250, 0), (33, 0)])
@@ -133,6 +151,9 @@ def test_pipeline_repeat_rich_world():
     gtx, gbsj = cg.Index.build(T.tx_text), cg.Index.build(T.bsj_text)
     assert np.array_equal(gtx.suffix_array(), otx.sa)
     r1, r2 = make_reads(T, 6, 30000, circ_frac=0.15)
+    Bd, _ = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1[:3000], r2[:3000], 0, dump_intervals=True)
+    seen = compare_tier_intervals(Bd, otx, obsj, r1[:3000], r2[:3000], 0)
+    assert seen.get(("wt", 5), 0) > 0 and seen.get(("bsj", 5), 0) > 0, seen        # the general kernels answered some of them
     B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2)
     fl, nh = R.wt_mates()
     assert (B.rec_nhits > 32).sum() > 50 and (B.rec_nhits > 200).sum() > 0      # wide hit lists were exercised
