@@ -281,6 +281,14 @@ class BatchResult:
         self.kernel_ms = tuple(r.kernel_ms)      # pack, wt, commit+compaction, bsj
         self.n_fallback_wt, self.n_fallback_bsj = r.n_fallback_wt, r.n_fallback_bsj
         self.n_tier2_wt, self.n_tier2_bsj = r.n_tier2_wt, r.n_tier2_bsj
+        self.n_cand = r.n_cand
+        # bytes cg_session_fetch copied device -> host for this batch: the batch header, and with the lists every array it exposes
+        self.d2h_bytes = 64
+        if r.exp_pair:
+            n_eq_tids = int(ctypes.cast(r.eq_off, ctypes.POINTER(ctypes.c_uint64))[r.n_eq]) if r.eq_off else 0
+            self.d2h_bytes += r.n_export * (4 + 1 + 4 + 1) + r.n_junc * JUNC_DTYPE.itemsize + 4 * r.n_cand + 16 * r.n_eq + 4 * n_eq_tids
+            if r.mate_flags:
+                self.d2h_bytes += 2 * r.n_pairs * 3
         if not want_lists:
             return
         self.exp_pair = _view(r.exp_pair, np.uint32, r.n_export)

@@ -137,6 +137,9 @@ struct IndexView {
     // random access settles the k - fm + 1 windows that contain the probed fm-mer (cg_thr.cuh::q_walk).
     const uint32_t* fbits;
     int fm;
+    // transcriptAtPosition(SA[i]) for every suffix-array index i (null = none): the hit enumeration and the span filter walk SA
+    // intervals, and with this array an interval's transcripts are one coalesced read instead of one random text block per suffix
+    const uint32_t* satid;
 };
 
 struct TB { uint64_t c0, c1, mask; uint32_t tid0, start0; };
@@ -165,6 +168,16 @@ CG_HD void tid_of(const IndexView& ix, uint32_t p, uint32_t& tid, uint32_t& loca
 // SA[i0 .. i0+n) (n <= 4) -> transcript id and transcript-local offset of each position, with the
 // suffix-array entries, then the text blocks, then the offsets fetched as three waves of independent loads
 CG_HD void sa_tids4(const IndexView& ix, uint32_t i0, int n, uint32_t* tid, uint32_t* local) {
+    if (ix.satid) {
+        uint32_t p[4], st[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { p[x] = x < n ? CG_LDG(&ix.sa[i0 + x]) : 0u; tid[x] = x < n ? CG_LDG(&ix.satid[i0 + x]) : 0u; }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) st[x] = x < n ? CG_LDG(&ix.offsets[tid[x]]) : 0u;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) if (x < n) local[x] = p[x] - st[x];
+        return;
+    }
     uint32_t p[4]; TB t[4]; int c[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) p[x] = x < n ? CG_LDG(&ix.sa[i0 + x]) : 0u;

@@ -248,6 +248,25 @@ k_fbits(IndexView ix, int fm, uint32_t* __restrict__ bits) {
     if (!((bits[x >> 5] >> (x & 31)) & 1u)) atomicOr(&bits[x >> 5], 1u << (x & 31));
     if (!((bits[y >> 5] >> (y & 31)) & 1u)) atomicOr(&bits[y >> 5], 1u << (y & 31));
 }
+// transcriptAtPosition(SA[i]) for every i (IndexView::satid)
+__global__ void __launch_bounds__(256)
+k_satid(IndexView ix, uint32_t* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= ix.n) return;
+    uint32_t tid, local;
+    tid_of(ix, ix.sa[i], tid, local);
+    out[i] = tid;
+}
+int build_satid(cg_index* idx) {
+    if (getenv("CG_NO_SATID")) return CG_OK;
+    IndexView v = idx->view();
+    CG_CUDA(cudaMalloc((void**)&idx->d_satid, idx->n * 4));
+    k_satid<<<grid_for(idx->n, 256), 256>>>(v, idx->d_satid);
+    CG_CUDA(cudaGetLastError());
+    CG_CUDA(cudaDeviceSynchronize());
+    return CG_OK;
+}
+
 int build_fbits(cg_index* idx) {
     int want = 16;
     if (const char* e = getenv("CG_FM")) want = atoi(e);
@@ -279,12 +298,13 @@ void free_index_device(cg_index* idx) {
     if (idx->d_hslots) cudaFree(idx->d_hslots);
     if (idx->d_offsets) cudaFree(idx->d_offsets);
     if (idx->d_fbits) cudaFree(idx->d_fbits);
-    idx->d_fbits = nullptr;
+    if (idx->d_satid) cudaFree(idx->d_satid);
+    idx->d_fbits = nullptr; idx->d_satid = nullptr;
     idx->d_text = nullptr; idx->d_sa = nullptr; idx->d_hslots = nullptr; idx->d_offsets = nullptr;
 }
 
 void finish_sizes(cg_index* idx) {
-    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4 + (idx->d_fbits ? (1ULL << (2 * idx->fm)) / 8 : 0);
+    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4 + (idx->d_fbits ? (1ULL << (2 * idx->fm)) / 8 : 0) + (idx->d_satid ? idx->n * 4 : 0);
 }
 
 int build_impl(int device, const char* text, uint64_t n, int k, const std::vector<std::string>* names, cg_index** out) {
@@ -348,6 +368,8 @@ int build_impl(int device, const char* text, uint64_t n, int k, const std::vecto
     rc = build_khash(idx);
     if (rc) return fail(rc);
     rc = build_fbits(idx);
+    if (rc) return fail(rc);
+    rc = build_satid(idx);
     if (rc) return fail(rc);
 #undef CG_TRY
     finish_sizes(idx);
@@ -524,7 +546,8 @@ static int index_open_impl(const char* dir, int device, cg_index** out) {
     cudaError_t e = cudaMalloc((void**)&idx->d_offsets, idx->offsets.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(idx->d_offsets, idx->offsets.data(), idx->offsets.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(cgi::cuda_fail(e, "upload offsets", __FILE__, __LINE__));
-    if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter is derived from the text: not part of the directory
+    if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter and the per-suffix transcript array are derived from
+    if ((rc = build_satid(idx))) return fail(rc);          // text + SA: not part of the directory
     finish_sizes(idx);
     *out = idx;
     return CG_OK;

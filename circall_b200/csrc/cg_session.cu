@@ -504,7 +504,8 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
                         bool pred = false; uint32_t tid = 0; int hitPos = 0;
                         if (c0 + lane < it.end) {
                             uint32_t p = CG_LDG(&ix.sa[c0 + lane]), local;
-                            tid_of(ix, p, tid, local);
+                            if (ix.satid) { tid = CG_LDG(&ix.satid[c0 + lane]); local = p - CG_LDG(&ix.offsets[tid]); }
+                            else tid_of(ix, p, tid, local);
                             uint32_t refLen = CG_LDG(&ix.offsets[tid + 1]) - CG_LDG(&ix.offsets[tid]) - 1;
                             hitPos = (int)local;
                             int junctPos = (int)(refLen / 2);                     // :333

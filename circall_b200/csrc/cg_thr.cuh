@@ -483,7 +483,15 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
 
 // up to four SA positions -> transcript ids (x, y, z, w; 0xffffffff past nn), the suffix-array entries then the text sectors as
 // two waves of loads
-CG_HDN u32x4 q_tids4(const uint32_t* sa, const u32x4* text, uint32_t i0, int nn) {
+CG_HDN u32x4 q_tids4(const uint32_t* sa, const u32x4* text, const uint32_t* satid, uint32_t i0, int nn) {
+    if (satid) {                                         // the index keeps transcriptAtPosition(SA[i]) per suffix-array index: one wave, contiguous
+        u32x4 r;
+        r.x = CG_LDG(&satid[i0]);
+        r.y = nn > 1 ? CG_LDG(&satid[i0 + 1]) : 0xffffffffu;
+        r.z = nn > 2 ? CG_LDG(&satid[i0 + 2]) : 0xffffffffu;
+        r.w = nn > 3 ? CG_LDG(&satid[i0 + 3]) : 0xffffffffu;
+        return r;
+    }
     uint32_t p[4], tid[4]; u32x4 t[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) p[x] = x < nn ? CG_LDG(&sa[i0 + x]) : 0u;
@@ -534,7 +542,7 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
     const int cb = m.cb(s);
     for (uint32_t c0 = 0; c0 < msp; c0 += 4) {
         const int nn = (int)cmin<uint32_t>(4u, msp - c0);
-        const u32x4 t = q_tids4(ix.sa, ix.text, mb + c0, nn);
+        const u32x4 t = q_tids4(ix.sa, ix.text, ix.satid, mb + c0, nn);
         m.st(cb + (int)c0, t.x);
         if (nn > 1) m.st(cb + (int)c0 + 1, t.y);
         if (nn > 2) m.st(cb + (int)c0 + 2, t.z);
@@ -554,7 +562,7 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
         uint32_t seen = 0;
         for (uint32_t c0 = ib; c0 < ie; c0 += 4) {
             const int nn = (int)cmin<uint32_t>(4u, ie - c0);
-            const u32x4 t = q_tids4(ix.sa, ix.text, c0, nn);
+            const u32x4 t = q_tids4(ix.sa, ix.text, ix.satid, c0, nn);
             for (int c = 0; c < nc; ++c) {
                 const uint32_t tc = m.ld(cb + c);
                 if (tc == t.x || tc == t.y || tc == t.z || tc == t.w) seen |= 1u << c;          // unused entries are 0xffffffff

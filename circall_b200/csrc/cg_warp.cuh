@@ -37,8 +37,11 @@ static const unsigned FULL = 0xffffffffu;
 // entries; <= 16 entries: libstdc++'s sort is a plain insertion sort); the general one, run on the reads the
 // fast one hands over, keeps worst-case state (a 256-base read cannot produce more) in per-warp global scratch
 static const int FAST_FI = 8, FAST_FK = 16, GEN_FI = 232, GEN_FK = 928;
+#ifndef CG_W_32ARY
+#define CG_W_32ARY 1          // wide open intervals: the three searches of extendSearchNaive 32 ways at a time instead of as binary searches
+#endif
 #ifndef CG_W_LINEAR
-#define CG_W_LINEAR 256
+#define CG_W_LINEAR (CG_W_32ARY ? 64 : 256)
 #endif
 static const int W_LINEAR = CG_W_LINEAR;     // widest open interval the extension resolves candidate by candidate (32 per round)
 
@@ -185,7 +188,7 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
             int l = -1;
             if (c0 + (uint32_t)lane < w) {
                 const uint32_t p = CG_LDG(&ix.sa[lbIn + 1 + c0 + lane]);
-                if ((CG_OPT_PF & 1) && w <= 32) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);   // transcript-id half of the block of p, for the hit enumeration
+                if ((CG_OPT_PF & 1) && w <= 32 && !ix.satid) prefetch_l2(&ix.text[2 * (uint64_t)(p >> 6) + 1]);   // transcript-id half of the block of p, for the hit enumeration
                 l = w_match<X>(r, s, qstart, p, startAt, m) >> 2;
             }
             const int cb = __reduce_max_sync(FULL, l);
@@ -199,6 +202,72 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
         o.len = best;
         return o;
     }
+#if CG_W_32ARY
+    // Wide open interval (a repeat family's k-mer: thousands of suffixes).  The reference runs three binary searches here — the
+    // query's insertion point (its neighbours hold the longest match), then the first suffix that shares query[0:maxI] and the first
+    // one past them — 3 x log2(w) dependent SA + text round trips.  The same three searches 32 ways at a time: 32 evenly spaced
+    // suffixes of the current range are compared by the 32 lanes at once, the predicate (monotone along the suffix array) is
+    // balloted and the range shrinks to the gap between two samples, until at most 32 candidates are left for one last round.
+    // Same results (the brute-force definition of SURVEY A6 / B2), a sixth of the dependent rounds.
+    // sample j (0..31) of the open interval (lo, hi) with n = hi - lo - 1 > 32 candidates: distinct, increasing
+#define W_SAMPLE(lo, n, j) ((lo) + 1u + (uint32_t)(((uint64_t)(j) * (uint64_t)((n) - 1u)) / 31u))
+    int maxI = startAt;
+    uint32_t wit = lbIn + 1;                              // a candidate that reaches maxI (every candidate shares the first startAt bases)
+    {   // ---- 1: insertion point (pred: query <= suffix) and the longest match seen on the way
+        uint32_t lo = lbIn, hi = ubIn;
+        for (;;) {
+            const uint32_t n = hi - lo - 1;
+            const bool last = n <= 32;
+            const bool have = last ? (uint32_t)lane < n : true;
+            const uint32_t c = last ? lo + 1 + (uint32_t)lane : W_SAMPLE(lo, n, lane);
+            int i = -1; bool le = false;
+            if (have) {
+                const int v = w_match<X>(r, s, qstart, CG_LDG(&ix.sa[c]), startAt, m);
+                i = v >> 2; le = i >= m || ((v & 3) - 1) < 0;
+            }
+            const int cb = __reduce_max_sync(FULL, i);
+            if (cb > maxI) {
+                const unsigned mk = __ballot_sync(FULL, i == cb);
+                maxI = cb; wit = __shfl_sync(FULL, c, __ffs(mk) - 1);
+            }
+            if (last) break;
+            const unsigned leB = __ballot_sync(FULL, le);
+            const int t = leB ? __ffs(leB) - 1 : 32;      // first sample the query does not sort after
+            const uint32_t nlo = t == 0 ? lo : __shfl_sync(FULL, c, t - 1), nhi = t == 32 ? hi : __shfl_sync(FULL, c, t & 31);
+            lo = nlo; hi = nhi;
+            if (hi - lo <= 1) break;                      // the insertion point lies between two adjacent samples: both were compared
+        }
+    }
+    // ---- 2: first suffix of (lbIn, wit] that is >= query[0:maxI]  (pass 0), first suffix of (wit, ubIn) that is > it (pass 1)
+    uint32_t bound[2];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        // invariant: pred(lo) false (or lo is the excluded end), pred(hi) true (or hi is the excluded end)
+        uint32_t lo = pass == 0 ? lbIn : wit, hi = pass == 0 ? wit : ubIn;
+        while (hi - lo > 1) {
+            const uint32_t n = hi - lo - 1;
+            const bool last = n <= 32;
+            const bool have = last ? (uint32_t)lane < n : true;
+            const uint32_t c = last ? lo + 1 + (uint32_t)lane : W_SAMPLE(lo, n, lane);
+            bool pr = false;
+            if (have) {
+                const int v = w_match<X>(r, s, qstart, CG_LDG(&ix.sa[c]), startAt, maxI);
+                const int i = v >> 2, ord = (v & 3) - 1;
+                pr = pass == 0 ? (i >= maxI || ord < 0) : (i < maxI && ord < 0);
+            }
+            const unsigned pB = __ballot_sync(FULL, pr);
+            const int t = pB ? __ffs(pB) - 1 : 32;
+            if (last) { if (t < 32) hi = lo + 1 + (uint32_t)t; lo = hi - 1; break; }
+            const uint32_t nlo = t == 0 ? lo : __shfl_sync(FULL, c, t - 1), nhi = t == 32 ? hi : __shfl_sync(FULL, c, t & 31);
+            lo = nlo; hi = nhi;
+        }
+        bound[pass] = hi;
+    }
+#undef W_SAMPLE
+    o.lb = bound[0]; o.ub = bound[1]; o.len = maxI;
+    return o;
+}
+#else
     uint32_t lb = lbIn, ub = ubIn;
     int prevLow = startAt, prevHigh = startAt, maxI = startAt;
     while (ub - lb > 1) {
@@ -224,6 +293,7 @@ __device__ __noinline__ Ext w_extend(RV r, int lane, int s, int qstart, uint32_t
     o.lb = lower; o.ub = hi; o.len = maxI;
     return o;
 }
+#endif
 
 template <int X>
 __device__ __noinline__ int w_lce(uint32_t p1, uint32_t p2, int startAt, int stopAt, int mode) {
@@ -464,6 +534,14 @@ __device__ __forceinline__ bool w_collect(RV rv, int lane, int lceMode, WStateT<
     return true;
 }
 
+// transcriptAtPosition(SA[i]): from the index's per-suffix transcript array when it has one, else through the text block
+template <int X>
+__device__ __forceinline__ uint32_t tid_at(uint32_t p);
+template <int X>
+__device__ __forceinline__ uint32_t sa_tid(uint32_t i) {
+    if (c_ix[X].satid) return CG_LDG(&c_ix[X].satid[i]);
+    return tid_at<X>(CG_LDG(&c_ix[X].sa[i]));
+}
 // transcriptAtPosition(p) alone (no offset look-up)
 template <int X>
 __device__ __forceinline__ uint32_t tid_at(uint32_t p) {
@@ -507,7 +585,7 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
     if (msp > 32) { H.ok = false; return H; }       // the candidates (narrowest interval) must fit the lanes; the others may be wider
     const uint32_t mb = ints[mi].begin, me = ints[mi].end;
     bool have = (uint32_t)lane < msp;
-    if (have) H.tid = tid_at<X>(CG_LDG(&ix.sa[mb + lane]));
+    if (have) H.tid = sa_tid<X>(mb + lane);
     // one lane per distinct transcript
     unsigned same = __match_any_sync(FULL, have ? H.tid : (0x80000000u | (uint32_t)lane));
     H.alive = have && (__ffs(same) - 1 == lane);
@@ -525,7 +603,7 @@ __device__ __noinline__ Hits w_hits_lanes(int lane, const Interval* ints, int n)
 #pragma unroll 1
         for (uint32_t c0 = ib; c0 < ie; c0 += 32) {
             uint32_t t = 0xffffffffu;
-            if (c0 + (uint32_t)lane < ie) t = tid_at<X>(CG_LDG(&ix.sa[c0 + lane]));
+            if (c0 + (uint32_t)lane < ie) t = sa_tid<X>(c0 + lane);
 #pragma unroll 1
             for (unsigned m = aB & ~seenB; m; m &= m - 1) {
                 int a = __ffs(m) - 1;
@@ -558,7 +636,7 @@ __device__ __noinline__ uint32_t w_hits_list(int lane, const Interval* ints, int
     __syncwarp();
     uint32_t N = 32;
     while (N < msp) N <<= 1;
-    for (uint32_t c = lane; c < N; c += 32) scr[c] = c < msp ? tid_at<X>(CG_LDG(&ix.sa[mb + c])) : 0xffffffffu;
+    for (uint32_t c = lane; c < N; c += 32) scr[c] = c < msp ? sa_tid<X>(mb + c) : 0xffffffffu;
     __syncwarp();
     for (uint32_t k2 = 2; k2 <= N; k2 <<= 1)
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
@@ -593,7 +671,7 @@ __device__ __noinline__ uint32_t w_hits_list(int lane, const Interval* ints, int
         if (dup) continue;
         // mark the candidates that occur among this interval's positions (binary search in the sorted list)
         for (uint32_t c = ib + lane; c < ie; c += 32) {
-            uint32_t t = tid_at<X>(CG_LDG(&ix.sa[c]));
+            uint32_t t = sa_tid<X>(c);
             uint32_t lo = 0, hi = cnt;
             while (lo < hi) { uint32_t md = (lo + hi) >> 1; if (scr[md] < t) lo = md + 1; else hi = md; }
             if (lo < cnt && scr[lo] == t && act[lo] == counter) act[lo] = (uint8_t)(counter + 1);

@@ -22,7 +22,7 @@ using namespace cg;
 
 struct EmuIndex {
     std::vector<u32x4> text, hslots;
-    std::vector<uint32_t> sa, offsets, fbits;
+    std::vector<uint32_t> sa, offsets, fbits, satid;
     IndexView v;
     uint64_t n_kmers = 0;
 };
@@ -135,7 +135,12 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
     E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
     E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0; E->v.hshift = 0;
     E->v.km = kmask(k); E->v.km3 = E->v.km / 3;
-    E->v.fbits = nullptr; E->v.fm = 0;
+    E->v.fbits = nullptr; E->v.fm = 0; E->v.satid = nullptr;
+    if (!getenv("CG_NO_SATID")) {      // transcriptAtPosition(SA[i]) per suffix-array index, as cg_index.cu::build_satid makes it
+        E->satid.resize(n);
+        for (uint64_t i = 0; i < n; ++i) { uint32_t tid, local; tid_of(E->v, E->sa[i], tid, local); E->satid[i] = tid; }
+        E->v.satid = E->satid.data();
+    }
     {   // seed filter, as cg_index.cu::build_fbits makes it: every '$'-free fm-mer of the text and its reverse complement
         int want = 16;
         if (const char* e = getenv("CG_FM")) want = atoi(e);

@@ -58,3 +58,36 @@ def compare_tier_intervals(B, oidx_tx, oidx_bsj, r1, r2, lce_mode=0, wt_items=No
                 assert np.array_equal(gf, f) and np.array_equal(gr, rc), (rec, tier, gf, f, gr, rc)
             seen[("bsj", tier)] = seen.get(("bsj", tier), 0) + 1
     return seen
+
+
+def assert_batch_equals_oracle(B, ctr, per_bsj, R):
+    """The full comparison of one fused batch with the oracle's run of the same pairs (set equality where the reference's own order
+    is free): export list, per-mate flags / hit counts when the session kept them, junction rows, candidate list, per-record hits and
+    split flags, the eight scalar counters + read lengths, the equivalence-class map and with it the per-BSJ count vector.
+    B: circall_b200.BatchResult fetched with lists; ctr, per_bsj: Session.counters() after that single batch; R: oracle.Run(mode 2)."""
+    import numpy as np
+    p, c = R.wt_export()
+    assert np.array_equal(B.exp_pair, p.astype(np.uint32)) and np.array_equal(B.exp_code, c), "export list"
+    if getattr(B, "mate_flags", None) is not None:
+        fl, nh = R.wt_mates()
+        assert np.array_equal(B.mate_flags, fl) and np.array_equal(B.mate_nhits, nh), "per-mate flags / hit counts"
+    oj = R.bsj_junctions()
+    gj = np.stack([B.junc[k].astype(np.int64) for k in ("rec", "dir", "query_pos", "len", "hit_pos", "tid")], 1) if B.n_junc else np.zeros((0, 6), np.int64)
+    assert oj.shape == gj.shape, "junction row count"
+    if oj.shape[0]:
+        so, sg = oj[np.lexsort(oj.T[::-1])], gj[np.lexsort(gj.T[::-1])]
+        assert np.array_equal(so, sg), "junction rows (as a multiset)"
+    assert np.array_equal(B.cand_rec, R.bsj_candidates().astype(np.uint32)), "candidate list"
+    onh, osp = R.bsj_records()
+    assert np.array_equal(B.rec_nhits, onh) and np.array_equal(B.rec_split, osp), "per-record hits / split"
+    ow, ob = R.counters(0), R.counters(1)
+    assert (ctr["wt_num_observed"], ctr["wt_num_mapped"], ctr["wt_num_hits"], ctr["wt_upper_bound"]) == \
+           (ow["numObserved"], ow["numMapped"], ow["numHits"], ow["upperBound"]), "wt counters"
+    assert (ctr["bsj_num_observed"], ctr["bsj_num_mapped"], ctr["bsj_num_hits"], ctr["bsj_upper_bound"]) == \
+           (ob["numObserved"], ob["numMapped"], ob["numHits"], ob["upperBound"]), "bsj counters"
+    assert ctr["wt_read_len"] == ow["readLen"] and ctr["bsj_read_len"] == ob["readLen"], "read lengths"
+    oeq = R.eq_classes(1)
+    geq = B.eq_classes()
+    for t in np.nonzero(per_bsj)[0]:
+        geq[(int(t),)] = int(per_bsj[t])
+    assert geq == oeq, "equivalence classes / per-BSJ counts"

@@ -5,7 +5,7 @@ nondeterministic, SURVEY.md §8 c)."""
 import numpy as np
 import pytest
 
-from tests.helpers import compare_tier_intervals, make_reads, ragged
+from tests.helpers import assert_batch_equals_oracle, compare_tier_intervals, make_reads, ragged
 
 pytestmark = pytest.mark.gpu
 
@@ -61,28 +61,8 @@ def _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, lce_mode=0, dump_interval
     R = oracle.Run(otx, obsj, 2, r1, r2, lce_mode=lce_mode)
     S = cg.Session(gtx, gbsj, stage=0, lce_mode=lce_mode, keep_mate_detail=True, dump_intervals=dump_intervals)
     B = S.run(r1, r2)
-    p, c = R.wt_export()
-    assert np.array_equal(B.exp_pair, p.astype(np.uint32)) and np.array_equal(B.exp_code, c)
-    fl, nh = R.wt_mates()
-    assert np.array_equal(B.mate_flags, fl) and np.array_equal(B.mate_nhits, nh)
-    oj = R.bsj_junctions()
-    gj = np.stack([B.junc[k].astype(np.int64) for k in ("rec", "dir", "query_pos", "len", "hit_pos", "tid")], 1) if B.n_junc else np.zeros((0, 6), np.int64)
-    assert sorted(map(tuple, oj.tolist())) == sorted(map(tuple, gj.tolist()))
-    assert np.array_equal(B.cand_rec, R.bsj_candidates().astype(np.uint32))
-    onh, osp = R.bsj_records()
-    assert np.array_equal(B.rec_nhits, onh) and np.array_equal(B.rec_split, osp)
     ctr, per_bsj = S.counters()
-    ow, ob = R.counters(0), R.counters(1)
-    assert (ctr["wt_num_observed"], ctr["wt_num_mapped"], ctr["wt_num_hits"], ctr["wt_upper_bound"]) == \
-           (ow["numObserved"], ow["numMapped"], ow["numHits"], ow["upperBound"])
-    assert (ctr["bsj_num_observed"], ctr["bsj_num_mapped"], ctr["bsj_num_hits"], ctr["bsj_upper_bound"]) == \
-           (ob["numObserved"], ob["numMapped"], ob["numHits"], ob["upperBound"])
-    assert ctr["wt_read_len"] == ow["readLen"] and ctr["bsj_read_len"] == ob["readLen"]
-    oeq = R.eq_classes(1)
-    geq = B.eq_classes()
-    for t in np.nonzero(per_bsj)[0]:
-        geq[(int(t),)] = int(per_bsj[t])
-    assert geq == oeq
+    assert_batch_equals_oracle(B, ctr, per_bsj, R)
     S.close()
     return B, R
 
