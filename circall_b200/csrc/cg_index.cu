@@ -228,6 +228,7 @@ int build_khash(cg_index* idx) {
     int hshift = 60;
     while (cap < nk * CG_TABLE_SLOTS_PER_KMER + 2) { cap <<= 1; --hshift; }
     bnd.alloc(0); tmp.alloc(0);
+    if (cap > (1ULL << 33)) CG_FAIL(CG_ERR_CAPACITY, "k-mer table would need more than 2^33 slots");
     CG_CUDA(cudaMalloc((void**)&idx->d_hslots, cap * 16));
     CG_CUDA(cudaMemset(idx->d_hslots, 0xFF, cap * 16));
     if (nB) k_insert<<<grid_for(nB, BS), BS>>>(B.as<uint32_t>(), nB, km.as<uint64_t>(), n, idx->d_hslots, cap - 1, hshift);
@@ -518,7 +519,7 @@ static int index_open_impl(const char* dir, int device, cg_index** out) {
     if (n == 0 || n >= (1ULL << 31) - 128) CG_FAIL(CG_ERR_IO, "meta.bin: text length out of range");
     if (n_tx == 0 || n_tx > n) CG_FAIL(CG_ERR_IO, "meta.bin: transcript count out of range");
     if (n_blocks != (n + 63) / 64 + 1) CG_FAIL(CG_ERR_IO, "meta.bin: text block count does not match the text length");
-    if (hcap < 16 || (hcap & (hcap - 1)) != 0 || hcap > (1ULL << 36) || n_kmers >= hcap) CG_FAIL(CG_ERR_IO, "meta.bin: table capacity must be a power of two above the k-mer count");
+    if (hcap < 16 || (hcap & (hcap - 1)) != 0 || hcap > (1ULL << 33) || n_kmers >= hcap) CG_FAIL(CG_ERR_IO, "meta.bin: table capacity must be a power of two above the k-mer count");
     if (!file_size_is(d + "/offsets.bin", (n_tx + 1) * 4)) CG_FAIL(CG_ERR_IO, "offsets.bin has the wrong size");
     if (!file_size_is(d + "/text.bin", n_blocks * 32)) CG_FAIL(CG_ERR_IO, "text.bin has the wrong size");
     if (!file_size_is(d + "/sa.bin", n * 4)) CG_FAIL(CG_ERR_IO, "sa.bin has the wrong size");

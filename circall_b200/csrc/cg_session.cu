@@ -13,6 +13,8 @@
 #include "cg_pre.cuh"
 #include "cg_thr.cuh"
 #include <algorithm>
+#include <mutex>
+#include <vector>
 #include <cstring>
 #include <cstddef>
 #include <cstdlib>
@@ -565,6 +567,7 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
 #define CG_PRE_THREADS 128
 #endif
 static const int PRE_THREADS = CG_PRE_THREADS;
+template <bool DUMP>        // DUMP: the debug surface of cg_opts::dump_intervals, its own instantiation so that the production kernel carries none of it
 __global__ void __launch_bounds__(PRE_THREADS)
 k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, IvDump dump) {
@@ -588,8 +591,8 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
         for (int j = 0; j < g.W2f; ++j) { const uint64_t v = __ldg(rec + j); m.st(2 * j, (uint32_t)v); m.st(2 * j + 1, (uint32_t)(v >> 32)); }
         m.st(2 * g.W2f, 0); m.st(2 * g.W2f + 1, 0);
         cgp::PreIv piv;
-        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh, cls, dump.head ? &piv : (cgp::PreIv*)nullptr);
-        if (done && dump.head) {
+        done = cgp::perfect_mate(cgw::c_ix[0], m, L, pairLen, fl, nh, cls, DUMP ? &piv : (cgp::PreIv*)nullptr);
+        if (DUMP && done) {
             // the list this path stands for (cg_pre.cuh): the full-length interval, then the k-mer interval of the forced last position —
             // twice on the forward strand (Phase B re-runs it after setting lastSearch, :300-321), once on the other (:412)
             const int k = cgw::c_ix[0].k;
@@ -633,11 +636,11 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
 // Circall_wt: over the mates list[..] the front kernel declined (all n_reads mates when list is null); ovf[r] = 1 hands mate r
 // to the warp kernels.  The list is grouped by look-up class: the lean instantiation (VOTE = false) takes its head
 // [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
-template <bool VOTE>
+template <bool VOTE, bool DUMP>
 __global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
          const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
-         uint8_t* __restrict__ ovf, IvDump dump) {
+         uint8_t* __restrict__ ovf, const uint8_t* __restrict__ cls, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : n_reads;
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -647,19 +650,19 @@ k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
     const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
     cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
     uint8_t fl = 0; uint32_t nh = 0; int why = 0, nF = 0, nR = 0;
-    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why, nF, nR);
+    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why, nF, nR, cls ? (int)cls[r] - 1 : -1);
     if (done) { flags[r] = fl; nhits[r] = nh; }
     else ovf[r] = 1;
-    if (dump.head && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
+    if (DUMP && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
 }
 
 // Circall_bsj: over the records list[..] (every exported record when list is null); ovf[rec] = 1 hands record rec to the warp
 // kernels (nothing was emitted for it).  seg as in k_wt_thr.
-template <bool VOTE>
+template <bool VOTE, bool DUMP>
 __global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
 k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, BsjOut o, int do_counts,
-          uint8_t* __restrict__ ovf, IvDump dump) {
+          uint8_t* __restrict__ ovf, const uint8_t* __restrict__ cls, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -673,8 +676,8 @@ k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
         cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
         JSink sink; sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; sink.rec = (uint32_t)rec;
         uint32_t nh = 0; bool split = false; int why = 0, at = 0, nF = 0, nR = 0;
-        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why, nF, nR);
-        if (dump.head && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
+        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why, nF, nR, cls ? (int)cls[rec] - 1 : -1);
+        if (DUMP && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
         if (!done) ovf[rec] = 1;
         else {
             // commit (Circall_bsj.cpp:383-491)
@@ -729,6 +732,19 @@ k_cand_flag(const uint32_t* __restrict__ nh, const uint8_t* __restrict__ sp, con
 
 inline unsigned grid_for(uint64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// A batch counts into its own staging vector [per-BSJ counts | scalar counters]; this kernel, last on the batch's stream, adds it
+// to the session's accumulator only when the batch ended clean (status 0) and clears it either way: a batch that fails with
+// CG_ERR_BASE / LENGTH / CAPACITY leaves no partial counts behind (cg_session_counters, cg_session_accumulator and the all-reduce
+// across GPUs only ever see whole batches).
+__global__ void __launch_bounds__(256)
+k_acc_fold(unsigned long long* __restrict__ batch, unsigned long long* __restrict__ acc, uint64_t n, const BatchHdr* hdr) {
+    const bool ok = hdr->status == 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = batch[i];
+        if (v) { if (ok) acc[i] += v; batch[i] = 0; }
+    }
+}
+
 // offsets of n reads of one length (cg_session_submit_fixed: the offsets are not worth their bytes on PCIe)
 __global__ void k_fixed_offsets(uint64_t* __restrict__ off, uint64_t n_plus_1, uint64_t len) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -766,7 +782,8 @@ struct cg_session {
     uint32_t iv_cap = 0;
     PinVec<uint32_t> h_ivhead_wt, h_ivoff_wt, h_ivhead_bsj, h_ivoff_bsj;
     PinVec<int4> h_ivpool_wt, h_ivpool_bsj;
-    unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]
+    unsigned long long* d_acc = nullptr;   // [n_bsj | 8 scalars]: totals of the batches that ended clean
+    unsigned long long* d_accb = nullptr;  // the same for the batch in flight (k_acc_fold)
     uint64_t n_bsj = 0;
     uint64_t junc_cap = 0, eq_cap = 0, eq_tids_cap = 0;
     // host result buffers
@@ -783,6 +800,51 @@ struct cg_session {
 };
 
 namespace {
+
+// ---- who owns the per-device constant index view (cgw::c_ix) ------------------------------------------------------------
+// The kernels read the two index views from constant memory (the warp kernels are written for code size and take them as immediate
+// operands), and a session rewrites them on its own stream before each stage.  Sessions on the same indices write the same bytes;
+// a session on OTHER indices must not do so while batches of the current owner are still running.  The registry below makes that a
+// property of the library instead of a rule for the caller: a session whose indices differ from the ones the constants hold first
+// makes its stream wait for every batch in flight on the device (their end-of-batch events), then takes the constants over.
+struct DeviceIx {
+    std::mutex mu;
+    const cg_index* owner[2] = {nullptr, nullptr};       // [0] txIdx, [1] bsjIdx currently in c_ix
+    std::vector<cg_session*> inflight;                   // sessions with a batch submitted and not yet fetched
+};
+DeviceIx g_devix[64];
+
+int acquire_ix(cg_session* s) {
+    if (s->device < 0 || s->device >= 64) return CG_OK;
+    DeviceIx& D = g_devix[s->device];
+    std::lock_guard<std::mutex> lock(D.mu);
+    const bool uses0 = s->opts.stage != 2, uses1 = s->opts.stage != 1;
+    const bool clash = (uses0 && D.owner[0] && D.owner[0] != s->tx) || (uses1 && D.owner[1] && D.owner[1] != s->bsj);
+    if (clash) {
+        for (cg_session* o : D.inflight)
+            if (o != s) CG_CUDA(cudaStreamWaitEvent(s->stream, o->ev1, 0));
+        // (the owners' later submits wait for this batch in turn: they find their indices displaced)
+    }
+    if (uses0) D.owner[0] = s->tx;
+    if (uses1) D.owner[1] = s->bsj;
+    if (std::find(D.inflight.begin(), D.inflight.end(), s) == D.inflight.end()) D.inflight.push_back(s);
+    return CG_OK;
+}
+void release_ix(cg_session* s) {
+    if (s->device < 0 || s->device >= 64) return;
+    DeviceIx& D = g_devix[s->device];
+    std::lock_guard<std::mutex> lock(D.mu);
+    D.inflight.erase(std::remove(D.inflight.begin(), D.inflight.end(), s), D.inflight.end());
+}
+void forget_index(const cg_session* s) {          // a destroyed session's indices may be closed next: never compare against a dangling owner
+    if (s->device < 0 || s->device >= 64) return;
+    DeviceIx& D = g_devix[s->device];
+    std::lock_guard<std::mutex> lock(D.mu);
+    bool used[2] = {false, false};
+    for (cg_session* o : D.inflight) { if (o == s) continue; if (o->opts.stage != 2 && o->tx == D.owner[0]) used[0] = true; if (o->opts.stage != 1 && o->bsj == D.owner[1]) used[1] = true; }
+    if (!used[0] && D.owner[0] == s->tx) D.owner[0] = nullptr;
+    if (!used[1] && D.owner[1] == s->bsj) D.owner[1] = nullptr;
+}
 
 template <class K, class... A>
 int launch(cg_session* s, K kern, dim3 grid, dim3 block, size_t smem, A... args) {
@@ -824,7 +886,7 @@ int run_bsj_stage(cg_session* s, int do_counts) {
     o.eq_ent = s->d_eqent.as<uint4>(); o.eq_cap = s->eq_cap;
     o.eq_tids = s->d_eqtids.as<uint32_t>(); o.eq_tids_cap = s->eq_tids_cap;
     o.rec_nhits = s->d_recnh.as<uint32_t>(); o.rec_split = s->d_recsp.as<uint8_t>();
-    o.per_bsj = s->d_acc; o.ctr = s->d_acc + s->n_bsj; o.hdr = s->d_hdr.as<BatchHdr>();
+    o.per_bsj = s->d_accb; o.ctr = s->d_accb + s->n_bsj; o.hdr = s->d_hdr.as<BatchHdr>();
     const uint32_t* em = stage2 ? nullptr : s->d_exp.as<uint32_t>();
     IvDump dbs; memset(&dbs, 0, sizeof dbs);
     if (s->opts.dump_intervals && do_counts == 3) {          // (not on the redo pass of a batch whose row buffers were too small)
@@ -851,13 +913,13 @@ int run_bsj_stage(cg_session* s, int do_counts) {
         rc = compact_classes(s, s->d_ovf3.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
         if (rc) return rc;
         const uint32_t* seg = (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(worst, CP_TILE));
-        rc = launch(s, k_bsj_thr<false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4,
+        rc = launch(s, dbs.head ? k_bsj_thr<false, true> : k_bsj_thr<false, false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (const uint8_t*)s->d_ovf3.as<uint8_t>(), dbs);
         if (rc) return rc;
-        rc = launch(s, k_bsj_thr<true>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4,
+        rc = launch(s, dbs.head ? k_bsj_thr<true, true> : k_bsj_thr<true, false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (const uint8_t*)s->d_ovf3.as<uint8_t>(), dbs);
         if (rc) return rc;
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
         if (rc) return rc;
@@ -920,6 +982,7 @@ int run_batch(cg_session* s) {
         uint64_t want_t = want_e * 8;
         if (s->eq_tids_cap < want_t) { CG_CUDA(s->d_eqtids.reserve(want_t * 4)); s->eq_tids_cap = want_t; }
     }
+    { int arc = acquire_ix(s); if (arc) return arc; }
     CG_CUDA(cudaMemsetAsync(s->d_hdr.p, 0, sizeof(BatchHdr), s->stream));
     IvDump dwt; memset(&dwt, 0, sizeof dwt);
     if (s->opts.dump_intervals) {
@@ -952,7 +1015,7 @@ int run_batch(cg_session* s) {
         // warp kernel, general warp kernel
         const uint32_t* cur_list = nullptr; const uint32_t* cur_n = nullptr;        // mates still to map (null: all of them)
         if (s->use_pre) {
-            rc = launch(s, k_wt_pre, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
+            rc = launch(s, dwt.head ? k_wt_pre<true> : k_wt_pre<false>, dim3(grid_for(n_reads, PRE_THREADS)), dim3(PRE_THREADS), (size_t)PRE_THREADS * cgp::pre_words(g.W2f + 1) * 4,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf.as<uint8_t>(), dwt);
             if (rc) return rc;
             // the front kernel leaves a look-up class per declined mate: the lockstep tier wants its work grouped by it
@@ -967,14 +1030,14 @@ int run_batch(cg_session* s) {
             // two-strand instantiation over the tail; an unsorted list (or none) goes through the lean one alone
             const bool sorted = cur_list && s->use_pre;
             const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
-            rc = launch(s, k_wt_thr<false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
+            rc = launch(s, dwt.head ? k_wt_thr<false, true> : k_wt_thr<false, false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), sorted ? (const uint8_t*)s->d_ovf.as<uint8_t>() : (const uint8_t*)nullptr, dwt);
             if (rc) return rc;
             if (sorted) {
-                rc = launch(s, k_wt_thr<true>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4,
+                rc = launch(s, dwt.head ? k_wt_thr<true, true> : k_wt_thr<true, false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4,
                             s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
+                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (const uint8_t*)s->d_ovf.as<uint8_t>(), dwt);
                 if (rc) return rc;
             }
             rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
@@ -1001,7 +1064,7 @@ int run_batch(cg_session* s) {
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
         rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
                     s->d_expflag.as<uint8_t>(), s->opts.keep_mate_detail ? s->d_mflags.as<uint8_t>() : (uint8_t*)nullptr,
-                    s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_acc + s->n_bsj, dh);
+                    s->opts.keep_mate_detail ? s->d_mnhits.as<uint16_t>() : (uint16_t*)nullptr, s->d_accb + s->n_bsj, dh);
         if (rc) return rc;
         rc = compact_flags(s, s->d_expflag.as<uint8_t>(), n_reads, s->d_exp.as<uint32_t>(), &dh->n_exp);
         if (rc) return rc;
@@ -1022,6 +1085,8 @@ int run_batch(cg_session* s) {
         rc = run_bsj_stage(s, 3);
         if (rc) return rc;
     }
+    rc = launch(s, k_acc_fold, dim3(s->sms * 4), dim3(256), 0, s->d_accb, s->d_acc, s->n_bsj + (uint64_t)C_NUM, (const BatchHdr*)s->d_hdr.as<BatchHdr>());
+    if (rc) return rc;
     CG_CUDA(cudaEventRecord(s->ev1, s->stream));
     CG_CUDA(cudaMemcpyAsync(s->h_hdr.p, s->d_hdr.p, sizeof(BatchHdr), cudaMemcpyDeviceToHost, s->stream));
     s->pending = true;
@@ -1064,6 +1129,8 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
     if (e == cudaSuccess) e = cudaEventCreate(&s->evc);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_acc, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->d_acc, 0, (s->n_bsj + C_NUM) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_accb, (s->n_bsj + C_NUM) * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_accb, 0, (s->n_bsj + C_NUM) * 8);
     if (e == cudaSuccess) e = s->h_hdr.reserve(sizeof(BatchHdr));
     if (e == cudaSuccess) {
         // persistent grids: as many blocks as stay resident (sized for the largest read geometry in common use)
@@ -1075,8 +1142,8 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         s->sms = sms;
         s->use_pre = getenv("CG_NO_PRE") == nullptr;
         s->use_thr = getenv("CG_NO_THR") == nullptr;
-        // the lockstep tier keeps table slot numbers in 32 bits (cg_thr.cuh::q_walk)
-        if ((tx && tx->hcap > (1ULL << 32)) || (bsj && bsj->hcap > (1ULL << 32))) s->use_thr = false;
+        // (the lockstep tier keeps table SECTOR numbers in 32 bits, cg_thr.cuh::q_walk: good for 2^33 slots = 137 GB of table, more than
+        // the index builder can allocate next to the rest of an index, so no table size switches a tier off)
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
         s->warp_grid_bsj = sms * (bb > 0 ? bb : 1);
         s->gen_grid = sms * CG_GEN_MINB;
@@ -1091,6 +1158,7 @@ void cg_session_destroy(cg_session* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    release_ix(s); forget_index(s);
 #ifdef CG_WARP_PROF
     {
         unsigned long long h[64];
@@ -1117,6 +1185,7 @@ void cg_session_destroy(cg_session* s) {
     s->h_mnhits.release(); s->h_junc.release(); s->h_eqent.release();
     s->h_ivhead_wt.release(); s->h_ivoff_wt.release(); s->h_ivhead_bsj.release(); s->h_ivoff_bsj.release(); s->h_ivpool_wt.release(); s->h_ivpool_bsj.release();
     if (s->d_acc) cudaFree(s->d_acc);
+    if (s->d_accb) cudaFree(s->d_accb);
     if (s->d_gscratch) cudaFree(s->d_gscratch);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1193,6 +1262,7 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
     CG_CUDA(cudaSetDevice(s->device));
     CG_CUDA(cudaStreamSynchronize(s->stream));
     s->pending = false;
+    release_ix(s);
     BatchHdr hdr = *s->h_hdr.as<BatchHdr>();
     if (hdr.status & ST_BADBASE) CG_FAIL(CG_ERR_BASE, "a read holds a character outside ACGTNacgtn");
     if (hdr.status & ST_TOOLONG) CG_FAIL(CG_ERR_LENGTH, "a read is longer than the batch's max_read_len");
@@ -1213,10 +1283,14 @@ int cg_session_fetch(cg_session* s, int want_lists, cg_batch_result* out) {
         if (hdr.n_eq_tids > s->eq_tids_cap) { CG_CUDA(s->d_eqtids.reserve((hdr.n_eq_tids + 1024) * 4)); s->eq_tids_cap = hdr.n_eq_tids + 1024; }
         BatchHdr* dh = s->d_hdr.as<BatchHdr>();
         CG_CUDA(cudaMemsetAsync(&dh->n_junc, 0, 3 * sizeof(unsigned long long), s->stream));
-        int rc = run_bsj_stage(s, 2);
+        int rc = acquire_ix(s);
         if (rc) return rc;
+        rc = run_bsj_stage(s, 2);
+        if (rc) { release_ix(s); return rc; }
+        CG_CUDA(cudaEventRecord(s->ev1, s->stream));
         CG_CUDA(cudaMemcpyAsync(s->h_hdr.p, s->d_hdr.p, sizeof(BatchHdr), cudaMemcpyDeviceToHost, s->stream));
         CG_CUDA(cudaStreamSynchronize(s->stream));
+        release_ix(s);
         BatchHdr h2 = *s->h_hdr.as<BatchHdr>();
         if (h2.n_junc != hdr.n_junc || h2.n_eq != hdr.n_eq || h2.n_eq_tids != hdr.n_eq_tids) CG_FAIL(CG_ERR_STATE, "redo of the bsj stage disagreed with the first pass");
     }

@@ -224,9 +224,9 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
                 const uint64_t mer = ((uint64_t)cgt::fsr(a, b, sf) | ((uint64_t)cgt::fsr(b, c, sf) << 32)) & ix.km;
                 if (!(both && (i & 1))) homo |= in && homopolymer_ix(mer, ix);
                 key[i] = (both && (i & 1)) ? revcomp(mer, k) : mer;
-                hs[i] = (uint32_t)home_slot(ix, key[i]);                           // (a table has fewer than 2^32 slots)
+                hs[i] = (uint32_t)(home_slot(ix, key[i]) >> 1);                    // home slots are even: the sector number fits 32 bits up to 2^33 slots
                 sl[i].x = sl[i].y = 0xffffffffu; sl[i].z = sl[i].w = 0;            // an empty slot: not found
-                if (in) { sl[i] = CG_LDG(&ix.hslots[hs[i]]); CG_WALK_STAT(table_loads, 1); }
+                if (in) { sl[i] = CG_LDG(&ix.hslots[2 * (uint64_t)hs[i]]); CG_WALK_STAT(table_loads, 1); }
             }
             if (homo) return -1;
             // Resolve all of them together.  A home slot is the even slot of a 32-byte sector and holds another k-mer for a third
@@ -241,7 +241,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
             }
             if (pend) {
 #pragma unroll
-                for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[hs[i] + 1]);
+                for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[2 * (uint64_t)hs[i] + 1]);
 #pragma unroll
                 for (int i = 0; i < QW; ++i) {
                     if ((pend >> i) & 1u) {
@@ -256,7 +256,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
 #pragma unroll 1
                 for (int step = 2; step < 4 && pend; ++step) {
 #pragma unroll
-                    for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[((uint64_t)hs[i] + step) & ix.hmask]);
+                    for (int i = 0; i < QW; ++i) if ((pend >> i) & 1u) sl[i] = CG_LDG(&ix.hslots[(2 * (uint64_t)hs[i] + step) & ix.hmask]);
 #pragma unroll
                     for (int i = 0; i < QW; ++i) {
                         if ((pend >> i) & 1u) {
@@ -270,7 +270,7 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
 #pragma unroll
                     for (int i = 0; i < QW; ++i) {
                         if ((pend >> i) & 1u) {
-                            const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], ((uint64_t)hs[i] + 4) & ix.hmask);
+                            const u32x4 r = q_resolve_from(ix.hslots, ix.hmask, key[i], (2 * (uint64_t)hs[i] + 4) & ix.hmask);
                             if (r.x) { fb |= 1u << i; sl[i].z = r.y; sl[i].w = r.z; }
                         }
                     }
@@ -295,8 +295,11 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
 //   VOTE = false: reads whose hits lie on one strand (a look-up that scores for the other strand declines the read)
 //   VOTE = true : both strands — Phase B then Phase C when rcHit >= fwdHit (:332), the kmerScores list and its vote (:442-490)
 // Returns Q_FOUND (nF / nR post-vote intervals in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.
+// known: which of the four up-front k-mers are in the table, as the kernel in front of this tier already found out (bit 0 read[0,k),
+// bit 1 its reverse complement, bit 2 read[L-k,L), bit 3 its reverse complement; the look-up class minus one) — an absent one is
+// not looked up again; < 0: not known.
 template <bool VOTE>
-CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, int& nF, int& nR) {
+CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, int& nF, int& nR, int known = -1) {
     const int k = ix.k, skipOverlap = k - 1;
     nF = nR = 0;
     if (L > 0xffff) return QD_ODD;
@@ -308,7 +311,12 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
         if (homopolymer_ix(mer0, ix) || homopolymer_ix(merL, ix)) return QD_HOMO;
         const uint64_t rc0 = revcomp(mer0, k), rcL = revcomp(merL, k);
         const uint64_t h0 = home_slot(ix, mer0), h1 = home_slot(ix, rc0), h2 = home_slot(ix, merL), h3 = home_slot(ix, rcL);
-        const u32x4 s0 = CG_LDG(&ix.hslots[h0]), s1 = CG_LDG(&ix.hslots[h1]), s2 = CG_LDG(&ix.hslots[h2]), s3 = CG_LDG(&ix.hslots[h3]);
+        u32x4 s0, s1, s2, s3;
+        s0.x = s0.y = 0xffffffffu; s0.z = s0.w = 0; s1 = s0; s2 = s0; s3 = s0;             // an empty slot: not found
+        if (known < 0 || (known & 1)) s0 = CG_LDG(&ix.hslots[h0]);
+        if (known < 0 || (known & 2)) s1 = CG_LDG(&ix.hslots[h1]);
+        if (known < 0 || (known & 4)) s2 = CG_LDG(&ix.hslots[h2]);
+        if (known < 0 || (known & 8)) s3 = CG_LDG(&ix.hslots[h3]);
         F0.b = F0.e = R0.b = R0.e = FL.b = FL.e = RL.b = RL.e = 0;
         F0.f = resolve(ix, mer0, h0, s0, F0.b, F0.e); R0.f = resolve(ix, rc0, h1, s1, R0.b, R0.e);
         FL.f = resolve(ix, merL, h2, s2, FL.b, FL.e); RL.f = resolve(ix, rcL, h3, s3, RL.b, RL.e);
@@ -597,8 +605,8 @@ CG_HD int q_hits2(const IndexView& ix, const QMemT<VOTE>& m, int nF, int nR, int
 
 // one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517): false = declined
 template <bool VOTE>
-CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why, int& nF, int& nR) {
-    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
+CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why, int& nF, int& nR, int known = -1) {
+    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR, known);
     why = r;
     if (r < 0) return false;
     flags = 0; nh = 0;
@@ -618,8 +626,8 @@ CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairL
 // one record of Circall_bsj (src/Circall_bsj.cpp:300-399): false = declined (nothing was emitted).  On success the
 // hit transcripts are left in ascending order at tids_at (word index in the scratch), nh of them.
 template <bool VOTE, class Sink>
-CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why, int& nF, int& nR) {
-    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR);
+CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why, int& nF, int& nR, int known = -1) {
+    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR, known);
     why = r;
     tids_at = m.cb(0);
     if (r < 0) return false;

@@ -161,8 +161,10 @@ typedef struct {
     uint32_t wt_read_len, bsj_read_len;   /* first read length seen (Circall_wt.cpp:303, Circall_bsj.cpp:310) */
 } cg_counters;
 
-/* Several sessions may be in flight on one device (each has its own stream: copies of one overlap kernels of the others), but
- * they must all have been created on the same pair of indices: the kernels read the index view from one per-device constant. */
+/* Several sessions may be in flight on one device (each has its own stream: copies of one overlap kernels of the others).  The
+ * kernels read the index views from per-device constant memory; sessions on the same indices share them, and a submit from a
+ * session on OTHER indices first waits (on the device, stream-ordered) for the batches in flight on the current ones — correct for
+ * any mix of sessions, concurrent only among sessions of one index pair. */
 int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* opts, cg_session** out);
 void cg_session_destroy(cg_session* s);
 /* host buffers (pageable or pinned): concatenated ASCII bases + n_pairs+1 offsets per mate file

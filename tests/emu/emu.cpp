@@ -74,6 +74,15 @@ static bool both_class(const IndexView& ix, const std::vector<uint64_t>& pk, int
     uint64_t mer0 = pk[0] & ix.km;
     return present(ix, mer0) && present(ix, revcomp(mer0, ix.k));
 }
+// the look-up class minus one, as k_wt_pre / k_bsj_cls leave it for the lockstep tier (which of the four end k-mers are in the table)
+static int known_of(const IndexView& ix, const std::vector<uint64_t>& pk, int L) {
+    if (L <= ix.k || getenv("CG_EMU_NO_KNOWN")) return -1;
+    int W2f = std::max(1, (L + 31) / 32);
+    std::vector<uint64_t> w(pk.begin(), pk.begin() + W2f); w.push_back(0);
+    const int j = (L - ix.k) >> 5, sh = ((L - ix.k) & 31) * 2;
+    const uint64_t mer0 = w[0] & ix.km, merL = (sh ? (w[j] >> sh) | (w[j + 1] << (64 - sh)) : w[j]) & ix.km;
+    return (present(ix, mer0) ? 1 : 0) | (present(ix, revcomp(mer0, ix.k)) ? 2 : 0) | (present(ix, merL) ? 4 : 0) | (present(ix, revcomp(merL, ix.k)) ? 8 : 0);
+}
 static uint64_t g_thr_why[2][16];
 static uint64_t g_thr_vote[2];
 static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
@@ -81,11 +90,11 @@ static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, in
     bool ok;
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
-        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR);
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR, known_of(ix, pk, L));
         if (ok) ++g_thr_vote[0];
     } else {
         cgq::QMemT<false> m;
-        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_wt_mate<false>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR);
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_wt_mate<false>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR, known_of(ix, pk, L));
     }
     if (!ok) ++g_thr_why[0][(-why) & 15];
     return ok;
@@ -96,11 +105,11 @@ static bool thr_bsj_host(const IndexView& ix, const std::vector<uint64_t>& pk, i
     bool ok;
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
-        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR);
+        ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR, known_of(ix, pk, L));
         if (ok) { ++g_thr_vote[1]; for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t); }
     } else {
         cgq::QMemT<false> m;
-        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_bsj_record<false>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR);
+        ok = thr_stage<false>(pk, L, scratch, m) && cgq::q_bsj_record<false>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR, known_of(ix, pk, L));
         if (ok) for (uint32_t t = 0; t < nh && t < (uint32_t)MAX_READ_OCCS; ++t) tids[t] = m.ld(at + t);
     }
     if (!ok) ++g_thr_why[1][(-why) & 15];

@@ -179,6 +179,54 @@ def test_stages_compose(gpu_world):
     assert np.array_equal(Bs.cand_rec, F.cand_rec)
 
 
+def test_sessions_on_different_indices_interleave(gpu_world):
+    """Two sessions on different index pairs with batches in flight at the same time on one device: the per-device constant index
+    view is handed from one pair to the other in stream order (cg_session.cu::acquire_ix), so both get their own results."""
+    import oracle
+    import synth
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    T2 = synth.Txome(23, 150)
+    g2tx, g2bsj = cg.Index.build(T2.tx_text), cg.Index.build(T2.bsj_text)
+    ra = make_reads(T, 61, 12000)
+    rb = make_reads(T2, 62, 12000)
+    want_a = cg.Session(gtx, gbsj).run(*ra)
+    want_b = cg.Session(g2tx, g2bsj).run(*rb)
+    A, B = cg.Session(gtx, gbsj), cg.Session(g2tx, g2bsj)
+    for _ in range(3):
+        A.submit(*ra); B.submit(*rb)
+        ga, gb = A.fetch(), B.fetch()
+        B.submit(*rb); A.submit(*ra)
+        gb2, ga2 = B.fetch(), A.fetch()
+        for got, want in ((ga, want_a), (ga2, want_a), (gb, want_b), (gb2, want_b)):
+            assert np.array_equal(got.exp_pair, want.exp_pair) and np.array_equal(got.exp_code, want.exp_code)
+            assert np.array_equal(np.sort(got.junc, order=["rec", "dir", "query_pos", "len", "hit_pos", "tid"]),
+                                  np.sort(want.junc, order=["rec", "dir", "query_pos", "len", "hit_pos", "tid"]))
+            assert np.array_equal(got.cand_rec, want.cand_rec) and np.array_equal(got.rec_nhits, want.rec_nhits)
+    assert want_a.n_junc > 0 and want_b.n_junc > 0
+
+
+def test_failed_batch_leaves_no_counts(gpu_world):
+    """A batch that fails (here: a character outside ACGTN in its last read) must not leave partial counts in the session's accumulator:
+    counters, per-BSJ vector and the all-reduce operand only ever hold whole batches, and the session stays usable."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    r1, r2 = make_reads(T, 43, 6000)
+    S = cg.Session(gtx, gbsj)
+    S.run(r1[:3000], r2[:3000], want_lists=False)
+    c0, p0 = S.counters()
+    bad = r1[3000:].copy()
+    bad[-1, 17] = ord("X")
+    with pytest.raises(cg.CircallError):
+        S.run(bad, r2[3000:], want_lists=False)
+    c1, p1 = S.counters()
+    assert c1 == c0 and np.array_equal(p1, p0)
+    S.run(r1[3000:], r2[3000:], want_lists=False)
+    c2, p2 = S.counters()
+    W = cg.Session(gtx, gbsj)
+    W.run(r1, r2, want_lists=False)
+    cw, pw = W.counters()
+    assert c2 == cw and np.array_equal(p2, pw) and cw["bsj_num_observed"] > c0["bsj_num_observed"] > 0
+
+
 def test_batches_accumulate(gpu_world):
     """Counters are linear in the input: two half batches == one full batch."""
     cg, T, otx, obsj, gtx, gbsj = gpu_world
