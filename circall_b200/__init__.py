@@ -116,6 +116,7 @@ def lib():
     L.cg_session_fetch.argtypes = [vp, i32, ctypes.POINTER(_BatchResult)]
     L.cg_session_counters.argtypes = [vp, ctypes.POINTER(_Counters), vp, u64]
     L.cg_session_accumulator.argtypes = [vp, pp, ctypes.POINTER(u64)]
+    L.cg_sessions_allreduce.argtypes = [ctypes.POINTER(vp), i32]
     L.cg_session_launches.argtypes = [vp]
     L.cg_session_launches.restype = u64
     L.cg_device_alloc.argtypes = [i32, u64, pp]
@@ -404,6 +405,12 @@ class Session:
     @property
     def launches(self):
         return lib().cg_session_launches(self._h)
+
+
+def allreduce_sessions(sessions):
+    """cg_sessions_allreduce: after it every session's accumulator (and counters) holds the total over all of them."""
+    arr = (ctypes.c_void_p * len(sessions))(*[s._h for s in sessions])
+    _check(lib().cg_sessions_allreduce(arr, len(sessions)))
 
 
 class DeviceBuffer:

@@ -14,6 +14,7 @@
 #include "cg_thr.cuh"
 #include <algorithm>
 #include <mutex>
+#include <dlfcn.h>
 #include <vector>
 #include <cstring>
 #include <cstddef>
@@ -1393,5 +1394,80 @@ int cg_session_accumulator(cg_session* s, void** dptr, uint64_t* n_u64) {
 }
 
 uint64_t cg_session_launches(const cg_session* s) { return s ? s->launches : 0; }
+
+// ---- the one collective of the path (SURVEY.md section 8 e): all-reduce of the accumulators -------------------------------------
+// NCCL is bound at first use (dlopen of libnccl.so.2), so the library loads in processes that bring their own NCCL (bench.py's ranks
+// are torch.distributed ranks and reduce through torch) and on boxes without one; only this entry point needs it.
+namespace {
+typedef void* nccl_comm_t;
+struct Nccl {
+    void* h = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll"); CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce"); GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd"); GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+Nccl g_nccl;
+__global__ void __launch_bounds__(256)
+k_acc_add(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+#define CG_NCCL(expr) do { int _r = (expr); if (_r != 0) { cgi::set_error(std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " in " #expr); return CG_ERR_CUDA; } } while (0)
+} // namespace
+
+int cg_sessions_allreduce(cg_session* const* ss, int n) {
+    if (!ss || n <= 0) CG_FAIL(CG_ERR_ARG, "no session given");
+    const uint64_t len = ss[0]->n_bsj + C_NUM;
+    for (int i = 0; i < n; ++i) {
+        if (!ss[i]) CG_FAIL(CG_ERR_ARG, "null session");
+        if (ss[i]->pending) CG_FAIL(CG_ERR_STATE, "fetch the pending batch of every session first");
+        if (ss[i]->n_bsj + C_NUM != len) CG_FAIL(CG_ERR_ARG, "the sessions count over different BSJ references");
+    }
+    // per device: the first session given is the leader, the others of that device are added into it
+    std::vector<int> devs; std::vector<cg_session*> lead;
+    for (int i = 0; i < n; ++i) {
+        size_t d = std::find(devs.begin(), devs.end(), ss[i]->device) - devs.begin();
+        if (d == devs.size()) { devs.push_back(ss[i]->device); lead.push_back(ss[i]); continue; }
+        CG_CUDA(cudaSetDevice(ss[i]->device));
+        CG_CUDA(cudaStreamSynchronize(ss[i]->stream));
+        k_acc_add<<<ss[i]->sms * 4, 256, 0, lead[d]->stream>>>(lead[d]->d_acc, ss[i]->d_acc, len);
+        CG_CUDA(cudaGetLastError());
+    }
+    if (devs.size() > 1 || getenv("CG_NCCL_ALWAYS")) {
+        if (!g_nccl.load()) CG_FAIL(CG_ERR_CUDA, "NCCL (libnccl.so.2) is not available: the all-reduce across GPUs needs it");
+        std::vector<nccl_comm_t> comm(devs.size(), nullptr);
+        CG_NCCL(g_nccl.CommInitAll(comm.data(), (int)devs.size(), devs.data()));
+        CG_NCCL(g_nccl.GroupStart());
+        for (size_t d = 0; d < devs.size(); ++d)        // in place, uint64 sum (ncclUint64 = 5, ncclSum = 0)
+            CG_NCCL(g_nccl.AllReduce(lead[d]->d_acc, lead[d]->d_acc, len, 5, 0, comm[d], lead[d]->stream));
+        CG_NCCL(g_nccl.GroupEnd());
+        for (size_t d = 0; d < devs.size(); ++d) { CG_CUDA(cudaSetDevice(devs[d])); CG_CUDA(cudaStreamSynchronize(lead[d]->stream)); }
+        for (size_t d = 0; d < devs.size(); ++d) g_nccl.CommDestroy(comm[d]);
+    }
+    // every session ends up holding the total
+    for (int i = 0; i < n; ++i) {
+        size_t d = std::find(devs.begin(), devs.end(), ss[i]->device) - devs.begin();
+        if (lead[d] == ss[i]) continue;
+        CG_CUDA(cudaSetDevice(ss[i]->device));
+        CG_CUDA(cudaMemcpyAsync(ss[i]->d_acc, lead[d]->d_acc, len * 8, cudaMemcpyDeviceToDevice, lead[d]->stream));
+    }
+    for (size_t d = 0; d < devs.size(); ++d) { CG_CUDA(cudaSetDevice(devs[d])); CG_CUDA(cudaStreamSynchronize(lead[d]->stream)); }
+    // read lengths are "the first one any worker saw": take the first non-zero
+    uint32_t wl = 0, bl = 0;
+    for (int i = 0; i < n; ++i) { if (!wl) wl = ss[i]->wt_read_len; if (!bl) bl = ss[i]->bsj_read_len; }
+    for (int i = 0; i < n; ++i) { ss[i]->wt_read_len = wl; ss[i]->bsj_read_len = bl; }
+    return CG_OK;
+}
 
 } // extern "C"

@@ -188,6 +188,13 @@ int cg_session_counters(cg_session* s, cg_counters* c, uint64_t* per_bsj, uint64
 /* device pointer of the dense accumulator [n_bsj per-BSJ counts | 8 scalar counters] as uint64, for the
  * single end-of-run all-reduce across GPUs (SURVEY.md §8 e); the caller owns the communicator */
 int cg_session_accumulator(cg_session* s, void** dptr, uint64_t* n_u64);
+/* The one collective of the path (the reference has none: its workers share one EquivalenceClassBuilder and atomics,
+ * src/Circall_bsj.cpp:402-491): all-reduce (sum) of the accumulators of `n` sessions of ONE process, on one or several devices —
+ * sessions of a device are added up on it, the per-device totals go through one ncclAllReduce (uint64, over NVLink; NCCL is bound at
+ * first use) and every session ends up holding the grand total, so that cg_session_counters on any of them returns the run's
+ * totals.  Call once, after the last fetch.  (Ranks of a multi-process job reduce cg_session_accumulator's vector through their own
+ * communicator instead: bench.py does with torch.distributed.) */
+int cg_sessions_allreduce(cg_session* const* sessions, int n);
 /* kernels launched by this session so far (bench.py gpu_launches) */
 uint64_t cg_session_launches(const cg_session* s);
 /* device / pinned-host allocation helpers (resident-input leg, pinned staging buffers of the host streamer) */

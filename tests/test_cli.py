@@ -150,6 +150,22 @@ def test_two_process_pipeline_and_fused_files(exe, tmp_path):
          "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"), "-o", fw, "-O", fb, "--batch", "1700"])
     check_wt(fw)
     check_bsj(fb)
+    # ---- several GPUs in the product (--gpus N: indices replicated, batches dealt round-robin, one all-reduce of the counters at the
+    # end): the same files, byte for byte, as one GPU — with as many devices as this box has, at most 4; on one device the run still
+    # goes through cg_sessions_allreduce (two sessions)
+    import circall_b200 as cg
+    ng = min(cg.device_count(), 4)
+    mw, mb = str(tmp_path / "mwt"), str(tmp_path / "mbs")
+    run([exe + "/circall_gpu", "fused", "-i", str(tmp_path / "txIdx"), "-b", str(tmp_path / "bsjIdx"), "-1", str(tmp_path / "r1.fq"),
+         "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"), "-o", mw, "-O", mb, "--batch", "1700", "--gpus", str(ng)])
+    check_wt(mw)
+    check_bsj(mb)
+    for d0, d1 in ((fw, mw), (fb, mb)):
+        for fn in sorted(os.listdir(d0)):
+            assert open(os.path.join(d0, fn), "rb").read() == open(os.path.join(d1, fn), "rb").read(), fn
+    p = run([exe + "/circall_gpu", "fused", "-i", str(tmp_path / "txIdx"), "-b", str(tmp_path / "bsjIdx"), "-1", str(tmp_path / "r1.fq"),
+             "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"), "-o", mw, "-O", mb, "--gpus", "99"], ok=False)
+    assert p.returncode == 1 and "devices" in p.stderr
 
 
 @pytest.mark.gpu

@@ -227,6 +227,31 @@ def test_failed_batch_leaves_no_counts(gpu_world):
     assert c2 == cw and np.array_equal(p2, pw) and cw["bsj_num_observed"] > c0["bsj_num_observed"] > 0
 
 
+def test_sessions_allreduce(gpu_world, monkeypatch):
+    """cg_sessions_allreduce: the accumulators of several sessions (one device here, every visible device when there are more; NCCL
+    forced on even for one device) sum to the counters of one session over all the reads, and every session ends up with the total."""
+    cg, T, otx, obsj, gtx, gbsj = gpu_world
+    monkeypatch.setenv("CG_NCCL_ALWAYS", "1")
+    r1, r2 = make_reads(T, 47, 9000)
+    W = cg.Session(gtx, gbsj)
+    W.run(r1, r2, want_lists=False)
+    cw, pw = W.counters()
+    nd = cg.device_count()
+    idx = [(gtx, gbsj)] + [(cg.Index.build(T.tx_text, device=d), cg.Index.build(T.bsj_text, device=d)) for d in range(1, min(nd, 4))]
+    SS = [cg.Session(*idx[i % len(idx)]) for i in range(3 * len(idx))]
+    parts = np.array_split(np.arange(r1.shape[0]), len(SS))
+    for s, ix in zip(SS, parts):
+        s.run(r1[ix], r2[ix], want_lists=False)
+    cg.allreduce_sessions(SS)
+    for s in SS:
+        c, p = s.counters()
+        for k in cw:
+            if not k.endswith("read_len"):
+                assert c[k] == cw[k], (k, c[k], cw[k])
+        assert np.array_equal(p, pw)
+    assert cw["bsj_num_mapped"] > 0 and pw.sum() > 0
+
+
 def test_batches_accumulate(gpu_world):
     """Counters are linear in the input: two half batches == one full batch."""
     cg, T, otx, obsj, gtx, gbsj = gpu_world

@@ -1,7 +1,7 @@
 // circall_b200 — drop-in executables over libcircall_gpu.so (C ABI, include/circall_gpu.h).
 //
 // One binary, dispatched on its name (or on the first argument):
-//   Circall_wt   -i TXINDEX  -1 R1.. -2 R2.. -o OUT [-p N] [--gpu D]      src/Circall_wt.cpp main :1415-1739, called at Circall_source.sh:273
+//   Circall_wt   -i TXINDEX  -1 R1.. -2 R2.. -o OUT [-p N] [--gpu D] [--gpus N]   src/Circall_wt.cpp main :1415-1739, called at Circall_source.sh:273
 //   Circall_bsj  -i BSJINDEX -1 U1.. -2 U2.. -o OUT [-p N] [--gpu D]      src/Circall_bsj.cpp,         called at Circall_source.sh:291
 //   Circall_pseudo -i PSEUDOINDEX -1 B1.. -2 B2.. -o OUT [-p N]           src/Circall_pseudo.cpp,      called at Circall_source.sh:340
 //   TxIndexer    -t FASTA -o INDEX [-k 31] [-f]                           src/TxIndexer.cpp:81-94,192-227
@@ -11,8 +11,11 @@
 // Options of the reference that do not apply (-l libtype, bias flags, ...) are accepted and ignored; a value that
 // follows an unknown option is skipped.  Errors go to stderr and exit(1) like the reference (Circall_wt.cpp:1726-1737).
 //
-// The host side streams the reads into two page-locked staging buffers and alternates two sessions, so the copy
-// and the kernels of one batch overlap the parsing and output writing of the other.
+// The host side streams the reads into page-locked staging buffers and rotates over two sessions per GPU, so the copy
+// and the kernels of one batch overlap the parsing and output writing of the others.  --gpus N (extension, SURVEY.md section 8 b / e)
+// replicates the indices on N devices (--gpu D .. D + N - 1) and deals the batches round-robin over them; the batches are fetched
+// in the order they were submitted, so the output files are the same as with one GPU, and the per-device counters meet in one
+// all-reduce at the end of the run (cg_sessions_allreduce: NCCL over NVLink).
 #include <algorithm>
 #include <cstdlib>
 #include <sys/stat.h>
@@ -27,7 +30,7 @@ void ck(int rc, const char* what) { if (rc) die(std::string(what) + ": " + cg_la
 struct Args {
     std::string index, bsj_index, out, out_bsj, fasta;
     std::vector<std::string> m1, m2;
-    int k = 31, gpu = 0, threads = 4, lce = 0;
+    int k = 31, gpu = 0, gpus = 1, threads = 4, lce = 0;
     uint64_t batch = 1u << 20;
     bool force = false;
 };
@@ -49,6 +52,7 @@ Args parse_args(int argc, char** argv, int first) {
         else if (o == "-k" || o == "--kmerSize") a.k = atoi(val().c_str());
         else if (o == "-f" || o == "--force") a.force = true;
         else if (o == "--gpu") a.gpu = atoi(val().c_str());
+        else if (o == "--gpus") a.gpus = atoi(val().c_str());
         else if (o == "--batch") a.batch = strtoull(val().c_str(), nullptr, 10);
         else if (o == "--lce-mode") a.lce = atoi(val().c_str());
         else if (o.size() > 1 && o[0] == '-') { if (i + 1 < argc && argv[i + 1][0] != '-') ++i; }   // accepted and ignored
@@ -126,9 +130,14 @@ int run_mapper(int stage, const Args& a) {
     int nd = 0;
     cg_device_count(&nd);
     if (nd == 0) die("no CUDA device: libcircall_gpu has no CPU path");
-    cg_index *tx = nullptr, *bsj = nullptr;
-    if (stage != 2) ck(cg_index_open(a.index.c_str(), a.gpu, &tx), "opening the transcript index");
-    if (stage != 1) ck(cg_index_open((stage == 2 ? a.index : a.bsj_index).c_str(), a.gpu, &bsj), "opening the BSJ index");
+    if (a.gpus < 1 || a.gpu < 0 || a.gpu + a.gpus > nd) die("--gpu / --gpus ask for devices this machine does not have (" + std::to_string(nd) + " visible)");
+    const int ND = a.gpus, NU = 2 * ND;                  // devices, work units (two sessions per device)
+    std::vector<cg_index*> txs(ND, nullptr), bsjs(ND, nullptr);
+    for (int d = 0; d < ND; ++d) {                        // the indices are replicated in every GPU's memory
+        if (stage != 2) ck(cg_index_open(a.index.c_str(), a.gpu + d, &txs[d]), "opening the transcript index");
+        if (stage != 1) ck(cg_index_open((stage == 2 ? a.index : a.bsj_index).c_str(), a.gpu + d, &bsjs[d]), "opening the BSJ index");
+    }
+    cg_index *tx = txs[0], *bsj = bsjs[0];
     const std::string out_wt = a.out, out_bsj = stage == 0 ? a.out_bsj : a.out;
     Outputs o;
     const std::string tag = std::to_string(1804289383);          // std::rand() without srand (Circall_wt.cpp:228): any unique tag works
@@ -140,11 +149,11 @@ int run_mapper(int stage, const Args& a) {
     }
     cg_opts opts; memset(&opts, 0, sizeof opts);
     opts.lce_mode = a.lce; opts.stage = stage; opts.max_batch_pairs = (uint32_t)a.batch;
-    cg_session* S[2] = {nullptr, nullptr};
-    cgh::Batch B[2];
+    std::vector<cg_session*> S(NU, nullptr);
+    std::vector<cgh::Batch> B(NU);
     const uint64_t cap = std::max<uint64_t>(a.batch * 160, 1u << 20);
-    for (int x = 0; x < 2; ++x) {
-        ck(cg_session_create(tx, bsj, &opts, &S[x]), "creating a session");
+    for (int x = 0; x < NU; ++x) {                       // unit x lives on device x % ND: consecutive batches go to different GPUs
+        ck(cg_session_create(txs[x % ND], bsjs[x % ND], &opts, &S[x]), "creating a session");
         void *p1, *p2;
         ck(cg_host_alloc(cap, &p1), "allocating pinned memory"); ck(cg_host_alloc(cap, &p2), "allocating pinned memory");
         B[x].b1 = (char*)p1; B[x].b2 = (char*)p2; B[x].cap = cap;
@@ -152,12 +161,12 @@ int run_mapper(int stage, const Args& a) {
     cgh::PairStream in(a.m1, a.m2);
     uint64_t pairs = 0;
     int cur = 0;
-    bool pending[2] = {false, false};
+    std::vector<char> pending(NU, 0);
     auto finish = [&](int x) {
         cg_batch_result r;
         ck(cg_session_fetch(S[x], 1, &r), "mapping a batch");
         emit(stage, B[x], r, bsj, o);
-        pending[x] = false;
+        pending[x] = 0;
     };
     try {
         for (;;) {
@@ -170,27 +179,21 @@ int run_mapper(int stage, const Args& a) {
                 fixed = B[cur].off1[i + 1] - B[cur].off1[i] == len && B[cur].off2[i + 1] - B[cur].off2[i] == len;
             if (fixed) ck(cg_session_submit_fixed(S[cur], B[cur].b1, B[cur].b2, B[cur].n, (uint32_t)len), "submitting a batch");
             else ck(cg_session_submit(S[cur], B[cur].b1, B[cur].off1.data(), B[cur].b2, B[cur].off2.data(), B[cur].n), "submitting a batch");
-            pending[cur] = true;
+            pending[cur] = 1;
             pairs += B[cur].n;
-            cur ^= 1;
+            cur = (cur + 1) % NU;
         }
     } catch (const std::string& e) { die(e); }
-    for (int x = 0; x < 2; ++x) if (pending[x ^ cur]) finish(x ^ cur);
+    for (int x = 0; x < NU; ++x) if (pending[(x + cur) % NU]) finish((x + cur) % NU);      // oldest first: the files keep the input order
 
-    // totals of the two sessions -> fragmentInfo.txt / rawCount.txt (ExportFeq.cpp:46-105)
+    // totals -> fragmentInfo.txt / rawCount.txt (ExportFeq.cpp:46-105): one all-reduce over every session of every device, after
+    // which any session holds them
     cg_index_info bi; memset(&bi, 0, sizeof bi);
     if (bsj) cg_index_get_info(bsj, &bi);
-    std::vector<uint64_t> per(bi.n_tx, 0), tmp(bi.n_tx, 0);
+    std::vector<uint64_t> per(bi.n_tx, 0);
     cg_counters tot; memset(&tot, 0, sizeof tot);
-    for (int x = 0; x < 2; ++x) {
-        cg_counters c;
-        ck(cg_session_counters(S[x], &c, bsj ? tmp.data() : nullptr, bsj ? bi.n_tx : 0), "reading the counters");
-        tot.wt_num_observed += c.wt_num_observed; tot.wt_num_mapped += c.wt_num_mapped; tot.wt_num_hits += c.wt_num_hits;
-        tot.bsj_num_observed += c.bsj_num_observed; tot.bsj_num_mapped += c.bsj_num_mapped; tot.bsj_num_hits += c.bsj_num_hits;
-        if (!tot.wt_read_len) tot.wt_read_len = c.wt_read_len;
-        if (!tot.bsj_read_len) tot.bsj_read_len = c.bsj_read_len;
-        for (uint32_t t = 0; t < bi.n_tx; ++t) per[t] += tmp[t];
-    }
+    ck(cg_sessions_allreduce(S.data(), NU), "reducing the counters");
+    ck(cg_session_counters(S[0], &tot, bsj ? per.data() : nullptr, bsj ? bi.n_tx : 0), "reading the counters");
     cgh::FragPrior fp;
     cg_index_info ti; memset(&ti, 0, sizeof ti);
     if (tx) cg_index_get_info(tx, &ti);
@@ -217,9 +220,8 @@ int run_mapper(int stage, const Args& a) {
     if (stage != 2) fprintf(stderr, "; wt: observed %llu mapped %llu hits %llu", (unsigned long long)tot.wt_num_observed, (unsigned long long)tot.wt_num_mapped, (unsigned long long)tot.wt_num_hits);
     if (stage != 1) fprintf(stderr, "; bsj: observed %llu mapped %llu hits %llu", (unsigned long long)tot.bsj_num_observed, (unsigned long long)tot.bsj_num_mapped, (unsigned long long)tot.bsj_num_hits);
     fprintf(stderr, "\n");
-    for (int x = 0; x < 2; ++x) { cg_session_destroy(S[x]); cg_host_free(B[x].b1); cg_host_free(B[x].b2); }
-    if (tx) cg_index_close(tx);
-    if (bsj) cg_index_close(bsj);
+    for (int x = 0; x < NU; ++x) { cg_session_destroy(S[x]); cg_host_free(B[x].b1); cg_host_free(B[x].b2); }
+    for (int d = 0; d < ND; ++d) { if (txs[d]) cg_index_close(txs[d]); if (bsjs[d]) cg_index_close(bsjs[d]); }
     return 0;
 }
 
