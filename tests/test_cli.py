@@ -162,7 +162,10 @@ def test_two_process_pipeline_and_fused_files(exe, tmp_path):
     check_bsj(mb)
     for d0, d1 in ((fw, mw), (fb, mb)):
         for fn in sorted(os.listdir(d0)):
-            assert open(os.path.join(d0, fn), "rb").read() == open(os.path.join(d1, fn), "rb").read(), fn
+            a, b = open(os.path.join(d0, fn), "rb").read(), open(os.path.join(d1, fn), "rb").read()
+            if d0 == fb and fn.startswith("UN_read1_"):          # junction rows of a batch come out in the order the warps finished
+                a, b = sorted(a.split(b"\n")), sorted(b.split(b"\n"))
+            assert a == b, fn
     p = run([exe + "/circall_gpu", "fused", "-i", str(tmp_path / "txIdx"), "-b", str(tmp_path / "bsjIdx"), "-1", str(tmp_path / "r1.fq"),
              "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"), "-o", mw, "-O", mb, "--gpus", "99"], ok=False)
     assert p.returncode == 1 and "devices" in p.stderr
