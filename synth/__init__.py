@@ -41,6 +41,8 @@ def _lib():
         for f in (L.syn_tx_name, L.syn_bsj_name):
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int]
+        L.syn_gene_exons.restype = ctypes.c_int
+        L.syn_gene_exons.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.syn_reads.restype = None
         L.syn_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                 ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
@@ -85,6 +87,13 @@ class Txome:
         b = ctypes.create_string_buffer(128)
         _lib().syn_bsj_name(self._h, i, b, 128)
         return b.value.decode()
+
+    def gene_exons(self, g):
+        """[(start, end)] of gene g's exons in the coordinates of the BSJ reference names (1-based, inclusive)"""
+        st = np.zeros(32, np.uint64)
+        en = np.zeros(32, np.uint64)
+        n = _lib().syn_gene_exons(self._h, g, st.ctypes.data, en.ctypes.data, 32)
+        return [(int(st[i]), int(en[i])) for i in range(n)]
 
     def reads(self, seed, n_pairs, L=100, frag_mean=250.0, frag_sd=25.0, err=0.005, circ_frac=0.01, n_rate=0.0,
               junk_frac=0.0, first=0, truth=False, nthreads=None, out=None):

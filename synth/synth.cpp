@@ -281,6 +281,16 @@ int syn_bsj_name(void* h, uint32_t i, char* buf, int cap) {
     return snprintf(buf, cap, "chrS__%llu__%llu__G%06u__%u__%u", s, e, g, g * 100 + T->bsj_exs[i], g * 100 + T->bsj_exe[i]);
 }
 
+// exons of gene g in genome coordinates (1-based, inclusive, like the coordinates in the BSJ names): returns their number
+int syn_gene_exons(void* h, uint32_t g, uint64_t* starts, uint64_t* ends, int cap) {
+    auto* T = (Txome*)h;
+    if (g >= T->genes.size()) return 0;
+    const Gene& G = T->genes[g];
+    int n = (int)G.es.size();
+    for (int i = 0; i < n && i < cap; ++i) { starts[i] = G.goff + G.es[i] + 1; ends[i] = G.goff + G.ee[i] + 1; }
+    return n;
+}
+
 // fixed-length reads: r1/r2 are n_pairs*L byte arrays; truth (optional) = 3 int32 per pair:
 // kind (0 linear, 1 back-spliced, 2 junk; +16 if the fragment was read from the other strand), id, pos
 void syn_reads(void* h, uint64_t seed, uint64_t first, uint64_t n_pairs, uint32_t L, double frag_mean, double frag_sd,

@@ -21,6 +21,10 @@ def build(force=False):
     if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(s) for s in srcs + [lib]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", srcs[0], "-o", exe, "-L" + os.path.dirname(lib), "-lcircall_gpu",
                                "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath-link,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+    # the R stage's joins (SE / PE filters, final table) as a host-only tool
+    flt, fsrc = os.path.join(out, "circall_filter"), os.path.join(HERE, "circall_filter.cpp")
+    if force or not os.path.exists(flt) or os.path.getmtime(flt) < os.path.getmtime(fsrc):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", fsrc, "-o", flt])
     for name in ("Circall_wt", "Circall_bsj", "Circall_pseudo", "TxIndexer"):
         p = os.path.join(out, name)
         if not os.path.islink(p):
