@@ -41,6 +41,21 @@ def test_parse_fasta_fastq_mix(exe, tmp_path):
     assert p.returncode == 1
 
 
+def test_fragment_length_prior_columns(exe):
+    """Row A11: the floating-point columns the executables write (fragLengthMedian / Mean / Sd of fragmentInfo.txt, effLens /
+    EffectiveLength of rawCount.txt) follow the reference's never-updated normal prior; pinned against oracle/r_fld.py, a restatement of
+    getNormalFragLengthCounts + EmpiricalDistribution::buildDistribution + computeSmoothedEffectiveLengths (unpinned: no reference run)."""
+    from oracle import r_fld
+    lens = [31, 100, 150, 298, 999, 1000, 5000]
+    out = run([exe + "/circall_gpu", "fld"] + [str(x) for x in lens]).stdout.split("\n")
+    med, mean, sd = (r_fld._f32(float(out[0].split()[i])) for i in (1, 3, 5))      # printed with 9 digits: enough to name the float
+    assert (med, mean, sd) == r_fld.empirical(r_fld.normal_counts())           # float values, bit for bit
+    assert 190 < mean < 210 and 70 < sd < 85
+    f = r_fld.correction_factors()
+    for ln, line in zip(lens, out[1:]):
+        assert abs(float(line.split()[2]) - r_fld.effective_length(ln, f)) <= 1e-9 * ln
+
+
 def _fasta(path, names, text):
     s = bytes(text).decode()
     with open(path, "w") as f:

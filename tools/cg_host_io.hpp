@@ -142,34 +142,54 @@ inline void put_record(FILE* f, const std::string& header_with_marker, const cha
 // (Circall_bsj.cpp:832-861: mean 200, sd 80, 10 000 samples over 1000 bins) and the conditional means behind
 // computeSmoothedEffectiveLengths (:977-1006).  These columns are constants of a run and not read downstream.
 struct FragPrior {
-    std::vector<int> counts;
-    std::vector<double> cond_mean;
-    double median = 0, mean = 0, sd = 0;
-    FragPrior(int maxLen = 1000, int samples = 10000, double mu = 200.0, double sigma = 80.0) : counts(maxLen, 0), cond_mean(maxLen, 0.0) {
+    // Nobody decrements remainingFLOps in Circall_wt / Circall_bsj, so both tools always take the normal prior (mean 200, sd 80, 10 000
+    // samples over 1000 lengths; src/Circall_bsj.cpp:1171-1181 and its options :1350,1374-1381):
+    //   counts   getNormalFragLengthCounts (:832-861)          -> ReadExperiment::setFragLengthDist (include/ReadExperiment.hpp:189-196)
+    //            -> EmpiricalDistribution::buildDistribution (src/EmpiricalDistribution.cpp:36-113): median / mean / sd of fragmentInfo.txt,
+    //               handed out as float (:128-146)
+    //   factors  getNormalFragLengthDist (:805-830), from the kernel itself, not from the rounded counts -> computeSmoothedEffectiveLengths
+    //            (:977-1006): the effLens / EffectiveLength columns of rawCount.txt
+    std::vector<uint32_t> counts;
+    std::vector<double> factors;
+    float median = 0, mean = 0, sd = 0;
+    FragPrior(int maxLen = 1000, int samples = 10000, size_t mu = 200, size_t sigma = 80) : counts(maxLen, 0), factors(maxLen, 0.0) {
         auto kernel = [&](double p) { double inv = 1.0 / sigma, x = inv * (p - mu); return std::exp(-0.5 * x * x) * inv; };
         double mass = 0;
-        for (int i = 0; i < maxLen; ++i) mass += kernel(i);
-        for (int i = 0; i < maxLen; ++i) counts[i] = (int)std::round(kernel(i) * samples / mass);
-        double tot = 0, s1 = 0;
-        for (int i = 0; i < maxLen; ++i) { tot += counts[i]; s1 += (double)counts[i] * i; }
-        mean = tot > 0 ? s1 / tot : 0;
-        double s2 = 0, cum = 0;
-        bool med = false;
-        for (int i = 0; i < maxLen; ++i) {
-            s2 += counts[i] * (i - mean) * (i - mean);
-            cum += counts[i];
-            if (!med && cum >= tot / 2) { median = i; med = true; }
-        }
-        sd = tot > 0 ? std::sqrt(s2 / tot) : 0;
+        for (int i = 0; i < maxLen; ++i) mass += kernel((double)i);
+        if (mass > 0) for (int i = 0; i < maxLen; ++i) counts[i] = (uint32_t)(int)std::round(kernel((double)i) * samples / mass);
         double cm = 0, cd = 0;
-        for (int i = 0; i < maxLen; ++i) {
-            cm += (double)counts[i] * i; cd += counts[i];
-            cond_mean[i] = cd > 0 ? cm / cd : 0.0;
+        for (int i = 0; i < maxLen; ++i) {                          // :819-828
+            const double d = kernel((double)i);
+            cm += i * d; cd += d;
+            if (cd > 0) factors[i] = cm / cd;
         }
+        // EmpiricalDistribution::buildDistribution with vals = 0 .. maxLen - 1, lens = counts
+        const size_t n = counts.size();
+        double valsum = 0;
+        for (size_t i = 0; i < n; ++i) valsum += counts[i];
+        double cumpr = 0;
+        unsigned lastval = 0;
+        for (; lastval < n; ++lastval) { cumpr += counts[lastval] / valsum; if (cumpr > 1.0 - 1e-6) break; }      // :52-59
+        const unsigned upper = std::min<unsigned>(lastval + 1, (unsigned)n);
+        valsum = 0;
+        for (unsigned i = 0; i < upper; ++i) valsum += counts[i];
+        std::vector<double> pdf(upper);
+        for (unsigned v = 0; v < upper; ++v) pdf[v] = counts[v] / valsum;                                           // :68-78 (vals[i] == i)
+        double m = 0;
+        for (unsigned v = 1; v < upper; ++v) m += v * pdf[v];                                                       // :82-86
+        double s2 = 0;
+        for (unsigned i = 0; i < upper; ++i) s2 += (i - m) * (i - m) * pdf[i];                                      // :90-94
+        size_t i = 0, j = n - 1;                                                                                    // :98-110: the median walks in from both ends
+        unsigned u = counts[0], v = counts[n - 1];
+        while (i < j) {
+            if (u <= v) { v -= u; u = counts[++i]; }
+            else { u -= v; v = counts[--j]; }
+        }
+        median = (float)i; mean = (float)m; sd = (float)std::sqrt(s2);
     }
-    double effective_length(uint32_t refLen) const {
-        int maxLen = (int)cond_mean.size();
-        double cf = (int)refLen >= maxLen ? cond_mean[maxLen - 1] : cond_mean[refLen];
+    double effective_length(uint32_t refLen) const {               // :990-1003
+        int maxLen = (int)factors.size();
+        double cf = (int)refLen >= maxLen ? factors[maxLen - 1] : factors[refLen];
         double e = (double)refLen - cf + 1.0;
         return e < 1.0 ? (double)refLen : e;
     }

@@ -8,6 +8,7 @@
 //   circall_gpu fused -i TXINDEX -b BSJINDEX -1 .. -2 .. -o OUTWT -O OUTBSJ   (extension: both steps in one pass, no
 //                intermediate Unmapped_readM_{1,2}.fa; the two output directories receive what the two tools write)
 //   circall_gpu parse -1 .. -2 ..          (no GPU: parses the inputs and prints record counts; used by the CPU tests)
+//   circall_gpu fld LEN..                  (no GPU: the fragment-length prior's fragmentInfo.txt columns and effective lengths)
 // Options of the reference that do not apply (-l libtype, bias flags, ...) are accepted and ignored; a value that
 // follows an unknown option is skipped.  Errors go to stderr and exit(1) like the reference (Circall_wt.cpp:1726-1737).
 //
@@ -301,6 +302,15 @@ int run_indexer(const Args& a) {
     return 0;
 }
 
+// circall_gpu fld LEN...: the fragment-length prior's columns of fragmentInfo.txt and the effective length of references of the given
+// lengths (no GPU; tests/test_cli.py pins them against a restatement of EmpiricalDistribution.cpp)
+int run_fld(int argc, char** argv, int first) {
+    cgh::FragPrior fp;
+    printf("median %.9g mean %.9g sd %.9g\n", (double)fp.median, (double)fp.mean, (double)fp.sd);
+    for (int i = first; i < argc; ++i) printf("efflen %s %.17g\n", argv[i], fp.effective_length((uint32_t)strtoul(argv[i], nullptr, 10)));
+    return 0;
+}
+
 int run_parse(const Args& a) {
     cgh::Batch B;
     std::vector<char> b1(1 << 24), b2(1 << 24);
@@ -330,6 +340,7 @@ int main(int argc, char** argv) {
     else if (me == "Circall_pseudo") cmd = "pseudo";
     else if (me == "TxIndexer") cmd = "index";
     else { if (argc < 2) die("usage: circall_gpu {wt|bsj|fused|pseudo|index|parse} options..."); cmd = argv[1]; first = 2; }
+    if (cmd == "fld") return run_fld(argc, argv, first);
     Args a = parse_args(argc, argv, first);
     if (cmd == "wt") return run_mapper(1, a);
     if (cmd == "bsj") return run_mapper(2, a);
