@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--e2e-offsets", action="store_true", help="end-to-end leg through cg_session_submit (offset arrays copied with the reads) instead of cg_session_submit_fixed")
     ap.add_argument("--numa-affinity", action="store_true", help="experiment: bind the rank to the CPUs local to its GPU before the page-locked buffers are allocated")
     ap.add_argument("--e2e-no-lists", action="store_true", help="experiment: the end-to-end leg without the per-record result lists (counts only)")
+    ap.add_argument("--resident-sessions", type=int, default=1, help="sessions the device-resident leg deals its batches to (each on its own stream: the short-list tail kernels of one overlap the thread tiers of the others); the step is cut into that many batches unless --batch is smaller")
     ap.add_argument("--sessions", type=int, default=4, help="sessions alternated by the end-to-end leg (copies of one overlap kernels of the others)")
     args = ap.parse_args()
     _claim_stdout()
@@ -280,7 +281,8 @@ def main():
     pin1, pin2 = cg.PinnedBuffer(n * L), cg.PinnedBuffer(n * L)
     r1, r2 = pin1.array.reshape(n, L), pin2.array.reshape(n, L)
     T.reads(cfg["read_seed"], n, L=L, frag_mean=cfg["frag_mean"], frag_sd=cfg["frag_sd"], circ_frac=cfg["circ_frac"], first=rank * n, out=(r1, r2))
-    batch = min(args.batch, n)
+    RS = max(1, args.resident_sessions)
+    batch = min(args.batch, (n + RS - 1) // RS)
     off = np.arange(batch + 1, dtype=np.uint64) * np.uint64(L)
     pinoff = cg.PinnedBuffer(off.nbytes); pinoff.array[:] = off.view(np.uint8)
     d1, d2, doff = cg.DeviceBuffer(n * L + 64, local), cg.DeviceBuffer(n * L + 64, local), cg.DeviceBuffer(off.nbytes, local)
@@ -288,6 +290,7 @@ def main():
     batches = [(b0, min(batch, n - b0)) for b0 in range(0, n, batch)]
 
     S = cg.Session(gtx, gbsj, stage=0)
+    RSS = [S] + [cg.Session(gtx, gbsj, stage=0) for _ in range(RS - 1)]
     accp, accn = S.accumulator()
 
     def acc_tensor(sess):
@@ -297,16 +300,22 @@ def main():
             __cuda_array_interface__ = {"shape": (nn,), "typestr": "<i8", "data": (p, False), "version": 3}
         return torch.as_tensor(_Acc(), device=torch.device("cuda", local))
     acc_t = acc_tensor(S) if world > 1 else None
+    acc_rs = [acc_tensor(x) for x in RSS[1:]] if world > 1 else []
     reduced = torch.empty(accn, dtype=torch.int64, device=torch.device("cuda", local)) if world > 1 else None
 
     def step_resident(stats=None):
-        for b0, nb in batches:
-            S.submit_device(d1.ptr + b0 * L, doff.ptr, d2.ptr + b0 * L, doff.ptr, nb, L)
-            B = S.fetch(want_lists=False)
-            if stats is not None:
-                stats.append(B)
+        for i0 in range(0, len(batches), RS):
+            grp = batches[i0:i0 + RS]
+            for sess, (b0, nb) in zip(RSS, grp):
+                sess.submit_device(d1.ptr + b0 * L, doff.ptr, d2.ptr + b0 * L, doff.ptr, nb, L)
+            for sess, _ in zip(RSS, grp):
+                B = sess.fetch(want_lists=False)
+                if stats is not None:
+                    stats.append(B)
         if world > 1:   # the one collective of the path: per-BSJ count vector + scalar counters (SURVEY §8 e)
             reduced.copy_(acc_t)
+            for t in acc_rs:
+                reduced.add_(t)
             dist.all_reduce(reduced)
 
     def bracket(fn, k):
@@ -332,9 +341,9 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     stats = []
-    l0 = S.launches
+    l0 = sum(x.launches for x in RSS)
     dt = bracket(lambda: step_resident(stats), args.steps)
-    launches = S.launches - l0
+    launches = sum(x.launches for x in RSS) - l0
     clk = clocks.stop()
     ms_step = 1e3 * dt / args.steps
     value = world * n / (ms_step * 1e-3)
@@ -347,9 +356,9 @@ def main():
     # ---- end to end through the C ABI from pinned host buffers, two sessions so copies overlap kernels
     e2e = None
     if not args.no_e2e:
-        SS = [S] + [cg.Session(gtx, gbsj, stage=0) for _ in range(max(1, args.sessions) - 1)]
+        SS = RSS + [cg.Session(gtx, gbsj, stage=0) for _ in range(max(1, args.sessions) - len(RSS))]
         NS = len(SS)
-        acc_all = [acc_t] + [acc_tensor(x) for x in SS[1:]] if world > 1 else []
+        acc_all = [acc_t] + acc_rs + [acc_tensor(x) for x in SS[len(RSS):]] if world > 1 else []
         ebatch = min(args.e2e_batch, batch)
         # submit sizes ramp up (and down at the end): the copy of the very first submit and the read-back of the very last one
         # cannot overlap anything, so they are kept short
@@ -395,7 +404,7 @@ def main():
                "call": "cg_session_submit" if args.e2e_offsets else "cg_session_submit_fixed"}
         if affinity:
             e2e["cpu_affinity"] = affinity
-        for x in SS[1:]:
+        for x in SS[len(RSS):]:
             x.close()
     if affinity:
         os.sched_setaffinity(0, all_cpus)                    # the cpu_baseline leg gets every host thread back
@@ -471,7 +480,8 @@ def main():
                 "device_ms_per_step": dev_ms, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                 "counters": {k: int(v) for k, v in ctr.items()}}
         _emit(line)
-    S.close()
+    for x in RSS:
+        x.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

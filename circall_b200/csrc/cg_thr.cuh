@@ -50,6 +50,15 @@
 namespace cgq {
 using namespace cg;
 
+#if defined(CG_HOST_EMU)
+// tests/emu: what one read costs, by operation (0 loop trips, 1 filter stages, 2 table rounds, 3 suffixes extended, 4 q_match word steps, 5 lce word
+// steps, 6 q_tids4 calls, 7 span-filter chunks)
+static uint32_t g_cost[8];
+#define CG_COST(i, n) (g_cost[i] += (uint32_t)(n))
+#else
+#define CG_COST(i, n) ((void)0)
+#endif
+
 static const int QW = CG_THR_WALK;
 #ifndef CG_THR_EXT
 #define CG_THR_EXT 4       // suffixes per round of the extension
@@ -99,6 +108,7 @@ CG_HDN int q_match(const u32x4* text, M m, int s, int q, uint32_t p, int i0, int
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
     cgt::u32x2 mk; mk.x = mk.y = 0;
     while (i < lim) {
+        CG_COST(4, 1);
         const uint32_t tp = p + (uint32_t)i, b = tp >> 6;
         if (b != curb) { cc = CG_LDG(&text[2 * (uint64_t)b]); mk = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b + 1])); curb = b; }
         const int half = (tp >> 5) & 1, o5 = tp & 31;
@@ -125,6 +135,7 @@ CG_HDN int q_lce(const u32x4* text, uint32_t n_text, uint32_t o1, uint32_t o2, i
     u32x4 c1, c2; c1.x = c1.y = c1.z = c1.w = 0; c2 = c1;
     cgt::u32x2 m1, m2; m1.x = m1.y = 0; m2 = m1;
     while (len < lim) {
+        CG_COST(5, 1);
         const uint32_t a = o1 + (uint32_t)len, b = o2 + (uint32_t)len;
         if ((a >> 6) != b1c) { b1c = a >> 6; c1 = CG_LDG(&text[2 * (uint64_t)b1c]); m1 = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b1c + 1])); }
         if ((b >> 6) != b2c) { b2c = b >> 6; if (b2c == b1c) { c2 = c1; m2 = m1; } else { c2 = CG_LDG(&text[2 * (uint64_t)b2c]); m2 = CG_LDG(reinterpret_cast<const cgt::u32x2*>(&text[2 * (uint64_t)b2c + 1])); } }
@@ -171,46 +182,94 @@ CG_HDN u32x4 q_resolve_from(const u32x4* hslots, uint64_t hmask, uint64_t key, u
 // homopolymer (a homopolymer fm-mer is never used as evidence), so the positions visited, the first hit and the homopolymer
 // decline are those of the unfiltered walk.
 #if defined(CG_HOST_EMU)
-struct WalkStats { uint64_t filter_loads = 0, table_loads = 0, dead_windows = 0; };     // tests/emu: what the walks of a run cost
+struct WalkStats { uint64_t filter_loads = 0, table_loads = 0, dead_windows = 0, calls = 0, rounds = 0, found = 0, hist[24] = {0}; };     // tests/emu: what the walks of a run cost
 static WalkStats g_walk;
 #define CG_WALK_STAT(f, n) (g_walk.f += (uint64_t)(n))
+struct WalkScope { int r = 0; ~WalkScope() { g_walk.calls += 1; g_walk.rounds += (uint64_t)r; g_walk.hist[r < 23 ? r : 23] += 1; } };
+#define CG_WALK_SCOPE WalkScope walk_scope_
+#define CG_WALK_ROUND (++walk_scope_.r, CG_COST(2, 1))
 #else
+#define CG_WALK_SCOPE ((void)0)
+#define CG_WALK_ROUND ((void)0)
 #define CG_WALK_STAT(f, n) ((void)0)
 #endif
-static const int Q_NP = 3;        // seed-filter look-ups per stage (cg::fm_for_k keeps Q_NP * S + 1 below 64 windows)
+// Geometry of a filter stage: Q_NP fm-mers at o0 + Q_D0 + Q_SP j, all in flight together.  An fm-mer at p is part of the windows p - S .. p
+// (S = k - fm), so the stage decides the windows o0 .. o0 + Q_D0 + Q_SP (Q_NP - 1); the table stage then goes on over Q_TAIL more windows
+// taken as alive (the window after a run of dead ones is the one a walk usually ends on: no second stage for it).
+#ifndef CG_THR_FNP
+#define CG_THR_FNP 6       // measured (k_wt_thr / k_bsj_thr, ms per 4 M pairs of config 2): 3 fm-mers S apart 3.10 / 5.56, 6 fm-mers S / 3 apart 2.84 / 5.03, 4 fm-mers S / 2 apart
+                           // in between: with S = 15 a stage of 6 decides 31 windows — the windows that cover one substitution — and a window holds three of the
+                           // fm-mers, so the stretches where the read enters a region of the text (fm-mers present, k-mers not yet) leave 5 windows alive instead of 15
+#endif
+#ifndef CG_THR_FD0
+#define CG_THR_FD0 0       // 0: S / CG_THR_FDIV
+#endif
+#ifndef CG_THR_FSP
+#define CG_THR_FSP 0       // 0: S / CG_THR_FDIV
+#endif
+#ifndef CG_THR_FDIV
+#define CG_THR_FDIV 3
+#endif
+#ifndef CG_THR_FTAIL
+#define CG_THR_FTAIL 0
+#endif
+#if defined(CG_HOST_EMU)
+static const int Q_NP = 8;
+#else
+static const int Q_NP = CG_THR_FNP;        // seed-filter look-ups per stage (Q_D0 + Q_SP (Q_NP - 1) + Q_TAIL + 1 windows must fit 64 bits)
+#endif
+#if defined(CG_HOST_EMU)
+static int Q_D0X = CG_THR_FD0, Q_SPX = CG_THR_FSP, Q_TAIL = CG_THR_FTAIL, Q_NPR = CG_THR_FNP, Q_DIV = CG_THR_FDIV;      // tests/emu sweeps them (Q_NPR <= Q_NP)
+#else
+static const int Q_D0X = CG_THR_FD0, Q_SPX = CG_THR_FSP, Q_TAIL = CG_THR_FTAIL, Q_NPR = CG_THR_FNP, Q_DIV = CG_THR_FDIV;
+#endif
 template <class M>
 CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, bool both, QProbe& F, bool& hasR, bool& homo) {
     const int k = ix.k;
     const int sh = both ? 1 : 0, per = QW >> sh;
     const int fm = ix.fm, S = k - fm;
+    const int Q_D0 = Q_D0X > 0 ? Q_D0X : cmax(1, S / Q_DIV), Q_SP = Q_SPX > 0 ? Q_SPX : cmax(1, S / Q_DIV);
     F.f = false; F.b = F.e = 0; hasR = false;
+    CG_WALK_SCOPE;
+    // ONE loop, one filter stage and one table round per trip at most, so that the lanes of a warp that are inside a walk do their
+    // rounds together (with the table rounds in a loop of their own under the stages, and a trip of that loop spent on skipping the
+    // windows the filter settled, the rounds of different lanes fell into different trips: 3.8 active lanes in a round, ncu r2j)
+    const bool usef = fm && Q_D0 + Q_SP * (Q_NPR - 1) + Q_TAIL + QW < 64;
+    int o0 = o, hi = usef ? o - 1 : lim;                     // the windows o0 .. hi are decided (dead bit j = window o0 + j is certainly not in the table)
+    uint64_t dead = 0;
     while (o <= lim) {
-        // ---- filter stage: dead bit j = window o0 + j is certainly not in the table
-        const int o0 = o;
-        uint64_t dead = 0;
-        int hi = lim;
-        if (fm) {
+        if (usef && o > hi) {                                // ---- filter stage
+            o0 = o; dead = 0;
+            CG_COST(1, 1);
             const uint32_t fmk = fm_mask(fm);
             uint32_t x[Q_NP], wv[Q_NP];
 #pragma unroll
             for (int j = 0; j < Q_NP; ++j) {
-                const int p = o0 + S * (j + 1);                                // this fm-mer lies inside the windows o0 + S j .. p
+                const int p = o0 + Q_D0 + Q_SP * j;                            // this fm-mer lies inside the windows p - S .. p
                 x[j] = 0; wv[j] = 0xffffffffu;
-                if (p + fm <= L && o0 + S * j <= lim) {
+                if (j < Q_NPR && p + fm <= L && p - S <= lim) {
                     const int wb = (s ? 2 * m.W2 : 0) + (p >> 4);
                     x[j] = cgt::fsr(m.ld(wb), m.ld(wb + 1), (p & 15) * 2) & fmk;
                     if (!fm_homopolymer(x[j], fm)) { wv[j] = CG_LDG(&ix.fbits[x[j] >> 5]); CG_WALK_STAT(filter_loads, 1); }
                 }
             }
+            const uint64_t full = (2ULL << S) - 1ULL;
 #pragma unroll
-            for (int j = 0; j < Q_NP; ++j) if (!((wv[j] >> (x[j] & 31)) & 1u)) dead |= ((2ULL << S) - 1ULL) << (S * j);
-            hi = cmin(lim, o0 + Q_NP * S);
+            for (int j = 0; j < Q_NP; ++j)
+                if (!((wv[j] >> (x[j] & 31)) & 1u)) { const int lo = Q_D0 + Q_SP * j - S; dead |= lo >= 0 ? full << lo : full >> -lo; }
+            hi = cmin(lim, o0 + Q_D0 + Q_SP * (Q_NPR - 1) + Q_TAIL);
         }
-        // ---- table stage over the windows of [o0, hi] that are still alive
-        while (o <= hi) {
-            const uint64_t dm = dead >> (o - o0);
-            if (dm & 1ULL) { const int sk = ctz64(~dm); CG_WALK_STAT(dead_windows, cmin(sk, hi - o + 1)); o += sk; continue; }
+        // ---- table round over the next windows that are still alive
+        {
+            const uint64_t dm0 = usef ? dead >> (o - o0) : 0ULL;
+            const int sk = ctz64(~dm0);                       // windows the filter settled (bits past the decided range are 0)
+            CG_WALK_STAT(dead_windows, cmin(sk, hi - o + 1));
+            o += sk;
+        }
+        if (o <= hi) {
+            const uint64_t dm = usef ? dead >> (o - o0) : 0ULL;
             uint64_t key[QW]; u32x4 sl[QW]; uint32_t hs[QW];
+            CG_WALK_ROUND;
             // the (at most) QW windows of this round start within QW bases of each other: they are cut out of four words of the
             // strand read once, instead of three scratch loads per window
             const int wb = (s ? 2 * m.W2 : 0) + (o >> 4), sh0 = (o & 15) * 2;
@@ -291,21 +350,32 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
     return -1;
 }
 
-// SACollectorCircall::operator() up to and including the strand vote.
+// SACollectorCircall::operator() up to and including the strand vote, as three pieces so that a kernel can run the segments of
+// different reads side by side (k_*_thr keep their lanes busy: a lane that finishes a read takes the next one while its neighbours
+// are still inside theirs — the loop below is the ONLY loop of those kernels): q_begin (the four up-front look-ups), q_step (one
+// trip of the reference's scan loops: LOOK -> EXTEND -> LCE -> next position), q_vote (:442-490).  q_collect strings them together
+// for one read (host emulation, cg_collect).
 //   VOTE = false: reads whose hits lie on one strand (a look-up that scores for the other strand declines the read)
 //   VOTE = true : both strands — Phase B then Phase C when rcHit >= fwdHit (:332), the kmerScores list and its vote (:442-490)
 // Returns Q_FOUND (nF / nR post-vote intervals in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.
 // known: which of the four up-front k-mers are in the table, as the kernel in front of this tier already found out (bit 0 read[0,k),
 // bit 1 its reverse complement, bit 2 read[L-k,L), bit 3 its reverse complement; the look-up class minus one) — an absent one is
 // not looked up again; < 0: not known.
+enum { Q_CONT = 2, Q_DONE = 3 };
+struct QState {
+    QProbe F0, R0, FL, RL;            // read[0,k), its reverse complement, read[L-k,L), its reverse complement
+    int L, s, o, nKS, nF, nR;
+    uint32_t fwdHit, rcHit;
+    bool phaseA, firstB, aOther, expectAbsent, lastSearch;
+};
+
 template <bool VOTE>
-CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, int& nF, int& nR, int known = -1) {
-    const int k = ix.k, skipOverlap = k - 1;
-    nF = nR = 0;
+CG_HD int q_begin(const IndexView& ix, const QMemT<VOTE>& m, int L, int known, QState& st) {
+    const int k = ix.k;
+    st.L = L; st.nF = st.nR = 0;
     if (L > 0xffff) return QD_ODD;
     if (!(k < L)) return Q_NOTFOUND;       // Phase A's loop needs rb + k < L (:112)
     // the four look-ups every path starts with: read[0,k), read[L-k,L) and their reverse complements
-    QProbe F0, R0, FL, RL;
     {
         const uint64_t mer0 = m.chunk(0, 0) & ix.km, merL = m.chunk(0, L - k) & ix.km;
         if (homopolymer_ix(mer0, ix) || homopolymer_ix(merL, ix)) return QD_HOMO;
@@ -317,150 +387,164 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
         if (known < 0 || (known & 2)) s1 = CG_LDG(&ix.hslots[h1]);
         if (known < 0 || (known & 4)) s2 = CG_LDG(&ix.hslots[h2]);
         if (known < 0 || (known & 8)) s3 = CG_LDG(&ix.hslots[h3]);
-        F0.b = F0.e = R0.b = R0.e = FL.b = FL.e = RL.b = RL.e = 0;
-        F0.f = resolve(ix, mer0, h0, s0, F0.b, F0.e); R0.f = resolve(ix, rc0, h1, s1, R0.b, R0.e);
-        FL.f = resolve(ix, merL, h2, s2, FL.b, FL.e); RL.f = resolve(ix, rcL, h3, s3, RL.b, RL.e);
+        st.F0.b = st.F0.e = st.R0.b = st.R0.e = st.FL.b = st.FL.e = st.RL.b = st.RL.e = 0;
+        st.F0.f = resolve(ix, mer0, h0, s0, st.F0.b, st.F0.e); st.R0.f = resolve(ix, rc0, h1, s1, st.R0.b, st.R0.e);
+        st.FL.f = resolve(ix, merL, h2, s2, st.FL.b, st.FL.e); st.RL.f = resolve(ix, rcL, h3, s3, st.RL.b, st.RL.e);
     }
-    bool phaseA = true, firstB = false, aOther = false, expectAbsent = false, lastSearch = false, homo = false;
-    int s = 0, o = 0, nKS = 0;
-    uint32_t fwdHit = 0, rcHit = 0;
-#define Q_PUSH_KS(kp, f, r) do { if (VOTE) { if (nKS >= Q_FK) return QD_NKS; m.st(m.ks(nKS), ks_pack((kp), (f), (r))); ++nKS; } } while (0)
-    for (;;) {
-        bool done = false;                                                         // this strand is finished
-        // ---------------- LOOK: the next position of strand s whose k-mer is in the table ----------------
-        int pos = -1;
-        QProbe hit; hit.f = false; hit.b = hit.e = 0;
-        bool other = false;
-        bool walk; int wlim;
-        if (phaseA) {
-            wlim = L - k - 1;                                                      // `re < read.end()` (:112)
-            if (F0.f || R0.f) { pos = 0; hit = F0; other = R0.f; walk = false; }   // :131-132 at position 0
-            else { walk = true; o = 1; }
+    st.phaseA = true; st.firstB = false; st.aOther = false; st.expectAbsent = false; st.lastSearch = false;
+    st.s = 0; st.o = 0; st.nKS = 0; st.fwdHit = 0; st.rcHit = 0;
+    return Q_CONT;
+}
+
+// one trip of the scan loop: Q_CONT (more to do), Q_DONE (both strands finished: q_vote next), Q_NOTFOUND or a QD_* reason
+template <bool VOTE>
+CG_HD int q_step(const IndexView& ix, const QMemT<VOTE>& m, int lceMode, QState& st) {
+    const int k = ix.k, skipOverlap = k - 1, L = st.L;
+#define Q_PUSH_KS(kp, f, r) do { if (VOTE) { if (st.nKS >= Q_FK) return QD_NKS; m.st(m.ks(st.nKS), ks_pack((kp), (f), (r))); ++st.nKS; } } while (0)
+    bool done = false;                                                         // this strand is finished
+    bool homo = false;
+    CG_COST(0, 1);
+    // ---------------- LOOK: the next position of strand s whose k-mer is in the table ----------------
+    int pos = -1;
+    QProbe hit; hit.f = false; hit.b = hit.e = 0;
+    bool other = false;
+    bool walk; int wlim;
+    if (st.phaseA) {
+        wlim = L - k - 1;                                                      // `re < read.end()` (:112)
+        if (st.F0.f || st.R0.f) { pos = 0; hit = st.F0; other = st.R0.f; walk = false; }   // :131-132 at position 0
+        else { walk = true; st.o = 1; }
+    } else {
+        wlim = L - k;                                                          // :234 / :341-344
+        walk = st.expectAbsent;
+        if (!walk) {
+            // expected present (:261+:268 / :372+:379): only ever asked at 0 or L - k, answered up front
+            QProbe a, b;
+            if (st.o == 0) { if (st.s == 0) { a = st.F0; b = st.R0; } else { a = st.RL; b = st.FL; } }
+            else if (st.o == L - k) { if (st.s == 0) { a = st.FL; b = st.RL; } else { a = st.R0; b = st.F0; } }
+            else return QD_ODD;
+            if (a.f) { pos = st.o; hit = a; other = b.f; }
+            else { st.o += 1; walk = true; }                                   // :324 / :436, then a walk
+        }
+    }
+    if (walk) {
+        bool hasR = false;
+        pos = q_walk(ix, m, L, st.s, st.o, wlim, st.phaseA, hit, hasR, homo);
+        if (homo) return QD_HOMO;
+        if (pos >= 0) {
+            if (st.phaseA) other = hasR;
+            else {                                                             // :268 / :379
+                uint32_t b2, e2;
+                other = probe(ix, revcomp(m.chunk(st.s, pos) & ix.km, k), b2, e2);
+            }
+        }
+    }
+    if (pos < 0) {
+        if (st.phaseA) return Q_NOTFOUND;                                      // :204
+        done = true;                                                           // ran off the read
+    }
+    if (!done) {
+        st.o = pos;
+        bool extendIt = true;
+        if (st.phaseA) {
+            st.phaseA = false;
+            if (!VOTE && hit.f && other) return QD_BOTH_A;                     // both strands seeded: the vote decides
+            if (hit.f) { st.s = 0; st.firstB = true; st.aOther = other; }      // :134-176, Phase B follows
+            else {                                                             // :178-191: rcHit only, Phase C from 0 (:332-346)
+                ++st.rcHit; Q_PUSH_KS(pos, -1, 1);
+                st.s = 1; st.o = 0; st.expectAbsent = false; extendIt = false;
+            }
         } else {
-            wlim = L - k;                                                          // :234 / :341-344
-            walk = expectAbsent;
-            if (!walk) {
-                // expected present (:261+:268 / :372+:379): only ever asked at 0 or L - k, answered up front
-                QProbe a, b;
-                if (o == 0) { if (s == 0) { a = F0; b = R0; } else { a = RL; b = FL; } }
-                else if (o == L - k) { if (s == 0) { a = FL; b = RL; } else { a = R0; b = F0; } }
-                else return QD_ODD;
-                if (a.f) { pos = o; hit = a; other = b.f; }
-                else { o += 1; walk = true; }                                      // :324 / :436, then a walk
-            }
+            if (!VOTE && other) return QD_OTHER;                               // :265-272 / :381-385: the other strand scores too
+            const int fpos = st.s == 0 ? st.o : L - (st.o + k);                // :366
+            if (st.s == 0) { ++st.fwdHit; if (other) ++st.rcHit; Q_PUSH_KS(fpos, 1, other ? 1 : 0); }
+            else { ++st.rcHit; if (other) ++st.fwdHit; Q_PUSH_KS(fpos, other ? 1 : 0, 1); }
         }
-        if (walk) {
-            bool hasR = false;
-            pos = q_walk(ix, m, L, s, o, wlim, phaseA, hit, hasR, homo);
-            if (homo) return QD_HOMO;
-            if (pos >= 0) {
-                if (phaseA) other = hasR;
-                else {                                                             // :268 / :379
-                    uint32_t b2, e2;
-                    other = probe(ix, revcomp(m.chunk(s, pos) & ix.km, k), b2, e2);
-                }
-            }
-        }
-        if (pos < 0) {
-            if (phaseA) return Q_NOTFOUND;                                         // :204
-            done = true;                                                           // ran off the read
-        }
-        if (!done) {
-            o = pos;
-            bool extendIt = true;
-            if (phaseA) {
-                phaseA = false;
-                if (!VOTE && hit.f && other) return QD_BOTH_A;                     // both strands seeded: the vote decides
-                if (hit.f) { s = 0; firstB = true; aOther = other; }               // :134-176, Phase B follows
-                else {                                                             // :178-191: rcHit only, Phase C from 0 (:332-346)
-                    ++rcHit; Q_PUSH_KS(pos, -1, 1);
-                    s = 1; o = 0; expectAbsent = false; extendIt = false;
-                }
-            } else {
-                if (!VOTE && other) return QD_OTHER;                               // :265-272 / :381-385: the other strand scores too
-                const int fpos = s == 0 ? o : L - (o + k);                         // :366
-                if (s == 0) { ++fwdHit; if (other) ++rcHit; Q_PUSH_KS(fpos, 1, other ? 1 : 0); }
-                else { ++rcHit; if (other) ++fwdHit; Q_PUSH_KS(fpos, other ? 1 : 0, 1); }
-            }
-            if (extendIt) {
-                // ---------------- EXTEND: extendSearchNaive(b - 1, e) from position o (:143 / :280 / :393) ----------------
-                if (hit.b == 0) return QD_SA0;
-                uint32_t lb = hit.b, ub = hit.e;
-                int matched = k;
-                const int mq = L - o;
-                if (mq > k) {
-                    const uint32_t w = hit.e - hit.b;
-                    if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
-                    int best = -1; uint32_t first = 0, last = 0;
-                    for (uint32_t c0 = 0; c0 < w; c0 += QX) {
-                        uint32_t p[QX];
+        if (extendIt) {
+            // ---------------- EXTEND: extendSearchNaive(b - 1, e) from position o (:143 / :280 / :393) ----------------
+            const int s = st.s, o = st.o;
+            if (hit.b == 0) return QD_SA0;
+            uint32_t lb = hit.b, ub = hit.e;
+            int matched = k;
+            const int mq = L - o;
+            if (mq > k) {
+                const uint32_t w = hit.e - hit.b;
+                if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
+                CG_COST(3, w);
+                int best = -1; uint32_t first = 0, last = 0;
+                for (uint32_t c0 = 0; c0 < w; c0 += QX) {
+                    uint32_t p[QX];
 #pragma unroll
-                        for (int c = 0; c < QX; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
+                    for (int c = 0; c < QX; ++c) p[c] = (c0 + c < w) ? CG_LDG(&ix.sa[hit.b + c0 + c]) : 0u;
 #pragma unroll
-                        for (int c = 0; c < QX; ++c) {
-                            if (c0 + c < w) {
-                                const int l = q_match(ix.text, m, s, o, p[c], k, mq);
-                                if (l > best) { best = l; first = last = c0 + c; }
-                                else if (l == best) last = c0 + c;
-                            }
+                    for (int c = 0; c < QX; ++c) {
+                        if (c0 + c < w) {
+                            const int l = q_match(ix.text, m, s, o, p[c], k, mq);
+                            if (l > best) { best = l; first = last = c0 + c; }
+                            else if (l == best) last = c0 + c;
                         }
                     }
-                    lb = hit.b + first; ub = hit.b + last + 1; matched = best;
                 }
-                const bool valid = ub > lb && ub - lb < 1000u;                     // :149 / :285 / :398 (maxInterval)
+                lb = hit.b + first; ub = hit.b + last + 1; matched = best;
+            }
+            const bool valid = ub > lb && ub - lb < 1000u;                     // :149 / :285 / :398 (maxInterval)
+            if (valid) {
+                const int n = s == 0 ? st.nF : st.nR;
+                if (n >= Q_FI) return QD_NINT;
+                m.st(m.iv(s, n), lb); m.st(m.iv(s, n) + 1, ub); m.st(m.iv(s, n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
+                if (s == 0) st.nF = n + 1; else st.nR = n + 1;
+            }
+            if (st.firstB) {                                                   // Phase A's bookkeeping (:149-191)
                 if (valid) {
-                    int& n = s == 0 ? nF : nR;
-                    if (n >= Q_FI) return QD_NINT;
-                    m.st(m.iv(s, n), lb); m.st(m.iv(s, n) + 1, ub); m.st(m.iv(s, n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
-                    ++n;
-                }
-                if (firstB) {                                                      // Phase A's bookkeeping (:149-191)
-                    if (valid) {
-                        ++fwdHit;
-                        if (aOther) { ++rcHit; Q_PUSH_KS(o, 1, 1); } else Q_PUSH_KS(o, 1, -1);
-                        if (o + matched < L) Q_PUSH_KS(o + matched - skipOverlap, -1, 0);      // :165-168
-                    } else return QD_ODD;                                          // (an interval of >= 1000 suffixes: not this tier's read)
-                } else if (valid && o + matched < L) {                             // :291 / :404
-                    Q_PUSH_KS(s == 0 ? o + matched - skipOverlap : L - (o + matched), 0, 0);
-                }
-                if (lastSearch) done = true;                                       // :300 / :412
-                else {
-                    // ---------------- LCE and the next position (:219-228 after Phase A, :302-321 / :414-433 in the loop) ----------------
-                    const int mismatch = o + matched;
-                    const int stopAt = L - mismatch;
-                    int l = matched;
-                    if (stopAt > matched) {                                        // else lce returns startAt at once
-                        const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
-                        l = q_lce(ix.text, ix.n, p1, p2, matched, stopAt, lceMode);
-                    }
-                    if (firstB) {
-                        firstB = false;
-                        const int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
-                        const int o2 = cmin(cmax(0, L - k), o + fwdSkip);          // :224-228
-                        expectAbsent = stopAt > 0 && o2 < L - k;
-                        o = o2;
-                    } else if (mismatch < L) {
-                        o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
-                        if (o > L - k) { o = L - k; lastSearch = true; expectAbsent = false; }
-                        else expectAbsent = true;
-                    } else { lastSearch = true; o = L - k; expectAbsent = false; }
-                    if (o + k > L) done = true;
-                }
+                    ++st.fwdHit;
+                    if (st.aOther) { ++st.rcHit; Q_PUSH_KS(o, 1, 1); } else Q_PUSH_KS(o, 1, -1);
+                    if (o + matched < L) Q_PUSH_KS(o + matched - skipOverlap, -1, 0);      // :165-168
+                } else return QD_ODD;                                          // (an interval of >= 1000 suffixes: not this tier's read)
+            } else if (valid && o + matched < L) {                             // :291 / :404
+                Q_PUSH_KS(s == 0 ? o + matched - skipOverlap : L - (o + matched), 0, 0);
             }
-        }
-        if (done) {
-            if (VOTE && s == 0 && rcHit >= fwdHit) {                               // Phase C after Phase B (:332-346)
-                s = 1; o = 0; expectAbsent = false; lastSearch = false;
-                continue;
+            if (st.lastSearch) done = true;                                    // :300 / :412
+            else {
+                // ---------------- LCE and the next position (:219-228 after Phase A, :302-321 / :414-433 in the loop) ----------------
+                const int mismatch = o + matched;
+                const int stopAt = L - mismatch;
+                int l = matched;
+                if (stopAt > matched) {                                        // else lce returns startAt at once
+                    const uint32_t p1 = CG_LDG(&ix.sa[lb]), p2 = (ub - 1 == lb) ? p1 : CG_LDG(&ix.sa[ub - 1]);
+                    l = q_lce(ix.text, ix.n, p1, p2, matched, stopAt, lceMode);
+                }
+                if (st.firstB) {
+                    st.firstB = false;
+                    const int fwdSkip = cmax(matched - skipOverlap, l - skipOverlap);
+                    const int o2 = cmin(cmax(0, L - k), o + fwdSkip);          // :224-228
+                    st.expectAbsent = stopAt > 0 && o2 < L - k;
+                    st.o = o2;
+                } else if (mismatch < L) {
+                    st.o = cmax(o + l - skipOverlap, mismatch - skipOverlap);
+                    if (st.o > L - k) { st.o = L - k; st.lastSearch = true; st.expectAbsent = false; }
+                    else st.expectAbsent = true;
+                } else { st.lastSearch = true; st.o = L - k; st.expectAbsent = false; }
+                if (st.o + k > L) done = true;
             }
-            break;
         }
     }
 #undef Q_PUSH_KS
-    // ---- strand vote (:442-490)
+    if (done) {
+        if (VOTE && st.s == 0 && st.rcHit >= st.fwdHit) {                      // Phase C after Phase B (:332-346)
+            st.s = 1; st.o = 0; st.expectAbsent = false; st.lastSearch = false;
+            return Q_CONT;
+        }
+        return Q_DONE;
+    }
+    return Q_CONT;
+}
+
+// the strand vote (:442-490)
+template <bool VOTE>
+CG_HD int q_vote(const IndexView& ix, const QMemT<VOTE>& m, QState& st) {
+    const int k = ix.k, nKS = st.nKS;
     if (VOTE) {
-        if (fwdHit > 0 && rcHit == 0) nR = 0;
-        else if (rcHit > 0 && fwdHit == 0) nF = 0;
+        if (st.fwdHit > 0 && st.rcHit == 0) st.nR = 0;
+        else if (st.rcHit > 0 && st.fwdHit == 0) st.nF = 0;
         else {
             for (int i = 1; i < nKS; ++i) {                                        // std::sort of <= 16 entries: a stable insertion sort
                 const uint32_t v = m.ld(m.ks(i)); int j = i - 1;
@@ -483,15 +567,27 @@ CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMod
                 }
                 fs += f; rs += r;
             }
-            if (fs > rs) nR = 0; else if (rs > fs) nF = 0;                         // :482-488
+            if (fs > rs) st.nR = 0; else if (rs > fs) st.nF = 0;                   // :482-488
         }
     }
     return Q_FOUND;
 }
 
+template <bool VOTE>
+CG_HD int q_collect(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, int& nF, int& nR, int known = -1) {
+    QState st;
+    int r = q_begin<VOTE>(ix, m, L, known, st);
+    while (r == Q_CONT) r = q_step<VOTE>(ix, m, lceMode, st);
+    if (r == Q_DONE) r = q_vote<VOTE>(ix, m, st);
+    nF = st.nF; nR = st.nR;
+    if (r != Q_FOUND) nF = nR = 0;
+    return r;
+}
+
 // up to four SA positions -> transcript ids (x, y, z, w; 0xffffffff past nn), the suffix-array entries then the text sectors as
 // two waves of loads
 CG_HDN u32x4 q_tids4(const uint32_t* sa, const u32x4* text, const uint32_t* satid, uint32_t i0, int nn) {
+    CG_COST(6, 1);
     if (satid) {                                         // the index keeps transcriptAtPosition(SA[i]) per suffix-array index: one wave, contiguous
         u32x4 r;
         r.x = CG_LDG(&satid[i0]);
@@ -603,12 +699,10 @@ CG_HD int q_hits2(const IndexView& ix, const QMemT<VOTE>& m, int nF, int nR, int
     return hF + hR - common;
 }
 
-// one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517): false = declined
+// one mate of Circall_wt (src/Circall_wt.cpp:275-342 / 283-517) after the collector returned r (>= 0) with nF / nR intervals in the
+// scratch: false = declined
 template <bool VOTE>
-CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why, int& nF, int& nR, int known = -1) {
-    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR, known);
-    why = r;
-    if (r < 0) return false;
+CG_HD bool q_wt_finish(const IndexView& ix, const QMemT<VOTE>& m, int r, int pairLen, int nF, int nR, uint8_t& flags, uint32_t& nh, int& why) {
     flags = 0; nh = 0;
     if (r == Q_NOTFOUND) return true;
     bool full = false;
@@ -622,15 +716,30 @@ CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairL
     nh = (uint32_t)h;
     return true;
 }
+template <bool VOTE>
+CG_HD bool q_wt_mate(const IndexView& ix, const QMemT<VOTE>& m, int L, int pairLen, int lceMode, uint8_t& flags, uint32_t& nh, int& why, int& nF, int& nR, int known = -1) {
+    const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR, known);
+    why = r;
+    if (r < 0) return false;
+    return q_wt_finish<VOTE>(ix, m, r, pairLen, nF, nR, flags, nh, why);
+}
 
 // one record of Circall_bsj (src/Circall_bsj.cpp:300-399): false = declined (nothing was emitted).  On success the
 // hit transcripts are left in ascending order at tids_at (word index in the scratch), nh of them.
+template <bool VOTE, class Sink>
+CG_HD bool q_bsj_finish(const IndexView& ix, const QMemT<VOTE>& m, int r, int nF, int nR, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why);
 template <bool VOTE, class Sink>
 CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lceMode, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why, int& nF, int& nR, int known = -1) {
     const int r = q_collect<VOTE>(ix, m, L, lceMode, nF, nR, known);
     why = r;
     tids_at = m.cb(0);
     if (r < 0) return false;
+    return q_bsj_finish<VOTE>(ix, m, r, nF, nR, sink, nh, split, tids_at, why);
+}
+// the record after the collector returned r (>= 0) with nF / nR intervals in the scratch
+template <bool VOTE, class Sink>
+CG_HD bool q_bsj_finish(const IndexView& ix, const QMemT<VOTE>& m, int r, int nF, int nR, Sink& sink, uint32_t& nh, bool& split, int& tids_at, int& why) {
+    tids_at = m.cb(0);
     nh = 0; split = false;
     if (r == Q_NOTFOUND) return true;
     int hF, hR;
@@ -649,6 +758,7 @@ CG_HD bool q_bsj_record(const IndexView& ix, const QMemT<VOTE>& m, int L, int lc
             const int len = (int)(lq & 0xffffu);
             for (uint32_t i0 = ib; i0 < ie; i0 += 4) {                                           // :326 / :355
                 const int nn = (int)cmin<uint32_t>(4u, ie - i0);
+                CG_COST(7, 1);
                 uint32_t tt[4], ll[4], o0[4], o1[4];
                 sa_tids4(ix, i0, nn, tt, ll);
 #pragma unroll

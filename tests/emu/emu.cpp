@@ -85,9 +85,14 @@ static int known_of(const IndexView& ix, const std::vector<uint64_t>& pk, int L)
 }
 static uint64_t g_thr_why[2][16];
 static uint64_t g_thr_vote[2];
+static std::vector<uint32_t> g_cost_log[2];      // per lockstep-tier call: class, ok, 8 cost counters  (0 wt, 1 bsj)
+static void cost_begin() { memset(cgq::g_cost, 0, sizeof cgq::g_cost); }
+static void cost_end(int which, int cls, bool ok) { auto& v = g_cost_log[which]; v.push_back((uint32_t)cls); v.push_back(ok); for (int i = 0; i < 8; ++i) v.push_back(cgq::g_cost[i]); }
 static bool thr_wt_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int pairLen, int lceMode, std::vector<uint32_t>& scratch, uint8_t& fl, uint32_t& nh) {
     int why = cgq::QD_N, nF = 0, nR = 0;
     bool ok;
+    cost_begin();
+    struct CostEnd { const IndexView& ix; const std::vector<uint64_t>& pk; int L; bool* ok; ~CostEnd() { cost_end(0, known_of(ix, pk, L) + (both_class(ix, pk, L) ? 16 : 0), *ok); } } ce{ix, pk, L, &ok};
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
         ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_wt_mate<true>(ix, m, L, pairLen, lceMode, fl, nh, why, nF, nR, known_of(ix, pk, L));
@@ -103,6 +108,8 @@ template <class Sink>
 static bool thr_bsj_host(const IndexView& ix, const std::vector<uint64_t>& pk, int L, int lceMode, std::vector<uint32_t>& scratch, Sink& sink, uint32_t& nh, bool& split, uint32_t* tids) {
     int why = cgq::QD_N, at = 0, nF = 0, nR = 0;
     bool ok;
+    cost_begin();
+    struct CostEnd { const IndexView& ix; const std::vector<uint64_t>& pk; int L; bool* ok; ~CostEnd() { cost_end(1, known_of(ix, pk, L) + (both_class(ix, pk, L) ? 16 : 0), *ok); } } ce{ix, pk, L, &ok};
     if (both_class(ix, pk, L) && !getenv("CG_EMU_NO_VOTE")) {
         cgq::QMemT<true> m;
         ok = thr_stage<true>(pk, L, scratch, m) && cgq::q_bsj_record<true>(ix, m, L, lceMode, sink, nh, split, at, why, nF, nR, known_of(ix, pk, L));
@@ -368,6 +375,12 @@ void emu_thr_why(uint64_t* out, int reset) { memcpy(out, g_thr_why, sizeof g_thr
 // seed filter of an index (0 = none) and what the lockstep tier's walks cost since the last reset: filter look-ups, table look-ups, windows the filter settled
 int emu_index_fm(void* h) { return ((EmuIndex*)h)->v.fm; }
 void emu_walk_stats(uint64_t* out, int reset) { out[0] = cgq::g_walk.filter_loads; out[1] = cgq::g_walk.table_loads; out[2] = cgq::g_walk.dead_windows; if (reset) cgq::g_walk = cgq::WalkStats(); }
+// per-call cost log of the lockstep tier (which: 0 wt, 1 bsj): 10 uint32 per call; returns the number of values, copies when out is given, clears when asked
+uint64_t emu_cost_log(int which, uint32_t* out, int clear) { auto& v = g_cost_log[which]; uint64_t n = v.size(); if (out) memcpy(out, v.data(), n * 4); if (clear) v.clear(); return n; }
+// geometry of the walks' filter stage (tests sweep it; cg_thr.cuh)
+void emu_walk_geometry(int np, int d0, int sp, int tail) { cgq::Q_NPR = np; cgq::Q_D0X = d0; cgq::Q_SPX = sp; cgq::Q_TAIL = tail; }
+// the same with the number of walks, their table rounds and the histogram of rounds per walk (out: 6 + 24 values)
+void emu_walk_stats_ex(uint64_t* out, int reset) { const auto& g = cgq::g_walk; out[0] = g.filter_loads; out[1] = g.table_loads; out[2] = g.dead_windows; out[3] = g.calls; out[4] = g.rounds; out[5] = g.found; for (int i = 0; i < 24; ++i) out[6 + i] = g.hist[i]; if (reset) cgq::g_walk = cgq::WalkStats(); }
 
 // std::sort replica check: sorts packed kmerScores entries with cg::StdSort
 void emu_stdsort(uint32_t* a, int n) { StdSort s; s.a = a; s.sort<true>(n); }
