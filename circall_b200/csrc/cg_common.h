@@ -20,6 +20,7 @@ struct cg_index {
     uint4* d_hslots = nullptr;
     uint32_t* d_offsets = nullptr;
     uint32_t* d_satid = nullptr;   // transcriptAtPosition(SA[i]) per suffix-array index, rebuilt from SA + text at build / open time
+    uint8_t* d_lcp = nullptr;      // min(255, lcp(SA[i-1], SA[i])) per suffix-array index, rebuilt from SA + text at build / open time
     uint32_t* d_fbits = nullptr;   // seed filter bit set (4^fm bits), rebuilt from the text at build / open time
     int fm = 0;
     std::vector<uint32_t> offsets;   // n_tx + 1
@@ -32,7 +33,7 @@ struct cg_index {
         v.hshift = 64; for (uint64_t c = hcap; c > 1; c >>= 1) --v.hshift;
         v.n = (uint32_t)n; v.n_tx = n_tx; v.k = k;
         v.km = cg::kmask(k); v.km3 = v.km / 3;
-        v.fbits = d_fbits; v.fm = d_fbits ? fm : 0; v.satid = d_satid;
+        v.fbits = d_fbits; v.fm = d_fbits ? fm : 0; v.satid = d_satid; v.lcp = d_lcp;
         return v;
     }
 };

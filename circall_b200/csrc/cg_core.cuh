@@ -59,6 +59,9 @@ __device__ __forceinline__ uint2 ldg_ix(const uint2* p) {
 __device__ __forceinline__ uint32_t ldg_ix(const uint32_t* p) {
     uint32_t v; asm("ld.global.nc" CG_LTC_Q ".u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
+__device__ __forceinline__ uint8_t ldg_ix(const uint8_t* p) {
+    uint32_t v; asm("ld.global.nc" CG_LTC_Q ".u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v;
+}
 }
 #define CG_LDG(p) cg::ldg_ix(p)
 #else
@@ -140,6 +143,11 @@ struct IndexView {
     // transcriptAtPosition(SA[i]) for every suffix-array index i (null = none): the hit enumeration and the span filter walk SA
     // intervals, and with this array an interval's transcripts are one coalesced read instead of one random text block per suffix
     const uint32_t* satid;
+    // min(255, longest common prefix of the suffixes SA[i - 1] and SA[i]) for every i >= 1 ('$' matches nothing; lcp[0] = 0; null = none).
+    // extendSearchNaive compares the query with every suffix of a k-mer interval; the suffixes are sorted, so from the match length
+    // of one suffix and this byte the match length of the next follows without touching the text, unless the two are equal
+    // (cg_thr.cuh::q_step, cg_pre.cuh): one comparison per interval instead of one per suffix
+    const uint8_t* lcp;
 };
 
 struct TB { uint64_t c0, c1, mask; uint32_t tid0, start0; };

@@ -268,6 +268,24 @@ int build_satid(cg_index* idx) {
     return CG_OK;
 }
 
+// min(255, lcp(SA[i - 1], SA[i])) for every i (IndexView::lcp)
+__global__ void __launch_bounds__(256)
+k_lcp(IndexView ix, uint8_t* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= ix.n) return;
+    out[i] = i == 0 ? (uint8_t)0 : (uint8_t)lce(ix, (uint32_t)i - 1, (uint32_t)i, 0, 255, 1);
+}
+int build_lcp(cg_index* idx) {
+    if (getenv("CG_NO_LCP")) return CG_OK;
+    CG_CUDA(cudaMalloc((void**)&idx->d_lcp, idx->n));
+    IndexView v = idx->view();
+    v.lcp = nullptr;
+    k_lcp<<<grid_for(idx->n, 256), 256>>>(v, idx->d_lcp);
+    CG_CUDA(cudaGetLastError());
+    CG_CUDA(cudaDeviceSynchronize());
+    return CG_OK;
+}
+
 int build_fbits(cg_index* idx) {
     int want = 16;
     if (const char* e = getenv("CG_FM")) want = atoi(e);
@@ -300,12 +318,13 @@ void free_index_device(cg_index* idx) {
     if (idx->d_offsets) cudaFree(idx->d_offsets);
     if (idx->d_fbits) cudaFree(idx->d_fbits);
     if (idx->d_satid) cudaFree(idx->d_satid);
-    idx->d_fbits = nullptr; idx->d_satid = nullptr;
+    if (idx->d_lcp) cudaFree(idx->d_lcp);
+    idx->d_fbits = nullptr; idx->d_satid = nullptr; idx->d_lcp = nullptr;
     idx->d_text = nullptr; idx->d_sa = nullptr; idx->d_hslots = nullptr; idx->d_offsets = nullptr;
 }
 
 void finish_sizes(cg_index* idx) {
-    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4 + (idx->d_fbits ? (1ULL << (2 * idx->fm)) / 8 : 0) + (idx->d_satid ? idx->n * 4 : 0);
+    idx->device_bytes = idx->n_blocks * 32 + idx->n * 4 + idx->hcap * 16 + ((uint64_t)idx->n_tx + 1) * 4 + (idx->d_fbits ? (1ULL << (2 * idx->fm)) / 8 : 0) + (idx->d_satid ? idx->n * 4 : 0) + (idx->d_lcp ? idx->n : 0);
 }
 
 int build_impl(int device, const char* text, uint64_t n, int k, const std::vector<std::string>* names, cg_index** out) {
@@ -371,6 +390,8 @@ int build_impl(int device, const char* text, uint64_t n, int k, const std::vecto
     rc = build_fbits(idx);
     if (rc) return fail(rc);
     rc = build_satid(idx);
+    if (rc) return fail(rc);
+    rc = build_lcp(idx);
     if (rc) return fail(rc);
 #undef CG_TRY
     finish_sizes(idx);
@@ -549,6 +570,7 @@ static int index_open_impl(const char* dir, int device, cg_index** out) {
     if (e != cudaSuccess) return fail(cgi::cuda_fail(e, "upload offsets", __FILE__, __LINE__));
     if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter and the per-suffix transcript array are derived from
     if ((rc = build_satid(idx))) return fail(rc);          // text + SA: not part of the directory
+    if ((rc = build_lcp(idx))) return fail(rc);
     finish_sizes(idx);
     *out = idx;
     return CG_OK;

@@ -82,19 +82,47 @@ CG_HD bool perfect_mate(const IndexView& ix, const cgt::TMem& m, int L, int pair
     const uint32_t w = e - b;
     if (b == 0 || w == 0 || w > (uint32_t)PRE_WMAX) return false;
     if (s == 1) cgt::make_rc(m, L);
-    // extendSearchNaive(b - 1, e) (:143 / :393): every suffix of the interval; all of their SA entries first
-    uint32_t p[PRE_WMAX];
-#pragma unroll
-    for (int c = 0; c < PRE_WMAX; ++c) p[c] = (uint32_t)c < w ? CG_LDG(&ix.sa[b + c]) : 0u;
+    // extendSearchNaive(b - 1, e) (:143 / :393): every suffix of the interval
     uint32_t fullB = 0;                                                 // candidates that match over the whole read
-#pragma unroll
-    for (int c = 0; c < PRE_WMAX; ++c)
-        if ((uint32_t)c < w && pre_match(ix, m, s, p[c], k, L) == L) fullB |= 1u << c;
-    if (!fullB) return false;                                           // the match stops early: not this kernel's mate
-    // hits: distinct transcripts of the full-length interval (contiguous in SA order)
     uint32_t tid[PRE_WMAX];
+    if (ix.lcp && ix.satid) {
+        // sorted suffixes: the match length of one follows from that of the one before and the lcp of the two (cg_thr.cuh::q_step);
+        // the text is only read for the first suffix and where the two lengths are equal
+        int hb[PRE_WMAX];
 #pragma unroll
-    for (int c = 0; c < PRE_WMAX; ++c) tid[c] = ((fullB >> c) & 1u) ? cgt::tid_from(CG_LDG(&ix.text[2 * (uint64_t)(p[c] >> 6) + 1]), p[c]) : 0xffffffffu;
+        for (int c = 0; c < PRE_WMAX; ++c) {
+            hb[c] = (c > 0 && (uint32_t)c < w) ? (int)CG_LDG(&ix.lcp[b + c]) : 0;
+            tid[c] = (uint32_t)c < w ? CG_LDG(&ix.satid[b + c]) : 0xffffffffu;
+        }
+        int lp = pre_match(ix, m, s, CG_LDG(&ix.sa[b]), k, L);
+        if (lp == L) fullB |= 1u;
+#pragma unroll
+        for (int c = 1; c < PRE_WMAX; ++c) {
+            if ((uint32_t)c < w) {
+                const int h = hb[c];
+                int l;
+                if (h > lp) l = lp;
+                else if (h < lp && h < 255) l = h;
+                else l = pre_match(ix, m, s, CG_LDG(&ix.sa[b + c]), cmin(h, lp), L);
+                if (l == L) fullB |= 1u << c;
+                lp = l;
+            }
+        }
+        if (!fullB) return false;                                       // the match stops early: not this kernel's mate
+#pragma unroll
+        for (int c = 0; c < PRE_WMAX; ++c) if (!((fullB >> c) & 1u)) tid[c] = 0xffffffffu;
+    } else {
+        uint32_t p[PRE_WMAX];                                           // all of their SA entries first
+#pragma unroll
+        for (int c = 0; c < PRE_WMAX; ++c) p[c] = (uint32_t)c < w ? CG_LDG(&ix.sa[b + c]) : 0u;
+#pragma unroll
+        for (int c = 0; c < PRE_WMAX; ++c)
+            if ((uint32_t)c < w && pre_match(ix, m, s, p[c], k, L) == L) fullB |= 1u << c;
+        if (!fullB) return false;                                       // the match stops early: not this kernel's mate
+        // hits: distinct transcripts of the full-length interval (contiguous in SA order)
+#pragma unroll
+        for (int c = 0; c < PRE_WMAX; ++c) tid[c] = ((fullB >> c) & 1u) ? cgt::tid_from(CG_LDG(&ix.text[2 * (uint64_t)(p[c] >> 6) + 1]), p[c]) : 0xffffffffu;
+    }
     uint32_t n = 0;
 #pragma unroll
     for (int c = 0; c < PRE_WMAX; ++c) {

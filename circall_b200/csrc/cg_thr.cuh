@@ -43,8 +43,10 @@
                            // 16 registers less and halves the unrolled code; the number of rounds does not matter
 #endif
 #ifndef CG_THR_MINB
-#define CG_THR_MINB 5      // resident blocks per SM asked of the lockstep kernels (96 registers; measured: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5, 6 -> 5.46 / 10.8;
-                           // asking for the largest shared-memory carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors)
+#define CG_THR_MINB 6      // resident blocks per SM (x 128 threads) asked of the lockstep kernels.  Round 1, DRAM-bound kernels: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5,
+                           // 6 -> 5.46 / 10.8.  Round 2 (seed filter, lcp bytes: a quarter of the DRAM bytes, the kernels wait on latency), step of 8 M pairs:
+                           // 4 -> 30.14 ms, 5 -> 29.85, 6 -> 29.33 (80 registers), 7 -> 30.59 (72, spills), 8 -> 31.28; asking for the largest shared-memory
+                           // carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors
 #endif
 
 namespace cgq {
@@ -471,6 +473,30 @@ CG_HD int q_step(const IndexView& ix, const QMemT<VOTE>& m, int lceMode, QState&
                 if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
                 CG_COST(3, w);
                 int best = -1; uint32_t first = 0, last = 0;
+                if (ix.lcp) {
+                    // The suffixes are sorted: with lp the match length of the one before and h = lcp of the two, this one matches
+                    // lp when h > lp and h when h < lp; only h == lp (or a saturated byte) needs the text, from there on.
+                    int lp = q_match(ix.text, m, s, o, CG_LDG(&ix.sa[hit.b]), k, mq);
+                    best = lp;
+                    for (uint32_t c0 = 1; c0 < w; c0 += QX) {
+                        int hb[QX];
+#pragma unroll
+                        for (int c = 0; c < QX; ++c) hb[c] = (c0 + c < w) ? (int)CG_LDG(&ix.lcp[hit.b + c0 + c]) : 0;
+#pragma unroll
+                        for (int c = 0; c < QX; ++c) {
+                            if (c0 + c < w) {
+                                const int h = hb[c];
+                                int l;
+                                if (h > lp) l = lp;
+                                else if (h < lp && h < 255) l = h;
+                                else l = q_match(ix.text, m, s, o, CG_LDG(&ix.sa[hit.b + c0 + c]), cmin(h, lp), mq);
+                                if (l > best) { best = l; first = last = c0 + c; }
+                                else if (l == best) last = c0 + c;
+                                lp = l;
+                            }
+                        }
+                    }
+                } else
                 for (uint32_t c0 = 0; c0 < w; c0 += QX) {
                     uint32_t p[QX];
 #pragma unroll

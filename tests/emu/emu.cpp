@@ -23,6 +23,7 @@ using namespace cg;
 struct EmuIndex {
     std::vector<u32x4> text, hslots;
     std::vector<uint32_t> sa, offsets, fbits, satid;
+    std::vector<uint8_t> lcp;
     IndexView v;
     uint64_t n_kmers = 0;
 };
@@ -151,7 +152,12 @@ void* emu_index_create(const char* text, uint64_t n, const int32_t* sa, int k) {
     E->v.text = E->text.data(); E->v.sa = E->sa.data(); E->v.offsets = E->offsets.data();
     E->v.n = (uint32_t)n; E->v.n_tx = ntx; E->v.k = k; E->v.hslots = nullptr; E->v.hmask = 0; E->v.hshift = 0;
     E->v.km = kmask(k); E->v.km3 = E->v.km / 3;
-    E->v.fbits = nullptr; E->v.fm = 0; E->v.satid = nullptr;
+    E->v.fbits = nullptr; E->v.fm = 0; E->v.satid = nullptr; E->v.lcp = nullptr;
+    if (!getenv("CG_NO_LCP")) {        // min(255, lcp(SA[i-1], SA[i])), as cg_index.cu::build_lcp makes it
+        E->lcp.assign(n, 0);
+        for (uint64_t i = 1; i < n; ++i) E->lcp[i] = (uint8_t)lce(E->v, (uint32_t)i - 1, (uint32_t)i, 0, 255, 1);
+        E->v.lcp = E->lcp.data();
+    }
     if (!getenv("CG_NO_SATID")) {      // transcriptAtPosition(SA[i]) per suffix-array index, as cg_index.cu::build_satid makes it
         E->satid.resize(n);
         for (uint64_t i = 0; i < n; ++i) { uint32_t tid, local; tid_of(E->v, E->sa[i], tid, local); E->satid[i] = tid; }
