@@ -402,6 +402,36 @@ def main():
         e2e = {"value": world * n / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned", "sessions": NS, "batch_pairs": ebatch,
                "call": "cg_session_submit" if args.e2e_offsets else "cg_session_submit_fixed"}
+        # what the host-to-device path of this box gives: 1 GiB page-locked pieces, every rank copying at the same time (the concurrent
+        # ceiling the end-to-end leg is measured against: at N = 8 the ranks share the host's memory and PCIe root complexes)
+        try:
+            hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+            dv = torch.empty(1 << 30, dtype=torch.uint8, device=torch.device("cuda", local))
+            dv.copy_(hp, non_blocking=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(4):
+                dv.copy_(hp, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            gbs = 4 * (1 << 30) / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+            if world > 1:
+                t = torch.tensor([gbs], dtype=torch.float64, device=torch.device("cuda", local))
+                dist.all_reduce(t)                      # aggregate over the ranks
+                gbs_all = float(t.item())
+            else:
+                gbs_all = gbs
+            e2e["h2d_ceiling_gbs"] = gbs_all
+            e2e["h2d_gbs"] = world * h2d / (dte / args.steps) / 1e9
+            e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs"] / gbs_all
+            e2e["h2d_ceiling_how"] = "4 x 1 GiB cudaMemcpyAsync from page-locked memory per rank, all ranks at once, summed"
+            del hp, dv
+        except Exception as ex:                                   # a measurement beside the metric: never fatal
+            e2e["h2d_ceiling_gbs"] = None
+            sys.stderr.write("h2d ceiling not measured: %r\n" % (ex,))
         if affinity:
             e2e["cpu_affinity"] = affinity
         for x in SS[len(RSS):]:

@@ -96,6 +96,7 @@ def lib():
     L.cg_index_close.argtypes = [vp]
     L.cg_index_close.restype = None
     L.cg_index_get_info.argtypes = [vp, ctypes.POINTER(_IndexInfo)]
+    L.cg_index_dir_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(_IndexInfo), ctypes.POINTER(ctypes.c_int)]
     L.cg_index_tx_name.argtypes = [vp, u32]
     L.cg_index_tx_name.restype = cp
     L.cg_index_set_tx_name.argtypes = [vp, u32, cp]
@@ -202,6 +203,14 @@ class Index:
 
     def save(self, directory):
         _check(lib().cg_index_save(self._h, os.fsencode(directory)))
+
+    @staticmethod
+    def dir_info(directory):
+        """What an index directory holds, read on the host (no device): dict(text_len, n_tx, k, n_kmers, hash_capacity, layout);
+        layout 1 = the reference's file set only (txpInfo.bin ...), 2 = with this library's cache beside it."""
+        info, lay = _IndexInfo(), ctypes.c_int(0)
+        _check(lib().cg_index_dir_info(os.fsencode(directory), ctypes.byref(info), ctypes.byref(lay)))
+        return dict(text_len=info.text_len, n_tx=info.n_tx, k=info.k, n_kmers=info.n_kmers, hash_capacity=info.hash_capacity, layout=lay.value)
 
     def close(self):
         if self._h:

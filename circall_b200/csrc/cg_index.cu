@@ -400,11 +400,6 @@ int build_impl(int device, const char* text, uint64_t n, int k, const std::vecto
     return CG_OK;
 }
 
-// ---- directory layout (this library's own) ----
-//   header.json    human-readable summary; its presence marks a finished index (TxIndexer.cpp:192-193)
-//   meta.bin       magic "CGIDX001", k, n, n_tx, n_kmers, hcap, n_blocks  (uint64 each)
-//   offsets.bin    (n_tx + 1) uint32      names.txt   one transcript name per line
-//   text.bin       n_blocks x 32 B        sa.bin      n uint32         hash.bin    hcap x 16 B
 bool write_file(const std::string& path, const void* p, uint64_t bytes) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
@@ -497,28 +492,189 @@ int cg_index_save(const cg_index* idx, const char* dir) {
     catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index save failed: ") + e.what()); }
     catch (...) { CG_FAIL(CG_ERR_IO, "index save failed"); }
 }
+// ---- directory layout ---------------------------------------------------------------------------------------------------
+// The file set RapMap's indexer writes behind TxIndexer (recollected — no sample index ships with the reference, so
+// the layout is UNPINNED), which is what an existing -txIdx / -bsjIdx directory holds:
+//   header.json        cereal JSON: IndexType, IndexVersion, UsesKmers, KmerLen, BigSA, PerfectHash
+//   versionInfo.json   Sailfish: indexVersion, indexType, kmerLength            (read at Circall_wt.cpp:1691-1693)
+//   txpInfo.bin        cereal binary: vector<string> names, vector<IndexT> offsets, string text ('$'-joined), vector<uint32> lengths
+//                      (cereal binary = u64 element count, then the raw little-endian payload; a string = u64 length + bytes)
+//   sa.bin             cereal binary vector<IndexT>            rsd.bin   bit array with a 1 at every '$': u64 bit count + bytes
+//   hash.bin           sparsehash dense_hash_map dump — never read here and not written: the k-mer table is rebuilt from SA + text
+// plus this library's own cache beside them, so that opening does not have to rebuild anything:
+//   cg_meta.bin        magic "CGIDX002", k, n, n_tx, n_kmers, hcap, n_blocks   (uint64 each)
+//   cg_text.bin        n_blocks x 32 B        cg_hash.bin    hcap x 16 B
+// cg_index_open reads names / offsets from txpInfo.bin; with a valid cache it loads cg_text.bin, sa.bin and cg_hash.bin, without
+// one (a directory the reference's TxIndexer wrote) it takes the text from txpInfo.bin and builds suffix array and table on the device.
+namespace {
+
+static const uint64_t CG_META_MAGIC = 0x3230305844494743ULL;   // "CGIDX002"
+
+struct RefDir {
+    std::vector<std::string> names;
+    std::vector<uint32_t> offsets;     // n_tx + 1 (the text length appended)
+    std::string text;                  // only when asked for
+    uint64_t n = 0;
+    int k = 0;
+    bool big = false;
+};
+
+bool rd_u64(FILE* f, uint64_t& v) { return fread(&v, 8, 1, f) == 1; }
+
+// KmerLen / kmerLength from header.json or versionInfo.json (0 when neither says)
+int json_int(const std::string& path, const char* const* keys) {
+    std::ifstream in(path);
+    if (!in) return 0;
+    std::string js((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    for (const char* const* k = keys; *k; ++k) {
+        size_t p = js.find(std::string("\"") + *k + "\"");
+        if (p == std::string::npos) continue;
+        p = js.find(':', p);
+        if (p == std::string::npos) continue;
+        ++p;
+        while (p < js.size() && (js[p] == ' ' || js[p] == '\t' || js[p] == '"')) ++p;
+        if (js.compare(p, 4, "true") == 0) return 1;
+        if (js.compare(p, 5, "false") == 0) return 0;
+        int v = 0; bool any = false;
+        while (p < js.size() && js[p] >= '0' && js[p] <= '9') { v = v * 10 + (js[p] - '0'); ++p; any = true; }
+        if (any) return v;
+    }
+    return 0;
+}
+
+// txpInfo.bin (+ the k the JSON files state); the text itself only when want_text
+int read_refdir(const std::string& d, bool want_text, RefDir& R) {
+    static const char* const kkeys[] = {"KmerLen", "kmerLen", "kmerLength", nullptr};
+    static const char* const bkeys[] = {"BigSA", "bigSA", nullptr};
+    R.k = json_int(d + "/header.json", kkeys);
+    if (!R.k) R.k = json_int(d + "/versionInfo.json", kkeys);
+    if (!R.k) R.k = 31;                                                  // TxIndexer's default (TxIndexer.cpp:87)
+    R.big = json_int(d + "/header.json", bkeys) != 0;
+    struct stat st;
+    if (stat((d + "/txpInfo.bin").c_str(), &st) != 0) CG_FAIL(CG_ERR_IO, "not an index directory (no txpInfo.bin): " + d);
+    const uint64_t fsz = (uint64_t)st.st_size;
+    FILE* f = fopen((d + "/txpInfo.bin").c_str(), "rb");
+    if (!f) CG_FAIL(CG_ERR_IO, "cannot open " + d + "/txpInfo.bin");
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    auto bad = [&](const char* what) { cgi::set_error(std::string("txpInfo.bin: ") + what); return (int)CG_ERR_IO; };
+    uint64_t n_tx = 0;
+    if (!rd_u64(f, n_tx) || n_tx == 0 || n_tx > fsz / 8) return bad("transcript count out of range");
+    R.names.resize((size_t)n_tx);
+    for (uint64_t t = 0; t < n_tx; ++t) {
+        uint64_t len = 0;
+        if (!rd_u64(f, len) || len > 65536) return bad("name length out of range");
+        R.names[t].resize((size_t)len);
+        if (len && fread(&R.names[t][0], 1, (size_t)len, f) != len) return bad("truncated name");
+    }
+    uint64_t n_off = 0;
+    if (!rd_u64(f, n_off) || n_off != n_tx) return bad("offset count does not match the transcript count");
+    const long at_off = ftell(f);
+    // IndexT is int32 unless the text needed the 64-bit index (BigSA): take what header.json says, and check it against the
+    // position of the text's length field either way
+    int width = R.big ? 8 : 4;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        uint64_t tl = 0;
+        if (fseek(f, at_off + (long)(n_off * (uint64_t)width), SEEK_SET) == 0 && rd_u64(f, tl) && tl > 0 &&
+            (uint64_t)at_off + n_off * (uint64_t)width + 8 + tl + 8 + n_tx * 4 <= fsz) { R.n = tl; break; }
+        width = 12 - width;
+    }
+    if (!R.n) return bad("cannot locate the text (neither 32- nor 64-bit offsets fit the file)");
+    if (R.n >= (1ULL << 31) - 128) { cgi::set_error("text >= 2^31: the 64-bit index (RapMapSAIndex<int64_t>) is not implemented"); return CG_ERR_LENGTH; }
+    fseek(f, at_off, SEEK_SET);
+    R.offsets.resize((size_t)n_tx + 1);
+    for (uint64_t t = 0; t < n_tx; ++t) {
+        uint64_t v = 0;
+        if (fread(&v, (size_t)width, 1, f) != 1) return bad("truncated offsets");
+        if (v >= R.n || (t && v <= R.offsets[t - 1])) return bad("offsets must increase and lie inside the text");
+        R.offsets[t] = (uint32_t)v;
+    }
+    R.offsets[n_tx] = (uint32_t)R.n;
+    if (R.offsets[0] != 0) return bad("first offset must be 0");
+    uint64_t tl = 0;
+    rd_u64(f, tl);
+    if (want_text) {
+        R.text.resize((size_t)R.n);
+        if (fread(&R.text[0], 1, (size_t)R.n, f) != R.n) return bad("truncated text");
+        if (R.text[R.n - 1] != '$') return bad("text must end with '$'");
+        for (uint64_t t = 1; t <= n_tx; ++t)
+            if (R.text[R.offsets[t] - 1] != '$') return bad("a transcript does not end with '$' where the next offset says");
+    }
+    return CG_OK;
+}
+
+void put_u64(std::string& o, uint64_t v) { o.append((const char*)&v, 8); }
+
+// the ASCII text ('$'-joined) back from the device's 2-bit blocks
+int text_from_device(const cg_index* idx, std::string& text) {
+    std::vector<uint4> blk((size_t)idx->n_blocks * 2);
+    CG_CUDA(cudaMemcpy(blk.data(), idx->d_text, idx->n_blocks * 32, cudaMemcpyDeviceToHost));
+    text.resize((size_t)idx->n);
+    for (uint64_t p = 0; p < idx->n; ++p) {
+        const uint4& c = blk[2 * (p >> 6)]; const uint4& m = blk[2 * (p >> 6) + 1];
+        const uint32_t o = (uint32_t)(p & 63);
+        const uint64_t codes = o < 32 ? ((uint64_t)c.x | ((uint64_t)c.y << 32)) : ((uint64_t)c.z | ((uint64_t)c.w << 32));
+        const uint64_t mask = (uint64_t)m.x | ((uint64_t)m.y << 32);
+        text[(size_t)p] = ((mask >> o) & 1ULL) ? '$' : "ACGT"[(codes >> (2 * (o & 31))) & 3ULL];
+    }
+    return CG_OK;
+}
+
+} // namespace
+
 static int index_save_impl(const cg_index* idx, const char* dir) {
     CG_CUDA(cudaSetDevice(idx->device));
     std::string d(dir);
     if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) CG_FAIL(CG_ERR_IO, "cannot create directory " + d);
-    uint64_t meta[8] = {0x3130305844494743ULL /* "CGIDX001" */, (uint64_t)idx->k, idx->n, idx->n_tx, idx->n_kmers, idx->hcap, idx->n_blocks, 0};
-    if (!write_file(d + "/meta.bin", meta, sizeof meta)) CG_FAIL(CG_ERR_IO, "cannot write " + d + "/meta.bin");
-    if (!write_file(d + "/offsets.bin", idx->offsets.data(), idx->offsets.size() * 4)) CG_FAIL(CG_ERR_IO, "cannot write offsets.bin");
-    {
-        std::string nm;
-        for (auto& s : idx->names) { nm += s; nm += '\n'; }
-        if (!write_file(d + "/names.txt", nm.data(), nm.size())) CG_FAIL(CG_ERR_IO, "cannot write names.txt");
-    }
     int rc;
-    if ((rc = save_dev(d + "/text.bin", idx->d_text, idx->n_blocks * 32))) return rc;
-    if ((rc = save_dev(d + "/sa.bin", idx->d_sa, idx->n * 4))) return rc;
-    if ((rc = save_dev(d + "/hash.bin", idx->d_hslots, idx->hcap * 16))) return rc;
-    char js[512];
+    // ---- the reference's file set
+    std::string text;
+    if ((rc = text_from_device(idx, text))) return rc;
+    {
+        std::string o;
+        put_u64(o, idx->n_tx);
+        for (auto& s : idx->names) { put_u64(o, s.size()); o += s; }
+        put_u64(o, idx->n_tx);
+        o.append((const char*)idx->offsets.data(), (size_t)idx->n_tx * 4);          // IndexT = int32 (text < 2^31)
+        put_u64(o, idx->n);
+        FILE* f = fopen((d + "/txpInfo.bin").c_str(), "wb");
+        if (!f) CG_FAIL(CG_ERR_IO, "cannot write " + d + "/txpInfo.bin");
+        bool ok = fwrite(o.data(), 1, o.size(), f) == o.size() && fwrite(text.data(), 1, text.size(), f) == text.size();
+        std::string l;
+        put_u64(l, idx->n_tx);
+        for (uint32_t t = 0; t < idx->n_tx; ++t) { const uint32_t len = idx->offsets[t + 1] - idx->offsets[t] - 1; l.append((const char*)&len, 4); }
+        ok = ok && fwrite(l.data(), 1, l.size(), f) == l.size();
+        if (fclose(f) != 0 || !ok) CG_FAIL(CG_ERR_IO, "cannot write " + d + "/txpInfo.bin");
+    }
+    {
+        std::vector<char> h(8 + idx->n * 4);
+        memcpy(h.data(), &idx->n, 8);
+        CG_CUDA(cudaMemcpy(h.data() + 8, idx->d_sa, idx->n * 4, cudaMemcpyDeviceToHost));
+        if (!write_file(d + "/sa.bin", h.data(), h.size())) CG_FAIL(CG_ERR_IO, "cannot write sa.bin");
+    }
+    {
+        std::vector<unsigned char> bits(8 + (idx->n + 7) / 8, 0);
+        memcpy(bits.data(), &idx->n, 8);
+        for (uint64_t p = 0; p < idx->n; ++p) if (text[(size_t)p] == '$') bits[8 + (p >> 3)] |= (unsigned char)(1u << (p & 7));
+        if (!write_file(d + "/rsd.bin", bits.data(), bits.size())) CG_FAIL(CG_ERR_IO, "cannot write rsd.bin");
+    }
+    text.clear(); text.shrink_to_fit();
+    char js[768];
     snprintf(js, sizeof js,
-             "{\n  \"IndexType\": \"circall_b200 quasi-index\",\n  \"IndexVersion\": \"CGIDX001\",\n  \"usesKmers\": true,\n"
-             "  \"kmerLen\": %d,\n  \"bigSA\": false,\n  \"perfectHash\": false,\n  \"textLen\": %llu,\n  \"numTranscripts\": %u,\n"
-             "  \"numKmers\": %llu\n}\n",
+             "{\n    \"value0\": {\n        \"IndexType\": 1,\n        \"IndexVersion\": \"q3\",\n        \"UsesKmers\": true,\n"
+             "        \"KmerLen\": %d,\n        \"BigSA\": false,\n        \"PerfectHash\": false,\n        \"writer\": \"circall_b200\",\n"
+             "        \"textLen\": %llu,\n        \"numTranscripts\": %u,\n        \"numKmers\": %llu\n    }\n}\n",
              idx->k, (unsigned long long)idx->n, idx->n_tx, (unsigned long long)idx->n_kmers);
+    {
+        char vj[256];
+        snprintf(vj, sizeof vj, "{\n    \"indexVersion\": 2,\n    \"indexType\": 1,\n    \"kmerLength\": %d\n}\n", idx->k);
+        if (!write_file(d + "/versionInfo.json", vj, strlen(vj))) CG_FAIL(CG_ERR_IO, "cannot write versionInfo.json");
+    }
+    // ---- this library's cache
+    if ((rc = save_dev(d + "/cg_text.bin", idx->d_text, idx->n_blocks * 32))) return rc;
+    if ((rc = save_dev(d + "/cg_hash.bin", idx->d_hslots, idx->hcap * 16))) return rc;
+    uint64_t meta[8] = {CG_META_MAGIC, (uint64_t)idx->k, idx->n, idx->n_tx, idx->n_kmers, idx->hcap, idx->n_blocks, 0};
+    if (!write_file(d + "/cg_meta.bin", meta, sizeof meta)) CG_FAIL(CG_ERR_IO, "cannot write " + d + "/cg_meta.bin");
+    // header.json last: its presence marks a finished index (TxIndexer.cpp:192-193)
     if (!write_file(d + "/header.json", js, strlen(js))) CG_FAIL(CG_ERR_IO, "cannot write header.json");
     return CG_OK;
 }
@@ -528,52 +684,78 @@ static bool file_size_is(const std::string& path, uint64_t bytes) {
     return stat(path.c_str(), &st) == 0 && (uint64_t)st.st_size == bytes;
 }
 
+// is the cache beside the reference's files usable for this text?  (nothing in cg_meta.bin is trusted: every field is checked
+// against the others, against txpInfo.bin and against the files' sizes before anything is allocated or indexed with it)
+static bool cache_valid(const std::string& d, const RefDir& R, uint64_t meta[8]) {
+    if (!file_size_is(d + "/cg_meta.bin", 64) || !read_file(d + "/cg_meta.bin", meta, 64) || meta[0] != CG_META_MAGIC) return false;
+    const uint64_t k = meta[1], n = meta[2], n_tx = meta[3], n_kmers = meta[4], hcap = meta[5], n_blocks = meta[6];
+    if (k < 3 || k > 31 || (k & 1) == 0 || (int)k != R.k) return false;
+    if (n != R.n || n_tx + 1 != R.offsets.size()) return false;
+    if (n_blocks != (n + 63) / 64 + 1) return false;
+    if (hcap < 16 || (hcap & (hcap - 1)) != 0 || hcap > (1ULL << 33) || n_kmers >= hcap) return false;
+    return file_size_is(d + "/cg_text.bin", n_blocks * 32) && file_size_is(d + "/sa.bin", 8 + n * 4) && file_size_is(d + "/cg_hash.bin", hcap * 16);
+}
+
 static int index_open_impl(const char* dir, int device, cg_index** out) {
     std::string d(dir);
+    RefDir R;
+    int rc = read_refdir(d, false, R);
+    if (rc) return rc;
     uint64_t meta[8];
-    if (!file_size_is(d + "/meta.bin", sizeof meta) || !read_file(d + "/meta.bin", meta, sizeof meta) || meta[0] != 0x3130305844494743ULL)
-        CG_FAIL(CG_ERR_IO, "not a circall_b200 index directory: " + d);
-    // nothing in meta.bin is trusted: every field is checked against the others and against the files' sizes before anything is
-    // allocated or indexed with it
-    const uint64_t k = meta[1], n = meta[2], n_tx = meta[3], n_kmers = meta[4], hcap = meta[5], n_blocks = meta[6];
-    if (k < 3 || k > 31 || (k & 1) == 0) CG_FAIL(CG_ERR_IO, "meta.bin: k must be odd and <= 31");
-    if (n == 0 || n >= (1ULL << 31) - 128) CG_FAIL(CG_ERR_IO, "meta.bin: text length out of range");
-    if (n_tx == 0 || n_tx > n) CG_FAIL(CG_ERR_IO, "meta.bin: transcript count out of range");
-    if (n_blocks != (n + 63) / 64 + 1) CG_FAIL(CG_ERR_IO, "meta.bin: text block count does not match the text length");
-    if (hcap < 16 || (hcap & (hcap - 1)) != 0 || hcap > (1ULL << 33) || n_kmers >= hcap) CG_FAIL(CG_ERR_IO, "meta.bin: table capacity must be a power of two above the k-mer count");
-    if (!file_size_is(d + "/offsets.bin", (n_tx + 1) * 4)) CG_FAIL(CG_ERR_IO, "offsets.bin has the wrong size");
-    if (!file_size_is(d + "/text.bin", n_blocks * 32)) CG_FAIL(CG_ERR_IO, "text.bin has the wrong size");
-    if (!file_size_is(d + "/sa.bin", n * 4)) CG_FAIL(CG_ERR_IO, "sa.bin has the wrong size");
-    if (!file_size_is(d + "/hash.bin", hcap * 16)) CG_FAIL(CG_ERR_IO, "hash.bin has the wrong size");
-    int rc = check_device(device);
+    if (!cache_valid(d, R, meta)) {
+        // a directory without this library's cache (the reference's TxIndexer wrote it): text from txpInfo.bin, everything else rebuilt
+        if ((rc = read_refdir(d, true, R))) return rc;
+        cg_index* idx = nullptr;
+        rc = build_impl(device, R.text.data(), R.text.size(), R.k, &R.names, &idx);
+        if (rc) return rc;
+        idx->build_seconds = 0;
+        *out = idx;
+        return CG_OK;
+    }
+    rc = check_device(device);
     if (rc) return rc;
     cg_index* idx = new cg_index();
-    idx->device = device; idx->k = (int)k; idx->n = n; idx->n_tx = (uint32_t)n_tx;
-    idx->n_kmers = n_kmers; idx->hcap = hcap; idx->n_blocks = n_blocks;
+    idx->device = device; idx->k = (int)meta[1]; idx->n = meta[2]; idx->n_tx = (uint32_t)meta[3];
+    idx->n_kmers = meta[4]; idx->hcap = meta[5]; idx->n_blocks = meta[6];
     auto fail = [&](int code) { free_index_device(idx); delete idx; return code; };
-    idx->offsets.resize((size_t)idx->n_tx + 1);
-    if (!read_file(d + "/offsets.bin", idx->offsets.data(), idx->offsets.size() * 4)) { cgi::set_error("cannot read offsets.bin"); return fail(CG_ERR_IO); }
-    if (idx->offsets[0] != 0 || idx->offsets[idx->n_tx] != n) { cgi::set_error("offsets.bin: first / last offset do not match the text"); return fail(CG_ERR_IO); }
-    for (uint32_t t = 0; t < idx->n_tx; ++t)
-        if (idx->offsets[t + 1] <= idx->offsets[t]) { cgi::set_error("offsets.bin: offsets must increase"); return fail(CG_ERR_IO); }
+    idx->offsets = R.offsets;
+    idx->names = R.names;
+    if ((rc = load_dev(d + "/cg_text.bin", (void**)&idx->d_text, idx->n_blocks * 32))) return fail(rc);
     {
-        std::ifstream in(d + "/names.txt");
-        std::string s;
-        while (std::getline(in, s)) idx->names.push_back(s);
-        if (idx->names.size() != idx->n_tx) { cgi::set_error("names.txt does not match the transcript count"); return fail(CG_ERR_IO); }
+        std::vector<char> h(8 + idx->n * 4);
+        uint64_t cnt = 0;
+        if (!read_file(d + "/sa.bin", h.data(), h.size()) || (memcpy(&cnt, h.data(), 8), cnt != idx->n)) { cgi::set_error("sa.bin does not hold one 32-bit entry per text position"); return fail(CG_ERR_IO); }
+        cudaError_t e = cudaMalloc((void**)&idx->d_sa, idx->n * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(idx->d_sa, h.data() + 8, idx->n * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail(cgi::cuda_fail(e, "upload sa.bin", __FILE__, __LINE__));
     }
-    if ((rc = load_dev(d + "/text.bin", (void**)&idx->d_text, idx->n_blocks * 32))) return fail(rc);
-    if ((rc = load_dev(d + "/sa.bin", (void**)&idx->d_sa, idx->n * 4))) return fail(rc);
-    if ((rc = load_dev(d + "/hash.bin", (void**)&idx->d_hslots, idx->hcap * 16))) return fail(rc);
+    if ((rc = load_dev(d + "/cg_hash.bin", (void**)&idx->d_hslots, idx->hcap * 16))) return fail(rc);
     cudaError_t e = cudaMalloc((void**)&idx->d_offsets, idx->offsets.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(idx->d_offsets, idx->offsets.data(), idx->offsets.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(cgi::cuda_fail(e, "upload offsets", __FILE__, __LINE__));
-    if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter and the per-suffix transcript array are derived from
-    if ((rc = build_satid(idx))) return fail(rc);          // text + SA: not part of the directory
+    if ((rc = build_fbits(idx))) return fail(rc);          // the seed filter, the per-suffix transcript array and the lcp bytes are derived
+    if ((rc = build_satid(idx))) return fail(rc);          // from text + SA: not part of the directory
     if ((rc = build_lcp(idx))) return fail(rc);
     finish_sizes(idx);
     *out = idx;
     return CG_OK;
+}
+
+// what a directory holds, read on the host (no device needed): layout 1 = the reference's file set only, 2 = with this library's cache
+int cg_index_dir_info(const char* dir, cg_index_info* info, int* layout) {
+    if (!dir || !info) CG_FAIL(CG_ERR_ARG, "null argument");
+    try {
+        RefDir R;
+        int rc = read_refdir(dir, false, R);
+        if (rc) return rc;
+        uint64_t meta[8];
+        const bool cached = cache_valid(dir, R, meta);
+        memset(info, 0, sizeof *info);
+        info->text_len = R.n; info->n_tx = (uint32_t)(R.offsets.size() - 1); info->k = R.k; info->device = -1;
+        if (cached) { info->n_kmers = meta[4]; info->hash_capacity = meta[5]; }
+        if (layout) *layout = cached ? 2 : 1;
+        return CG_OK;
+    } catch (const std::exception& e) { CG_FAIL(CG_ERR_IO, std::string("index directory unreadable: ") + e.what()); }
 }
 
 int cg_index_open(const char* dir, int device, cg_index** out) {

@@ -46,7 +46,13 @@ int cg_device_count(int* n);
  * cg_index_build_fasta: same from a FASTA file, applying RapMap's record normalisation
  *    and keeping names up to the first whitespace.
  * cg_index_save / cg_index_open: replace the index directory I/O of SailfishIndex::load
- *   (include/ReadExperiment.hpp:66-67).  The directory layout is this library's own.
+ *   (include/ReadExperiment.hpp:66-67).  The directory holds the file set RapMap's indexer writes behind TxIndexer
+ *   (header.json, versionInfo.json, txpInfo.bin, sa.bin, rsd.bin — SURVEY.md B7: recollected, unpinned; hash.bin, a sparsehash
+ *   dump, is neither read nor written) plus this library's cache (cg_meta.bin, cg_text.bin, cg_hash.bin).  cg_index_open takes a
+ *   directory with the cache as it is and a directory without one — an existing -txIdx / -bsjIdx written by the reference's
+ *   TxIndexer — by reading the text from txpInfo.bin and rebuilding suffix array and k-mer table on the device.
+ * cg_index_dir_info: what a directory holds, read on the host (no device needed): text length, transcripts, k;
+ *   layout 1 = the reference's file set only, 2 = with this library's cache.
  */
 int cg_index_build(int device, const char* text, uint64_t n, int k, cg_index** out);
 int cg_index_build_fasta(int device, const char* fasta_path, int k, cg_index** out);
@@ -65,6 +71,7 @@ typedef struct {
     double build_seconds;   /* 0 for an opened index */
 } cg_index_info;
 int cg_index_get_info(const cg_index* idx, cg_index_info* info);
+int cg_index_dir_info(const char* dir, cg_index_info* info, int* layout);
 /* txpNames[t], txpLens[t], txpOffsets[t]  (ReadExperiment.hpp:126-135) */
 const char* cg_index_tx_name(const cg_index* idx, uint32_t t);
 int cg_index_set_tx_name(cg_index* idx, uint32_t t, const char* name);

@@ -34,6 +34,14 @@ def test_parse_fasta_fastq_mix(exe, tmp_path):
     p = run([exe + "/circall_gpu", "parse", "-1", str(a), str(c), "-2", str(b)])
     f = p.stdout.split()
     assert f[1] == "3" and f[3] == str(10 + 4 + 2 + 6 + 2 + 1)
+    # gzip files are read directly (zlib passes plain text through): no `gunzip -c` FIFO needed (Circall_source.sh:273)
+    import gzip
+    ag, bg = tmp_path / "a.fa.gz", tmp_path / "b.fq.gz"
+    ag.write_bytes(gzip.compress(a.read_bytes()))
+    bg.write_bytes(gzip.compress(b.read_bytes()[:len("@r1/2 x\nACGTAA\n+\nIIIIII\n@r2/2\nGG\n+r2/2\nII\n")]))
+    p = run([exe + "/circall_gpu", "parse", "-1", str(ag), "-2", str(bg)])
+    f = p.stdout.split()
+    assert f[1] == "2" and f[3] == str(10 + 4 + 6 + 2)
     # unequal record counts are an error, exit status 1 (the reference's error behaviour)
     p = run([exe + "/circall_gpu", "parse", "-1", str(a), "-2", str(b)], ok=False)
     assert p.returncode == 1 and "different numbers" in p.stderr

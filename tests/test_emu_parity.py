@@ -134,3 +134,32 @@ def test_seed_filter_exact_and_cheaper(small_world, monkeypatch):
         assert dead > 0 and filt > 0
         assert filt + table < 0.5 * cost[0][1], cost              # random accesses of the walks: at least halved
     assert cost[16][1] < 0.35 * cost[0][1], cost
+
+
+def test_lcp_extension_exact(small_world, monkeypatch):
+    """extendSearchNaive over a k-mer interval with the suffix array's lcp bytes (cg_thr.cuh::q_step, cg_pre.cuh: the match length of a
+    suffix from that of the one before it and the lcp of the two; the text is read for the first suffix and where the two are equal)
+    against the same tiers comparing every suffix with the text: the outputs are the oracle's either way, and the lcp path compares far
+    fewer 32-base words."""
+    T, otx, obsj = small_world
+    r1, r2 = T.reads(78, 5000, L=100, circ_frac=0.05)
+    L = emu._lib()
+    import ctypes
+    L.emu_cost_log.restype = ctypes.c_uint64
+    L.emu_cost_log.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    words = {}
+    for no_lcp in (False, True):
+        if no_lcp:
+            monkeypatch.setenv("CG_NO_LCP", "1")
+        etx, ebsj = emu.EmuIndex(T.tx_text, otx.sa), emu.EmuIndex(T.bsj_text, obsj.sa)
+        for w in (0, 1):
+            L.emu_cost_log(w, None, 1)
+        _pipeline((T, otx, obsj, etx, ebsj), r1, r2, 0)
+        tot = 0
+        for w in (0, 1):
+            n = L.emu_cost_log(w, None, 0)
+            a = np.zeros(n, np.uint32)
+            L.emu_cost_log(w, a.ctypes.data, 1)
+            tot += int(a.reshape(-1, 10)[:, 2 + 4].sum())        # q_match word steps
+        words[no_lcp] = tot
+    assert 0 < words[False] < 0.6 * words[True], words

@@ -20,7 +20,7 @@ def build(force=False):
     srcs = [os.path.join(HERE, "circall_gpu_main.cpp"), os.path.join(HERE, "cg_host_io.hpp"), os.path.join(ROOT, "include", "circall_gpu.h")]
     if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(s) for s in srcs + [lib]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", srcs[0], "-o", exe, "-L" + os.path.dirname(lib), "-lcircall_gpu",
-                               "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath-link,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+                               "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath-link,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart", "-lz"])
     # the R stage's joins (SE / PE filters, final table) as a host-only tool
     flt, fsrc = os.path.join(out, "circall_filter"), os.path.join(HERE, "circall_filter.cpp")
     if force or not os.path.exists(flt) or os.path.getmtime(flt) < os.path.getmtime(fsrc):

@@ -4,7 +4,9 @@
 //   PairStream        pair_sequence_parser<char**> as Circall_wt.cpp:87,1197-1200 uses it: FASTA or FASTQ,
 //                     detected per file from its first byte; header = the whole line after '>' / '@' (spaces kept,
 //                     the R stage matches on it); any number of files per mate, read strictly sequentially so that
-//                     FIFOs (`<(gunzip -c x.fa.gz)`, Circall_source.sh:273) work.
+//                     FIFOs (`<(gunzip -c x.fa.gz)`, Circall_source.sh:273) work.  Files go through zlib, which passes plain
+//                     text through and inflates gzip: `-1 reads_1.fq.gz` needs no gunzip child any more (row N3, second half;
+//                     the inflate stays on the host).
 //   write_* helpers   the record formats of SURVEY Appendix C (Circall_wt.cpp:352-363,526-538; Circall_bsj.cpp:339-341,
 //                     366-368,392-399; ExportFeq.cpp:81-103).
 // Header-only, no CUDA: the CPU tests drive it through `circall_gpu parse`.
@@ -16,6 +18,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <zlib.h>
 
 namespace cgh {
 
@@ -23,29 +26,39 @@ namespace cgh {
 class SeqStream {
 public:
     explicit SeqStream(std::vector<std::string> files) : files_(std::move(files)) {}
-    ~SeqStream() { if (f_) fclose(f_); }
+    ~SeqStream() { if (f_) gzclose(f_); }
     // next record; false at the end of the last file.  Throws std::string on a malformed file.
     bool next(std::string& header, std::string& seq) {
         for (;;) {
             if (!f_) {
                 if (fi_ >= files_.size()) return false;
-                f_ = fopen(files_[fi_].c_str(), "rb");
+                f_ = gzopen(files_[fi_].c_str(), "rb");
                 if (!f_) throw std::string("cannot open ") + files_[fi_];
+                gzbuffer(f_, 1 << 20);
                 ++fi_;
-                kind_ = 0; have_line_ = false;
+                kind_ = 0; have_line_ = false; bp_ = bn_ = 0;
             }
             if (read_record(header, seq)) return true;
-            fclose(f_); f_ = nullptr;
+            gzclose(f_); f_ = nullptr;
         }
     }
 
 private:
+    int getc_buf() {
+        if (bp_ == bn_) {
+            const int n = gzread(f_, buf_, (unsigned)sizeof buf_);
+            if (n < 0) { int e = 0; const char* m = gzerror(f_, &e); throw std::string("read error in ") + files_[fi_ - 1] + ": " + (m ? m : "?"); }
+            if (n == 0) return EOF;
+            bp_ = 0; bn_ = (size_t)n;
+        }
+        return (unsigned char)buf_[bp_++];
+    }
     bool getline(std::string& s) {
         if (have_line_) { s.swap(line_); have_line_ = false; return true; }
         s.clear();
         int c;
         bool any = false;
-        while ((c = getc_unlocked(f_)) != EOF) {
+        while ((c = getc_buf()) != EOF) {
             any = true;
             if (c == '\n') break;
             s.push_back((char)c);
@@ -79,7 +92,9 @@ private:
     }
     std::vector<std::string> files_;
     size_t fi_ = 0;
-    FILE* f_ = nullptr;
+    gzFile f_ = nullptr;
+    char buf_[1 << 16];
+    size_t bp_ = 0, bn_ = 0;
     int kind_ = 0;
     std::string line_;
     bool have_line_ = false;
