@@ -634,36 +634,86 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
     return true;
 }
 
-// Circall_wt: over the mates list[..] the front kernel declined (all n_reads mates when list is null); ovf[r] = 1 hands mate r
-// to the warp kernels.  The list is grouped by look-up class: the lean instantiation (VOTE = false) takes its head
-// [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
-template <bool VOTE, bool DUMP>
+// The lockstep tier runs as two kernels per list: k_thr_col (the collector: q_begin, the q_step loop, q_vote — its intervals go to a
+// slot of the hand-over buffer) and k_wt_fin / k_bsj_fin (hit enumeration, full-length test / span filter, commit).  As one kernel
+// (72 KB of code for Circall_bsj) the warps of an SM, each at its own place in the collector or in the hit enumeration, ran out of the
+// 32 KB instruction cache: 56 % of k_bsj_thr's stall samples were instruction-fetch stalls (ncu r2s).  Split, each kernel's loop fits,
+// and the second one starts with all lanes of a warp at the same instruction.
+// Hand-over, slot x = position in the work list (cap slots): res[x] = status (int8) | nF << 8 | nR << 16, the intervals of the nF forward
+// then the nR reverse-complement entries as three words each, word j of slot x at iv[j * cap + x] (coalesced across a warp).
+static const int THR_IVW = 3 * cgq::Q_FI;          // words per slot; a two-strand read that keeps more than Q_FI intervals after the vote is declined
+
+// Over the work list[..] (null: all items): Circall_wt mates (BSJ = false: item = mate), or Circall_bsj records (BSJ = true: item = record,
+// read = exp_mate[item], or mate 1 of pair item when exp_mate is null).  The list is grouped by look-up class: the lean instantiation
+// (VOTE = false) takes its head [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
+template <bool VOTE, bool BSJ>
 __global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
-k_wt_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads, const uint32_t* __restrict__ list,
-         const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
-         uint8_t* __restrict__ ovf, const uint8_t* __restrict__ cls, IvDump dump) {
+k_thr_col(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_items,
+          const uint32_t* __restrict__ n_exp, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
+          int lceMode, const uint8_t* __restrict__ cls, uint32_t* __restrict__ res, uint32_t* __restrict__ iv, uint64_t cap) {
+    extern __shared__ uint32_t thr_smem[];
+    const uint64_t total = list ? (uint64_t)*n_list : (n_exp ? (uint64_t)*n_exp : n_items);
+    const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
+    const uint64_t x = lo + (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
+    if (x >= hi) return;
+    const uint64_t item = list ? (uint64_t)list[x] : x;
+    const uint64_t r = BSJ ? (exp_mate ? (uint64_t)exp_mate[item] : 2 * item) : item;
+    const int L = lens[r];
+    const IndexView& ix = cgw::c_ix[BSJ ? 1 : 0];
+    cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+    cgq::QState st; st.nF = st.nR = 0;
+    int status = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) ? cgq::q_begin<VOTE>(ix, m, L, cls ? (int)cls[item] - 1 : -1, st) : (int)cgq::QD_N;
+    while (status == cgq::Q_CONT) status = cgq::q_step<VOTE>(ix, m, lceMode, st);
+    if (status == cgq::Q_DONE) status = cgq::q_vote<VOTE>(ix, m, st);
+    int nF = status == cgq::Q_FOUND ? st.nF : 0, nR = status == cgq::Q_FOUND ? st.nR : 0;
+    if (VOTE && nF + nR > cgq::Q_FI) { status = cgq::QD_NINT; nF = nR = 0; }
+    res[x] = (uint32_t)(status & 0xff) | ((uint32_t)nF << 8) | ((uint32_t)nR << 16);
+    for (int i = 0; i < nF + nR; ++i) {
+        const int at = i < nF ? m.iv(0, i) : m.iv(1, i - nF);
+        iv[(uint64_t)(3 * i) * cap + x] = m.ld(at); iv[(uint64_t)(3 * i + 1) * cap + x] = m.ld(at + 1); iv[(uint64_t)(3 * i + 2) * cap + x] = m.ld(at + 2);
+    }
+}
+// the slot of work item x back into a thread's scratch: status, nF, nR
+template <bool VOTE>
+__device__ __forceinline__ int thr_take(const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, uint64_t x, const cgq::QMemT<VOTE>& m, int& nF, int& nR) {
+    const uint32_t w = res[x];
+    nF = (int)((w >> 8) & 0xffu); nR = (int)((w >> 16) & 0xffu);
+    for (int i = 0; i < nF + nR; ++i) {
+        const int at = i < nF ? m.iv(0, i) : m.iv(1, i - nF);
+        m.st(at, iv[(uint64_t)(3 * i) * cap + x]); m.st(at + 1, iv[(uint64_t)(3 * i + 1) * cap + x]); m.st(at + 2, iv[(uint64_t)(3 * i + 2) * cap + x]);
+    }
+    return (int)(int8_t)(w & 0xffu);
+}
+
+// Circall_wt after the collector: ovf[r] = 1 hands mate r to the warp kernels
+template <bool VOTE, bool DUMP>
+__global__ void __launch_bounds__(THR_THREADS, 12)
+k_wt_fin(const uint16_t* __restrict__ lens, uint64_t n_reads, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
+         const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
+         uint8_t* __restrict__ ovf, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : n_reads;
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
     const uint64_t x = lo + (uint64_t)blockIdx.x * THR_THREADS + threadIdx.x;
     if (x >= hi) return;
     const uint64_t r = list ? (uint64_t)list[x] : x;
-    const int L = lens[r], pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
-    cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
-    uint8_t fl = 0; uint32_t nh = 0; int why = 0, nF = 0, nR = 0;
-    const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_wt_mate<VOTE>(cgw::c_ix[0], m, L, pairLen, lceMode, fl, nh, why, nF, nR, cls ? (int)cls[r] - 1 : -1);
+    const int pairLen = lens[r & ~1ULL];          // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
+    cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = 0;
+    int nF, nR;
+    const int status = thr_take<VOTE>(res, iv, cap, x, m, nF, nR);
+    uint8_t fl = 0; uint32_t nh = 0; int why = status;
+    const bool done = status >= 0 && cgq::q_wt_finish<VOTE>(cgw::c_ix[0], m, status, pairLen, nF, nR, fl, nh, why);
     if (done) { flags[r] = fl; nhits[r] = nh; }
     else ovf[r] = 1;
-    if (DUMP && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
+    if (DUMP && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, status == cgq::Q_FOUND, m, nF, nR);
 }
 
-// Circall_bsj: over the records list[..] (every exported record when list is null); ovf[rec] = 1 hands record rec to the warp
-// kernels (nothing was emitted for it).  seg as in k_wt_thr.
+// Circall_bsj after the collector: rows to the junction buffer, per-BSJ counts, multi-transcript classes, per-record hits / split;
+// ovf[rec] = 1 hands the record to the warp kernels (nothing was emitted for it)
 template <bool VOTE, bool DUMP>
-__global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
-k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_fixed,
-          const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg, int lceMode, BsjOut o, int do_counts,
-          uint8_t* __restrict__ ovf, const uint8_t* __restrict__ cls, IvDump dump) {
+__global__ void __launch_bounds__(THR_THREADS, 12)
+k_bsj_fin(const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
+          const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -672,13 +722,13 @@ k_bsj_thr(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     const uint64_t rec = active && list ? (uint64_t)list[x] : x;
     uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;
     if (active) {
-        const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
-        const int L = lens[r];
-        cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+        cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = 0;
+        int nF, nR;
+        const int status = thr_take<VOTE>(res, iv, cap, x, m, nF, nR);
         JSink sink; sink.buf = o.junc; sink.cursor = &o.hdr->n_junc; sink.cap = o.junc_cap; sink.rec = (uint32_t)rec;
-        uint32_t nh = 0; bool split = false; int why = 0, at = 0, nF = 0, nR = 0;
-        const bool done = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) && cgq::q_bsj_record<VOTE>(cgw::c_ix[1], m, L, lceMode, sink, nh, split, at, why, nF, nR, cls ? (int)cls[rec] - 1 : -1);
-        if (DUMP && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, why == cgq::Q_FOUND, m, nF, nR);
+        uint32_t nh = 0; bool split = false; int why = status, at = 0;
+        const bool done = status >= 0 && cgq::q_bsj_finish<VOTE>(cgw::c_ix[1], m, status, nF, nR, sink, nh, split, at, why);
+        if (DUMP && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, status == cgq::Q_FOUND, m, nF, nR);
         if (!done) ovf[rec] = 1;
         else {
             // commit (Circall_bsj.cpp:383-491)
@@ -780,6 +830,8 @@ struct cg_session {
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
         d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3, d_exppair, d_expcode, d_cand;
     GrowBuf d_ivhead_wt, d_ivoff_wt, d_ivpool_wt, d_ivhead_bsj, d_ivoff_bsj, d_ivpool_bsj, d_ivcur;   // cg_opts::dump_intervals
+    GrowBuf d_thr_res, d_thr_iv;         // hand-over between the collector and the finishing kernels of the lockstep tier (thr_cap slots)
+    uint64_t thr_cap = 0;
     uint32_t iv_cap = 0;
     PinVec<uint32_t> h_ivhead_wt, h_ivoff_wt, h_ivhead_bsj, h_ivoff_bsj;
     PinVec<int4> h_ivpool_wt, h_ivpool_bsj;
@@ -914,14 +966,26 @@ int run_bsj_stage(cg_session* s, int do_counts) {
         rc = compact_classes(s, s->d_ovf3.as<uint8_t>(), worst, s->d_list.as<uint32_t>(), &dh->n_t2_bsj);
         if (rc) return rc;
         const uint32_t* seg = (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(worst, CP_TILE));
-        rc = launch(s, dbs.head ? k_bsj_thr<false, true> : k_bsj_thr<false, false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4,
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (const uint8_t*)s->d_ovf3.as<uint8_t>(), dbs);
-        if (rc) return rc;
-        rc = launch(s, dbs.head ? k_bsj_thr<true, true> : k_bsj_thr<true, false>, dim3(grid_for(worst, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4,
-                    s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list.as<uint32_t>(), (const uint32_t*)&dh->n_t2_bsj, seg,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf.as<uint8_t>(), (const uint8_t*)s->d_ovf3.as<uint8_t>(), dbs);
-        if (rc) return rc;
+        {
+            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4;
+            const size_t sf0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(0) * 4, sf1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(0) * 4;
+            const dim3 grid(grid_for(worst, THR_THREADS)), blk2(THR_THREADS);
+            const uint32_t* l2 = (const uint32_t*)s->d_list.as<uint32_t>(); const uint32_t* n2 = (const uint32_t*)&dh->n_t2_bsj;
+            const uint32_t* nexp = em ? (const uint32_t*)&dh->n_exp : (const uint32_t*)nullptr;
+            uint32_t* res = s->d_thr_res.as<uint32_t>(); uint32_t* ivb = s->d_thr_iv.as<uint32_t>();
+            rc = launch(s, k_thr_col<false, true>, grid, blk2, sm0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2, n2, seg,
+                        s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
+            if (rc) return rc;
+            rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2, n2, seg,
+                        s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
+            if (rc) return rc;
+            rc = launch(s, dbs.head ? k_bsj_fin<false, true> : k_bsj_fin<false, false>, grid, blk2, sf0, em, s->n_pairs, l2, n2, seg,
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+            if (rc) return rc;
+            rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs, l2, n2, seg,
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+            if (rc) return rc;
+        }
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
         if (rc) return rc;
         cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_bsj;
@@ -972,6 +1036,7 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_expcode.reserve(n_reads + 16));
     if (stage != 1) CG_CUDA(s->d_cand.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
+    if (s->use_thr) { s->thr_cap = n_reads; CG_CUDA(s->d_thr_res.reserve(n_reads * 4 + 16)); CG_CUDA(s->d_thr_iv.reserve(n_reads * 4 * (uint64_t)THR_IVW + 16)); }
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
         CG_CUDA(s->d_recnh.reserve(n_reads * 4));
@@ -1031,14 +1096,25 @@ int run_batch(cg_session* s) {
             // two-strand instantiation over the tail; an unsorted list (or none) goes through the lean one alone
             const bool sorted = cur_list && s->use_pre;
             const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
-            rc = launch(s, dwt.head ? k_wt_thr<false, true> : k_wt_thr<false, false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4,
-                        s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), sorted ? (const uint8_t*)s->d_ovf.as<uint8_t>() : (const uint8_t*)nullptr, dwt);
+            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4;
+            const size_t sf0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(0) * 4, sf1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(0) * 4;
+            const dim3 grid(grid_for(n_reads, THR_THREADS)), blk2(THR_THREADS);
+            const uint8_t* clsp = sorted ? (const uint8_t*)s->d_ovf.as<uint8_t>() : (const uint8_t*)nullptr;
+            uint32_t* res = s->d_thr_res.as<uint32_t>(); uint32_t* ivb = s->d_thr_iv.as<uint32_t>();
+            rc = launch(s, k_thr_col<false, false>, grid, blk2, sm0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
+                        cur_list, cur_n, seg, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
             if (rc) return rc;
             if (sorted) {
-                rc = launch(s, dwt.head ? k_wt_thr<true, true> : k_wt_thr<true, false>, dim3(grid_for(n_reads, THR_THREADS)), dim3(THR_THREADS), (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4,
-                            s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, seg, s->opts.lce_mode,
-                            s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (const uint8_t*)s->d_ovf.as<uint8_t>(), dwt);
+                rc = launch(s, k_thr_col<true, false>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
+                            cur_list, cur_n, seg, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
+                if (rc) return rc;
+            }
+            rc = launch(s, dwt.head ? k_wt_fin<false, true> : k_wt_fin<false, false>, grid, blk2, sf0, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
+            if (rc) return rc;
+            if (sorted) {
+                rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
+                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
                 if (rc) return rc;
             }
             rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
@@ -1179,7 +1255,7 @@ void cg_session_destroy(cg_session* s) {
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
                        &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3, &s->d_exppair, &s->d_expcode, &s->d_cand,
-                       &s->d_ivhead_wt, &s->d_ivoff_wt, &s->d_ivpool_wt, &s->d_ivhead_bsj, &s->d_ivoff_bsj, &s->d_ivpool_bsj, &s->d_ivcur})
+                       &s->d_ivhead_wt, &s->d_ivoff_wt, &s->d_ivpool_wt, &s->d_ivhead_bsj, &s->d_ivoff_bsj, &s->d_ivpool_bsj, &s->d_ivcur, &s->d_thr_res, &s->d_thr_iv})
         b->release();
     s->h_hdr.release();
     s->h_exp_pair.release(); s->h_exp_code.release(); s->h_cand.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();
