@@ -162,11 +162,17 @@ __device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) 
 #ifndef CG_WARP_MINB
 #define CG_WARP_MINB 4     // resident blocks per SM asked of the fast warp kernels: 64 registers, 32 warps per SM (the kernels are latency-bound)
 #endif
+// next work item of a warp, drawn from a counter (zero at launch)
+__device__ __forceinline__ uint64_t warp_draw(uint32_t* __restrict__ work, int lane) {
+    uint32_t x = 0;
+    if (lane == 0) x = atomicAdd(work, 1u);
+    return (uint64_t)__shfl_sync(0xffffffffu, x, 0);
+}
 template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, uint64_t n_reads,
           const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, int lceMode,
-          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump) {
+          uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump, uint32_t* __restrict__ work) {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, false) / 8);
@@ -174,7 +180,8 @@ k_wt_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     GenPtrs gp;
     if (GEN) gp = gen_ptrs(gscratch, warp);
     const uint64_t n = LIST ? (uint64_t)*n_list : n_reads;
-    for (uint64_t x = warp; x < n; x += nwarps) {
+    // the reads of a list differ a hundredfold in what they cost (repeat families): warps draw them from a counter instead of striding
+    for (uint64_t x = warp_draw(work, lane); x < n; x = warp_draw(work, lane)) {
         const uint64_t r = LIST ? (uint64_t)list[x] : x;
         int L = lens[r];
         int pairLen = lens[r & ~1ULL];             // readLen is mate 1's length for both mates (Circall_wt.cpp:242)
@@ -268,7 +275,7 @@ k_wt_commit(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ nhit
 }
 
 // ---- ordered compaction of a byte-flag array: indices of the set flags, in order -----------------
-static const int CP_THREADS = 256, CP_ITEMS = 4, CP_TILE = CP_THREADS * CP_ITEMS;
+static const int CP_THREADS = 256, CP_ITEMS = 16, CP_TILE = CP_THREADS * CP_ITEMS;     // (4 items: 4 x the tiles, and the single-block scan of 16 class counts per tile took 0.2 ms per stage)
 
 __global__ void __launch_bounds__(CP_THREADS)
 k_flag_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ bc) {
@@ -283,13 +290,19 @@ k_flag_count(const uint8_t* __restrict__ f, uint64_t n, uint32_t* __restrict__ b
 // exclusive scan of nb block counts by one block; total -> *total
 __global__ void __launch_bounds__(1024)
 k_flag_scan(uint32_t* bc, uint32_t nb, uint32_t* total) {
+    // one block, SCAN_ITEMS consecutive counts per thread and trip (the class sort scans 16 counts per tile: 250 k entries for 8 M pairs —
+    // one entry per thread and trip took 0.22 ms, a launch-sized hole in the middle of every stage)
+    const int SCAN_ITEMS = 8;
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nb ? bc[i] : 0, x = v;
+    for (uint32_t base = 0; base < nb; base += 1024 * SCAN_ITEMS) {
+        const uint32_t i0 = base + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = i0 + j < nb ? bc[i0 + j] : 0; sum += v[j]; }
+        uint32_t x = sum;
         int l = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (l >= d) x += y; }
@@ -302,10 +315,11 @@ k_flag_scan(uint32_t* bc, uint32_t nb, uint32_t* total) {
             wsum[l] = z - s;
         }
         __syncthreads();
-        uint32_t excl = carry + wsum[w] + x - v;
-        if (i < nb) bc[i] = excl;
+        uint32_t excl = carry + wsum[w] + x - sum;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) { if (i0 + j < nb) bc[i0 + j] = excl; excl += v[j]; }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 1023) carry = excl;
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
@@ -430,7 +444,7 @@ template <bool GEN, bool LIST>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, GEN ? CG_GEN_MINB : CG_WARP_MINB)
 k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g,
            const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list,
-           int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump) {
+           int lceMode, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, unsigned char* gscratch, IvDump dump, uint32_t* __restrict__ work) {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t* mine = smem + (size_t)wib * (warp_smem_bytes(g, GEN, true) / 8);
@@ -440,7 +454,7 @@ k_bsj_warp(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, P
     if (GEN) gp = gen_ptrs(gscratch, warp);
     const uint64_t n = LIST ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     uint32_t obs = 0, mapped = 0, hits = 0, upper = 0;          // per-warp totals (kept by every lane alike)
-    for (uint64_t x = warp; x < n; x += nwarps) {
+    for (uint64_t x = warp_draw(work, lane); x < n; x = warp_draw(work, lane)) {
         const uint64_t rec = LIST ? (uint64_t)list[x] : x;
         const uint64_t r = exp_mate ? (uint64_t)exp_mate[rec] : 2 * rec;
         int L = lens[r];
@@ -616,6 +630,9 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
 #define CG_THR_THREADS 64        // measured 32 / 64 / 128 / 256: k_bsj_thr 7.70 / 7.45 / 7.57 / 7.70 ms, the two-strand kernels 0.41 / 0.41 / 0.56 / 0.64
 #endif
 static const int THR_THREADS = CG_THR_THREADS;
+#ifndef CG_THR_VOTE_MINB
+#define CG_THR_VOTE_MINB 5      // resident blocks per SM (x 128 threads) of the two-strand collector (measured, step of 8 M pairs: 3 -> 21.74 ms, 4 -> 21.48, 5 -> 21.41)
+#endif
 // stage the packed read of this thread into its scratch; false when the read holds an N (or is empty)
 template <class M>
 __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, const PackGeom& g, int L, const M& m) {
@@ -647,7 +664,7 @@ static const int THR_IVW = 3 * cgq::Q_FI;          // words per slot; a two-stra
 // read = exp_mate[item], or mate 1 of pair item when exp_mate is null).  The list is grouped by look-up class: the lean instantiation
 // (VOTE = false) takes its head [0, *seg), the two-strand one its tail [*seg, *n_list); seg null = one instantiation over everything.
 template <bool VOTE, bool BSJ>
-__global__ void __launch_bounds__(THR_THREADS, (VOTE ? 3 : CG_THR_MINB) * (128 / THR_THREADS))
+__global__ void __launch_bounds__(THR_THREADS, (VOTE ? CG_THR_VOTE_MINB : CG_THR_MINB) * (128 / THR_THREADS))
 k_thr_col(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, PackGeom g, const uint32_t* __restrict__ exp_mate, uint64_t n_items,
           const uint32_t* __restrict__ n_exp, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
           int lceMode, const uint8_t* __restrict__ cls, uint32_t* __restrict__ res, uint32_t* __restrict__ iv, uint64_t cap) {
@@ -690,7 +707,7 @@ template <bool VOTE, bool DUMP>
 __global__ void __launch_bounds__(THR_THREADS, 12)
 k_wt_fin(const uint16_t* __restrict__ lens, uint64_t n_reads, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
          const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, uint8_t* __restrict__ flags, uint32_t* __restrict__ nhits,
-         uint8_t* __restrict__ ovf, IvDump dump) {
+         uint8_t* __restrict__ ovf, uint8_t* __restrict__ retry, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : n_reads;
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -704,6 +721,7 @@ k_wt_fin(const uint16_t* __restrict__ lens, uint64_t n_reads, const uint32_t* __
     uint8_t fl = 0; uint32_t nh = 0; int why = status;
     const bool done = status >= 0 && cgq::q_wt_finish<VOTE>(cgw::c_ix[0], m, status, pairLen, nF, nR, fl, nh, why);
     if (done) { flags[r] = fl; nhits[r] = nh; }
+    else if (!VOTE && retry && (status == cgq::QD_BOTH_A || status == cgq::QD_OTHER)) retry[r] = 1;      // the other strand scores too: the two-strand instantiation's read
     else ovf[r] = 1;
     if (DUMP && done) iv_dump_thread(dump, r, VOTE ? TIER_THR_VOTE : TIER_THR, status == cgq::Q_FOUND, m, nF, nR);
 }
@@ -713,7 +731,8 @@ k_wt_fin(const uint16_t* __restrict__ lens, uint64_t n_reads, const uint32_t* __
 template <bool VOTE, bool DUMP>
 __global__ void __launch_bounds__(THR_THREADS, 12)
 k_bsj_fin(const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ seg,
-          const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, BsjOut o, int do_counts, uint8_t* __restrict__ ovf, IvDump dump) {
+          const uint32_t* __restrict__ res, const uint32_t* __restrict__ iv, uint64_t cap, BsjOut o, int do_counts, uint8_t* __restrict__ ovf,
+          uint8_t* __restrict__ retry, IvDump dump) {
     extern __shared__ uint32_t thr_smem[];
     const uint64_t total = list ? (uint64_t)*n_list : (exp_mate ? (uint64_t)o.hdr->n_exp : n_fixed);
     const uint64_t lo = (VOTE && seg) ? (uint64_t)*seg : 0, hi = (!VOTE && seg) ? (uint64_t)*seg : total;
@@ -729,8 +748,10 @@ k_bsj_fin(const uint32_t* __restrict__ exp_mate, uint64_t n_fixed, const uint32_
         uint32_t nh = 0; bool split = false; int why = status, at = 0;
         const bool done = status >= 0 && cgq::q_bsj_finish<VOTE>(cgw::c_ix[1], m, status, nF, nR, sink, nh, split, at, why);
         if (DUMP && done) iv_dump_thread(dump, rec, VOTE ? TIER_THR_VOTE : TIER_THR, status == cgq::Q_FOUND, m, nF, nR);
-        if (!done) ovf[rec] = 1;
-        else {
+        if (!done) {
+            if (!VOTE && retry && (status == cgq::QD_BOTH_A || status == cgq::QD_OTHER)) retry[rec] = 1;
+            else ovf[rec] = 1;
+        } else {
             // commit (Circall_bsj.cpp:383-491)
             o.rec_nhits[rec] = nh; o.rec_split[rec] = split ? 1 : 0;
             upper = nh > 0;                                                       // :383
@@ -830,6 +851,8 @@ struct cg_session {
     GrowBuf d_r1, d_r2, d_off1, d_off2, d_pk, d_lens, d_flags, d_nhits, d_expflag, d_mflags, d_mnhits, d_bc, d_exp,
         d_junc, d_eqent, d_eqtids, d_recnh, d_recsp, d_hdr, d_ovf, d_list, d_ovf2, d_list2, d_ovf3, d_list3, d_exppair, d_expcode, d_cand;
     GrowBuf d_ivhead_wt, d_ivoff_wt, d_ivpool_wt, d_ivhead_bsj, d_ivoff_bsj, d_ivpool_bsj, d_ivcur;   // cg_opts::dump_intervals
+    GrowBuf d_ovf4, d_list4, d_work;     // second pass of the two-strand instantiation: retry flags, list, counts
+    bool use_retry = true;
     GrowBuf d_thr_res, d_thr_iv;         // hand-over between the collector and the finishing kernels of the lockstep tier (thr_cap slots)
     uint64_t thr_cap = 0;
     uint32_t iv_cap = 0;
@@ -967,7 +990,7 @@ int run_bsj_stage(cg_session* s, int do_counts) {
         if (rc) return rc;
         const uint32_t* seg = (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(worst, CP_TILE));
         {
-            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(s->geom.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(s->geom.W2f + 1) * 4;
+            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words_col(s->geom.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words_col(s->geom.W2f + 1) * 4;
             const size_t sf0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(0) * 4, sf1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(0) * 4;
             const dim3 grid(grid_for(worst, THR_THREADS)), blk2(THR_THREADS);
             const uint32_t* l2 = (const uint32_t*)s->d_list.as<uint32_t>(); const uint32_t* n2 = (const uint32_t*)&dh->n_t2_bsj;
@@ -979,33 +1002,51 @@ int run_bsj_stage(cg_session* s, int do_counts) {
             rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2, n2, seg,
                         s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
             if (rc) return rc;
+            CG_CUDA(cudaMemsetAsync(s->d_ovf4.p, 0, worst, s->stream));
+            uint8_t* retry = s->use_retry ? s->d_ovf4.as<uint8_t>() : (uint8_t*)nullptr;
             rc = launch(s, dbs.head ? k_bsj_fin<false, true> : k_bsj_fin<false, false>, grid, blk2, sf0, em, s->n_pairs, l2, n2, seg,
-                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), retry, dbs);
             if (rc) return rc;
             rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs, l2, n2, seg,
-                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), dbs);
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), (uint8_t*)nullptr, dbs);
             if (rc) return rc;
+            if (retry) {
+                // second pass: what the lean instantiation declined because the other strand scored, through the two-strand one
+                // (a sixth of the warp kernels' cost per read)
+                uint32_t* n4 = s->d_work.as<uint32_t>() + 1;
+                rc = compact_flags(s, retry, worst, s->d_list4.as<uint32_t>(), n4);
+                if (rc) return rc;
+                rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp,
+                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
+                            s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
+                if (rc) return rc;
+                rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs,
+                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
+                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), (uint8_t*)nullptr, dbs);
+                if (rc) return rc;
+            }
         }
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
         if (rc) return rc;
         cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_bsj;
     }
     CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, worst, s->stream));
+    CG_CUDA(cudaMemsetAsync(s->d_work.as<uint32_t>() + 4, 0, 16, s->stream));          // draw counters of the two warp kernels
     const uint8_t* ovf_fast = s->d_ovf2.as<uint8_t>();
     if (cur_list)
         rc = launch(s, k_bsj_warp<false, true>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, cur_list, cur_n,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs, s->d_work.as<uint32_t>() + 4);
     else
         rc = launch(s, k_bsj_warp<false, false>, dim3(s->warp_grid_bsj), blk, smf,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)nullptr, (const uint32_t*)nullptr,
-                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs);
+                    s->opts.lce_mode, o, do_counts, s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dbs, s->d_work.as<uint32_t>() + 4);
     if (rc) return rc;
     rc = compact_flags(s, ovf_fast, worst, s->d_list2.as<uint32_t>(), &dh->n_ovf_bsj);
     if (rc) return rc;
     rc = launch(s, k_bsj_warp<true, true>, dim3(s->gen_grid), blk, smg,
                 s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, (const uint32_t*)s->d_list2.as<uint32_t>(),
-                (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch, dbs);
+                (const uint32_t*)&dh->n_ovf_bsj, s->opts.lce_mode, o, do_counts, (uint8_t*)nullptr, s->d_gscratch, dbs, s->d_work.as<uint32_t>() + 5);
     if (rc) return rc;
     // the candidate list (records with a junction row and 1 .. maxReadOccs hits), in record order; d_ovf2 is free again
     rc = launch(s, k_cand_flag, dim3(grid_for(worst, 256)), dim3(256), 0, (const uint32_t*)o.rec_nhits, (const uint8_t*)o.rec_split,
@@ -1036,6 +1077,7 @@ int run_batch(cg_session* s) {
     CG_CUDA(s->d_expcode.reserve(n_reads + 16));
     if (stage != 1) CG_CUDA(s->d_cand.reserve(n_reads * 4 + 16));
     CG_CUDA(s->d_hdr.reserve(sizeof(BatchHdr)));
+    CG_CUDA(s->d_ovf4.reserve(n_reads + 16)); CG_CUDA(s->d_list4.reserve(n_reads * 4 + 16)); CG_CUDA(s->d_work.reserve(64));
     if (s->use_thr) { s->thr_cap = n_reads; CG_CUDA(s->d_thr_res.reserve(n_reads * 4 + 16)); CG_CUDA(s->d_thr_iv.reserve(n_reads * 4 * (uint64_t)THR_IVW + 16)); }
     if (s->opts.keep_mate_detail) { CG_CUDA(s->d_mflags.reserve(n_reads)); CG_CUDA(s->d_mnhits.reserve(n_reads * 2)); }
     if (stage != 1) {
@@ -1096,7 +1138,7 @@ int run_batch(cg_session* s) {
             // two-strand instantiation over the tail; an unsorted list (or none) goes through the lean one alone
             const bool sorted = cur_list && s->use_pre;
             const uint32_t* seg = sorted ? (const uint32_t*)(s->d_bc.as<uint32_t>() + (size_t)CLS_VOTE * grid_for(n_reads, CP_TILE)) : (const uint32_t*)nullptr;
-            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(g.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(g.W2f + 1) * 4;
+            const size_t sm0 = (size_t)THR_THREADS * cgq::QMemT<false>::words_col(g.W2f + 1) * 4, sm1 = (size_t)THR_THREADS * cgq::QMemT<true>::words_col(g.W2f + 1) * 4;
             const size_t sf0 = (size_t)THR_THREADS * cgq::QMemT<false>::words(0) * 4, sf1 = (size_t)THR_THREADS * cgq::QMemT<true>::words(0) * 4;
             const dim3 grid(grid_for(n_reads, THR_THREADS)), blk2(THR_THREADS);
             const uint8_t* clsp = sorted ? (const uint8_t*)s->d_ovf.as<uint8_t>() : (const uint8_t*)nullptr;
@@ -1109,12 +1151,27 @@ int run_batch(cg_session* s) {
                             cur_list, cur_n, seg, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
                 if (rc) return rc;
             }
+            CG_CUDA(cudaMemsetAsync(s->d_ovf4.p, 0, n_reads, s->stream));
+            uint8_t* retry = (s->use_retry && sorted) ? s->d_ovf4.as<uint8_t>() : (uint8_t*)nullptr;
             rc = launch(s, dwt.head ? k_wt_fin<false, true> : k_wt_fin<false, false>, grid, blk2, sf0, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
-                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), retry, dwt);
             if (rc) return rc;
             if (sorted) {
                 rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
-                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), dwt);
+                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (uint8_t*)nullptr, dwt);
+                if (rc) return rc;
+            }
+            if (retry) {
+                // second pass: what the lean instantiation declined because the other strand scored, through the two-strand one
+                uint32_t* n4 = s->d_work.as<uint32_t>() + 0;
+                rc = compact_flags(s, retry, n_reads, s->d_list4.as<uint32_t>(), n4);
+                if (rc) return rc;
+                rc = launch(s, k_thr_col<true, false>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
+                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
+                if (rc) return rc;
+                rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads,
+                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
+                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (uint8_t*)nullptr, dwt);
                 if (rc) return rc;
             }
             rc = compact_flags(s, s->d_ovf3.as<uint8_t>(), n_reads, s->d_list3.as<uint32_t>(), &dh->n_t3_wt);
@@ -1122,21 +1179,22 @@ int run_batch(cg_session* s) {
             cur_list = s->d_list3.as<uint32_t>(); cur_n = &dh->n_t3_wt;
         }
         CG_CUDA(cudaMemsetAsync(s->d_ovf2.p, 0, n_reads, s->stream));
+        CG_CUDA(cudaMemsetAsync(s->d_work.as<uint32_t>() + 4, 0, 16, s->stream));      // draw counters of the two warp kernels
         const uint8_t* ovf_fast = s->d_ovf2.as<uint8_t>();
         if (cur_list)
             rc = launch(s, k_wt_warp<false, true>, dim3(s->warp_grid_wt), blk, smf,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, cur_list, cur_n, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt);
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt, s->d_work.as<uint32_t>() + 4);
         else
             rc = launch(s, k_wt_warp<false, false>, dim3(s->warp_grid_wt), blk, smf,
                         s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)nullptr, (const uint32_t*)nullptr, s->opts.lce_mode,
-                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt);
+                        s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf2.as<uint8_t>(), (unsigned char*)nullptr, dwt, s->d_work.as<uint32_t>() + 4);
         if (rc) return rc;
         rc = compact_flags(s, ovf_fast, n_reads, s->d_list2.as<uint32_t>(), &dh->n_ovf_wt);
         if (rc) return rc;
         rc = launch(s, k_wt_warp<true, true>, dim3(s->gen_grid), blk, smg,
                     s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, n_reads, (const uint32_t*)s->d_list2.as<uint32_t>(), (const uint32_t*)&dh->n_ovf_wt,
-                    s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch, dwt);
+                    s->opts.lce_mode, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), (uint8_t*)nullptr, s->d_gscratch, dwt, s->d_work.as<uint32_t>() + 5);
         if (rc) return rc;
         CG_CUDA(cudaEventRecord(s->evw, s->stream));
         rc = launch(s, k_wt_commit, dim3(grid_for(n_pairs, 256)), dim3(256), 0, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), n_pairs,
@@ -1219,6 +1277,7 @@ int cg_session_create(const cg_index* tx, const cg_index* bsj, const cg_opts* op
         s->sms = sms;
         s->use_pre = getenv("CG_NO_PRE") == nullptr;
         s->use_thr = getenv("CG_NO_THR") == nullptr;
+        s->use_retry = getenv("CG_NO_RETRY") == nullptr;
         // (the lockstep tier keeps table SECTOR numbers in 32 bits, cg_thr.cuh::q_walk: good for 2^33 slots = 137 GB of table, more than
         // the index builder can allocate next to the rest of an index, so no table size switches a tier off)
         s->warp_grid_wt = sms * (bw > 0 ? bw : 1);
@@ -1255,7 +1314,7 @@ void cg_session_destroy(cg_session* s) {
     for (GrowBuf* b : {&s->d_r1, &s->d_r2, &s->d_off1, &s->d_off2, &s->d_pk, &s->d_lens, &s->d_flags, &s->d_nhits, &s->d_expflag,
                        &s->d_mflags, &s->d_mnhits, &s->d_bc, &s->d_exp, &s->d_junc, &s->d_eqent, &s->d_eqtids, &s->d_recnh, &s->d_recsp, &s->d_hdr,
                        &s->d_ovf, &s->d_list, &s->d_ovf2, &s->d_list2, &s->d_ovf3, &s->d_list3, &s->d_exppair, &s->d_expcode, &s->d_cand,
-                       &s->d_ivhead_wt, &s->d_ivoff_wt, &s->d_ivpool_wt, &s->d_ivhead_bsj, &s->d_ivoff_bsj, &s->d_ivpool_bsj, &s->d_ivcur, &s->d_thr_res, &s->d_thr_iv})
+                       &s->d_ivhead_wt, &s->d_ivoff_wt, &s->d_ivpool_wt, &s->d_ivhead_bsj, &s->d_ivoff_bsj, &s->d_ivpool_bsj, &s->d_ivcur, &s->d_thr_res, &s->d_thr_iv, &s->d_ovf4, &s->d_list4, &s->d_work})
         b->release();
     s->h_hdr.release();
     s->h_exp_pair.release(); s->h_exp_code.release(); s->h_cand.release(); s->h_recnh.release(); s->h_eq_tids_raw.release(); s->h_recsp.release(); s->h_mflags.release();

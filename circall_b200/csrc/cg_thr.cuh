@@ -27,7 +27,7 @@
 //     needs the kmerScores vote (:442-490): declined.
 // Declined as well (nothing is emitted, the warp-per-read kernels redo the read from scratch with identical
 // results): N in the read, a homopolymer window among the looked-up positions, a k-mer interval starting at SA index
-// 0, an open interval wider than Q_W in the extension, more than Q_FI intervals, a maximal interval wider than Q_W in
+// 0, an open interval wider than Q_WL (Q_W without lcp bytes) in the extension, more than Q_FI intervals, a maximal interval wider than Q_WH in
 // the hit enumeration, an interval wider than Q_SPAN in the span filter.
 //
 // Hit enumeration: cg_warp.cuh::w_hits_lanes' exact shortcut (intervals whose query range lies inside a longer one
@@ -67,7 +67,9 @@ static const int QW = CG_THR_WALK;
 #endif
 static const int QX = CG_THR_EXT;
 static const int Q_FI = 8;        // intervals kept (one strand)
-static const int Q_W = 16;        // widest interval resolved suffix by suffix (extension, hit candidates, intersection)
+static const int Q_W = 16;        // widest k-mer interval the extension compares suffix by suffix with the text (an index without lcp bytes)
+static const int Q_WL = 256;      // widest k-mer interval the extension walks with the lcp bytes (a byte per suffix, the text only where two lengths tie)
+static const int Q_WH = 32;       // widest maximal interval in the hit enumeration (candidates, intersection: one bit per candidate)
 static const int Q_SPAN = 64;     // widest interval the span filter walks
 
 static const int Q_FK = 16;       // kmerScores entries (two-strand instantiation; <= 16: libstdc++'s sort is a plain insertion sort)
@@ -77,7 +79,7 @@ static const int Q_FK = 16;       // kmerScores entries (two-strand instantiatio
 //   [2 W2, 4 W2)      reverse-complement strand, same layout
 //   then 3 Q_FI       intervals of a strand: begin, end, len | qpos << 16   (VOTE: forward list, then reverse-complement list)
 //   VOTE: Q_FK        kmerScores entries (cg::ks_pack)
-//   then Q_W          hit candidates (transcript ids) of a strand            (VOTE: one area per strand)
+//   then Q_WH         hit candidates (transcript ids) of a strand            (VOTE: one area per strand; not in the collector kernel's scratch)
 template <bool VOTE>
 struct QMemT {
     uint32_t* base; int stride; int W2;
@@ -85,8 +87,9 @@ struct QMemT {
     CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
     CG_HD int iv(int s, int i) const { return 4 * W2 + 3 * ((VOTE ? s * Q_FI : 0) + i); }
     CG_HD int ks(int j) const { return 4 * W2 + 3 * Q_FI * 2 + j; }
-    CG_HD int cb(int s) const { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + s * Q_W : 0); }
-    CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + 2 * Q_W : Q_W); }
+    CG_HD int cb(int s) const { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + s * Q_WH : 0); }
+    CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + 2 * Q_WH : Q_WH); }
+    CG_HD static int words_col(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK : 0); }      // the collector alone: no candidates
     // 32-base window of strand s at oriented position i (i < L)
     CG_HD uint64_t chunk(int s, int i) const {
         int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
@@ -109,6 +112,9 @@ CG_HDN int q_match(const u32x4* text, M m, int s, int q, uint32_t p, int i0, int
     uint32_t curb = 0xffffffffu;
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
     cgt::u32x2 mk; mk.x = mk.y = 0;
+#ifdef CG_PF_TEXT
+    if (i0 < lim) cgt::prefetch_text(text, p + (uint32_t)i0, p + (uint32_t)lim);
+#endif
     while (i < lim) {
         CG_COST(4, 1);
         const uint32_t tp = p + (uint32_t)i, b = tp >> 6;
@@ -470,7 +476,7 @@ CG_HD int q_step(const IndexView& ix, const QMemT<VOTE>& m, int lceMode, QState&
             const int mq = L - o;
             if (mq > k) {
                 const uint32_t w = hit.e - hit.b;
-                if (w > (uint32_t)Q_W) return QD_WIDE_EXT;
+                if (w > (uint32_t)(ix.lcp ? Q_WL : Q_W)) return QD_WIDE_EXT;
                 CG_COST(3, w);
                 int best = -1; uint32_t first = 0, last = 0;
                 if (ix.lcp) {
@@ -664,7 +670,7 @@ CG_HD int q_hits(const IndexView& ix, const M& m, int s, int n, uint32_t& alive,
     for (int i = 0; i < n; ++i) {
         if (!((keep >> i) & 1u)) continue;
         const uint32_t sp = m.ld(m.iv(s, i) + 1) - m.ld(m.iv(s, i));
-        if (sp > (uint32_t)Q_W) wide = true;
+        if (sp > (uint32_t)Q_WH) wide = true;
         if (sp < msp) { msp = sp; mi = i; }
     }
     if (wide || mi < 0) return QD_WIDE_HITS;
@@ -772,7 +778,7 @@ CG_HD bool q_bsj_finish(const IndexView& ix, const QMemT<VOTE>& m, int r, int nF
     const int h = q_hits2<VOTE>(ix, m, nF, nR, hF, hR);
     if (h < 0) { why = h; return false; }
     if (h == 0) return true;                                                                     // :319
-    if (h > Q_W) { why = QD_WIDE_HITS; return false; }
+    if (h > Q_WH) { why = QD_WIDE_HITS; return false; }
     for (int s = 0; s < 2; ++s)
         for (int i = 0; i < (s == 0 ? nF : nR); ++i)
             if (m.ld(m.iv(s, i) + 1) - m.ld(m.iv(s, i)) > (uint32_t)Q_SPAN) { why = QD_WIDE_SPAN; return false; }
@@ -814,7 +820,7 @@ CG_HD bool q_bsj_finish(const IndexView& ix, const QMemT<VOTE>& m, int r, int nF
                 const uint32_t t = m.ld(m.cb(1) + b);
                 bool dup = false;
                 for (int a = 0; a < hF; ++a) dup |= m.ld(m.cb(0) + a) == t;
-                if (!dup) { m.st(m.cb(0) + j, t); ++j; }                             // j <= h <= Q_W: stays inside the forward area
+                if (!dup) { m.st(m.cb(0) + j, t); ++j; }                             // j <= h <= Q_WH: stays inside the forward area
             }
     }
     for (int i = 1; i < j; ++i) {
