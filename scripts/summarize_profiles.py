@@ -51,7 +51,7 @@ def main():
         f.write("# %-58s %8s %12s %8s\n" % ("kernel", "launches", "total ms", "share"))
         for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write("%-60s %8d %12.3f %7.1f%%\n" % (k[:60], n, t, 100 * t / allt))
-        step = {k: v for k, v in tot.items() if re.search(r"k_pack|k_wt|k_bsj|k_flag|k_bsm|k_merge", k)}
+        step = {k: v for k, v in tot.items() if re.search(r"k_pack|k_wt|k_bsj|k_thr|k_flag|k_cls_|k_exp|k_cand|k_acc|k_fixed|k_merge", k)}
         st = sum(v[1] for v in step.values())
         f.write("\n# kernels of the timed step only (index construction above is set-up)\n")
         for k, (n, t) in sorted(step.items(), key=lambda kv: -kv[1][1]):
@@ -73,11 +73,15 @@ def main():
             rd, wr = r[h.index("dram__bytes_read.sum")], r[h.index("dram__bytes_write.sum")]
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             b = float(rd) * scale[u[h.index("dram__bytes_read.sum")]] + float(wr) * scale[u[h.index("dram__bytes_write.sum")]]
-            key = "k_wt" if "k_wt" in k else "k_bsj" if "k_bsj" in k else None
-            if key:
+            # the lockstep tier's collector is one template for both stages: k_thr_col<VOTE, BSJ>
+            key = "k_wt" if ("k_wt" in k or re.search(r"k_thr_col<\w+, (0|false)>", k)) else "k_bsj" if ("k_bsj" in k or re.search(r"k_thr_col<\w+, (1|true)>", k)) else None
+            if key and "k_wt_commit" not in k:
                 traffic.setdefault(key, {}).setdefault(k, []).append(b)
-    # a stage (what bench.py brackets with events as k_wt / k_bsj) = all of its tiers: mean bytes per launch of each kernel, summed
-    tj = {key: sum(sum(v) / len(v) for v in d.values()) for key, d in traffic.items()}
+            if "k_pack" in k:
+                traffic.setdefault("_batches", []).append(1)
+    # a stage (what bench.py brackets with events as k_wt / k_bsj) = all of its tiers: bytes of every captured launch of the stage, per batch
+    nbat = max(1, len(traffic.pop("_batches", [])))
+    tj = {key: sum(sum(v) for v in d.values()) / nbat for key, d in traffic.items()}
     tj["pairs_per_batch"] = pairs_per_batch
     tj["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per batch, summed over the kernels (tiers) of the stage, ncu --set full, %s" % os.path.basename(rep)
     json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
