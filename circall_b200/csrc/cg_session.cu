@@ -942,6 +942,15 @@ int compact_flags(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, ui
     return launch(s, k_flag_write, dim3(nb), dim3(CP_THREADS), 0, f, n, s->d_bc.as<uint32_t>(), out);
 }
 
+// out[*n_out ..) = list[*seg .. *n_list); *n_new = *n_out + (*n_list - *seg): the two-strand tail of a class-sorted list appended to
+// the list of the lean instantiation's other-strand declines, so that ONE two-strand pass runs over both
+__global__ void k_list_append(const uint32_t* __restrict__ list, const uint32_t* __restrict__ seg, const uint32_t* __restrict__ n_list,
+                              uint32_t* __restrict__ out, const uint32_t* __restrict__ n_out, uint32_t* __restrict__ n_new) {
+    const uint32_t lo = *seg, hi = *n_list, base = *n_out, n = hi > lo ? hi - lo : 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[base + i] = list[lo + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_new = base + n;
+}
+
 // indices of the non-zero entries of the class array f[0..n), grouped by class (1..16); count into *total
 int compact_classes(cg_session* s, const uint8_t* f, uint64_t n, uint32_t* out, uint32_t* total) {
     uint32_t nb = grid_for(n, CP_TILE);
@@ -999,32 +1008,28 @@ int run_bsj_stage(cg_session* s, int do_counts) {
             rc = launch(s, k_thr_col<false, true>, grid, blk2, sm0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2, n2, seg,
                         s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
             if (rc) return rc;
-            rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2, n2, seg,
-                        s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
-            if (rc) return rc;
             CG_CUDA(cudaMemsetAsync(s->d_ovf4.p, 0, worst, s->stream));
             uint8_t* retry = s->use_retry ? s->d_ovf4.as<uint8_t>() : (uint8_t*)nullptr;
             rc = launch(s, dbs.head ? k_bsj_fin<false, true> : k_bsj_fin<false, false>, grid, blk2, sf0, em, s->n_pairs, l2, n2, seg,
                         (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), retry, dbs);
             if (rc) return rc;
-            rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs, l2, n2, seg,
-                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), (uint8_t*)nullptr, dbs);
-            if (rc) return rc;
+            // ONE two-strand pass: the tail of the class-sorted list and what the lean instantiation declined because the other strand
+            // scored (a sixth of the warp kernels' cost per read)
+            const uint32_t* l2s = l2; const uint32_t* n2s = n2; const uint32_t* segs = seg;
             if (retry) {
-                // second pass: what the lean instantiation declined because the other strand scored, through the two-strand one
-                // (a sixth of the warp kernels' cost per read)
                 uint32_t* n4 = s->d_work.as<uint32_t>() + 1;
                 rc = compact_flags(s, retry, worst, s->d_list4.as<uint32_t>(), n4);
                 if (rc) return rc;
-                rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp,
-                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
-                            s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
+                rc = launch(s, k_list_append, dim3(s->sms * 2), dim3(256), 0, l2, seg, n2, s->d_list4.as<uint32_t>(), (const uint32_t*)n4, n4 + 2);
                 if (rc) return rc;
-                rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs,
-                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
-                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), (uint8_t*)nullptr, dbs);
-                if (rc) return rc;
+                l2s = s->d_list4.as<uint32_t>(); n2s = n4 + 2; segs = nullptr;
             }
+            rc = launch(s, k_thr_col<true, true>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), s->geom, em, s->n_pairs, nexp, l2s, n2s, segs,
+                        s->opts.lce_mode, (const uint8_t*)s->d_ovf3.as<uint8_t>(), res, ivb, s->thr_cap);
+            if (rc) return rc;
+            rc = launch(s, dbs.head ? k_bsj_fin<true, true> : k_bsj_fin<true, false>, grid, blk2, sf1, em, s->n_pairs, l2s, n2s, segs,
+                        (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, o, do_counts, s->d_ovf.as<uint8_t>(), (uint8_t*)nullptr, dbs);
+            if (rc) return rc;
         }
         rc = compact_flags(s, s->d_ovf.as<uint8_t>(), worst, s->d_list3.as<uint32_t>(), &dh->n_t3_bsj);
         if (rc) return rc;
@@ -1143,34 +1148,30 @@ int run_batch(cg_session* s) {
             const dim3 grid(grid_for(n_reads, THR_THREADS)), blk2(THR_THREADS);
             const uint8_t* clsp = sorted ? (const uint8_t*)s->d_ovf.as<uint8_t>() : (const uint8_t*)nullptr;
             uint32_t* res = s->d_thr_res.as<uint32_t>(); uint32_t* ivb = s->d_thr_iv.as<uint32_t>();
+            // lean collector + finish over the head of the class-sorted list; then ONE two-strand pass over its tail and over what the
+            // lean one declined because the other strand scored
             rc = launch(s, k_thr_col<false, false>, grid, blk2, sm0, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
                         cur_list, cur_n, seg, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
             if (rc) return rc;
-            if (sorted) {
-                rc = launch(s, k_thr_col<true, false>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
-                            cur_list, cur_n, seg, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
-                if (rc) return rc;
-            }
             CG_CUDA(cudaMemsetAsync(s->d_ovf4.p, 0, n_reads, s->stream));
             uint8_t* retry = (s->use_retry && sorted) ? s->d_ovf4.as<uint8_t>() : (uint8_t*)nullptr;
             rc = launch(s, dwt.head ? k_wt_fin<false, true> : k_wt_fin<false, false>, grid, blk2, sf0, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
                         (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), retry, dwt);
             if (rc) return rc;
             if (sorted) {
-                rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads, cur_list, cur_n, seg,
-                            (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (uint8_t*)nullptr, dwt);
-                if (rc) return rc;
-            }
-            if (retry) {
-                // second pass: what the lean instantiation declined because the other strand scored, through the two-strand one
-                uint32_t* n4 = s->d_work.as<uint32_t>() + 0;
-                rc = compact_flags(s, retry, n_reads, s->d_list4.as<uint32_t>(), n4);
-                if (rc) return rc;
+                const uint32_t* l2s = cur_list; const uint32_t* n2s = cur_n; const uint32_t* segs = seg;      // the two-strand pass's list
+                if (retry) {
+                    uint32_t* n4 = s->d_work.as<uint32_t>() + 0;
+                    rc = compact_flags(s, retry, n_reads, s->d_list4.as<uint32_t>(), n4);
+                    if (rc) return rc;
+                    rc = launch(s, k_list_append, dim3(s->sms * 2), dim3(256), 0, cur_list, seg, cur_n, s->d_list4.as<uint32_t>(), (const uint32_t*)n4, n4 + 2);
+                    if (rc) return rc;
+                    l2s = s->d_list4.as<uint32_t>(); n2s = n4 + 2; segs = nullptr;
+                }
                 rc = launch(s, k_thr_col<true, false>, grid, blk2, sm1, s->d_pk.as<uint64_t>(), s->d_lens.as<uint16_t>(), g, (const uint32_t*)nullptr, n_reads, (const uint32_t*)nullptr,
-                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
+                            l2s, n2s, segs, s->opts.lce_mode, clsp, res, ivb, s->thr_cap);
                 if (rc) return rc;
-                rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads,
-                            (const uint32_t*)s->d_list4.as<uint32_t>(), (const uint32_t*)n4, (const uint32_t*)nullptr,
+                rc = launch(s, dwt.head ? k_wt_fin<true, true> : k_wt_fin<true, false>, grid, blk2, sf1, s->d_lens.as<uint16_t>(), n_reads, l2s, n2s, segs,
                             (const uint32_t*)res, (const uint32_t*)ivb, s->thr_cap, s->d_flags.as<uint8_t>(), s->d_nhits.as<uint32_t>(), s->d_ovf3.as<uint8_t>(), (uint8_t*)nullptr, dwt);
                 if (rc) return rc;
             }
