@@ -627,7 +627,7 @@ k_wt_pre(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pac
 
 // ---- lockstep thread tier (cg_thr.cuh): one thread per read, single-strand reads ------------------------------------
 #ifndef CG_THR_THREADS
-#define CG_THR_THREADS 64        // measured 32 / 64 / 128 / 256: k_bsj_thr 7.70 / 7.45 / 7.57 / 7.70 ms, the two-strand kernels 0.41 / 0.41 / 0.56 / 0.64
+#define CG_THR_THREADS 64        // measured in round 1, 32 / 64 / 128 / 256: bsj lockstep kernel 7.70 / 7.45 / 7.57 / 7.70 ms, the two-strand kernels 0.41 / 0.41 / 0.56 / 0.64; round 2 after the split: 64 -> 23.93 ms per step, 128 -> 25.12
 #endif
 static const int THR_THREADS = CG_THR_THREADS;
 #ifndef CG_THR_VOTE_MINB
@@ -654,7 +654,7 @@ __device__ __forceinline__ bool thr_stage(const uint64_t* __restrict__ rec, cons
 // The lockstep tier runs as two kernels per list: k_thr_col (the collector: q_begin, the q_step loop, q_vote — its intervals go to a
 // slot of the hand-over buffer) and k_wt_fin / k_bsj_fin (hit enumeration, full-length test / span filter, commit).  As one kernel
 // (72 KB of code for Circall_bsj) the warps of an SM, each at its own place in the collector or in the hit enumeration, ran out of the
-// 32 KB instruction cache: 56 % of k_bsj_thr's stall samples were instruction-fetch stalls (ncu r2s).  Split, each kernel's loop fits,
+// 32 KB instruction cache: 56 % of the single Circall_bsj kernel's stall samples were instruction-fetch stalls (ncu r2s).  Split, each kernel's loop fits,
 // and the second one starts with all lanes of a warp at the same instruction.
 // Hand-over, slot x = position in the work list (cap slots): res[x] = status (int8) | nF << 8 | nR << 16, the intervals of the nF forward
 // then the nR reverse-complement entries as three words each, word j of slot x at iv[j * cap + x] (coalesced across a warp).

@@ -1,5 +1,5 @@
-// circall_b200 — thread-per-read collector for single-strand reads ("lockstep tier"): second front kernel of
-// k_wt (after cg_pre.cuh) and front kernel of k_bsj.
+// circall_b200 — thread-per-read collector ("lockstep tier"): second tier of Circall_wt (after cg_pre.cuh) and first tier of Circall_bsj.
+// Kernels (cg_session.cu): k_thr_col (q_begin / q_step loop / q_vote) and k_wt_fin / k_bsj_fin (q_wt_finish / q_bsj_finish).
 //
 // The clean-match front kernel showed what this hardware wants: one THREAD per read with several independent
 // random sectors in flight each, as long as the 32 reads of a warp run the same instructions.  This file gives
@@ -7,8 +7,8 @@
 // SACollectorCircall::operator() (include/SACollectorCircall.hpp:24-582) for a read whose hits sit on ONE strand,
 // written so that every heavy operation occurs exactly once in the instruction stream —
 //
-//     for each segment of the read:   LOOK (table look-ups, QW per round)   ->  EXTEND (extendSearchNaive, 4 suffixes
-//                                     in flight)  ->  LCE  ->  next position
+//     for each segment of the read:   LOOK (seed-filter stage + table look-ups, QW per round)   ->  EXTEND (extendSearchNaive: one
+//                                     text comparison + the lcp bytes of the interval)  ->  LCE  ->  next position
 //
 // — and the lanes of a warp meet at each of them whatever segment of whatever strand they are on.  (Round 1's resumable /
 // sequential state-machine tiers failed on exactly this: every control state carried its own copy of the engines and
@@ -38,7 +38,7 @@
 #include "cg_thrmem.cuh"
 
 #ifndef CG_THR_WALK
-#define CG_THR_WALK 4      // table look-ups per thread in a walk round.  Measured (k_wt_thr / k_bsj_thr, ms per 4 M pairs): 8 -> 4.93 / 9.28,
+#define CG_THR_WALK 4      // table look-ups per thread in a walk round.  Measured in round 1 (lockstep kernels of wt / bsj, ms per 4 M pairs): 8 -> 4.93 / 9.28,
                            // 4 -> 4.72 / 8.17, 2 -> 4.92 / 8.60 at 5 blocks per SM: the narrower round over-fetches less when the walk ends, needs
                            // 16 registers less and halves the unrolled code; the number of rounds does not matter
 #endif
@@ -205,7 +205,7 @@ struct WalkScope { int r = 0; ~WalkScope() { g_walk.calls += 1; g_walk.rounds +=
 // (S = k - fm), so the stage decides the windows o0 .. o0 + Q_D0 + Q_SP (Q_NP - 1); the table stage then goes on over Q_TAIL more windows
 // taken as alive (the window after a run of dead ones is the one a walk usually ends on: no second stage for it).
 #ifndef CG_THR_FNP
-#define CG_THR_FNP 6       // measured (k_wt_thr / k_bsj_thr, ms per 4 M pairs of config 2): 3 fm-mers S apart 3.10 / 5.56, 6 fm-mers S / 3 apart 2.84 / 5.03, 4 fm-mers S / 2 apart
+#define CG_THR_FNP 6       // measured (lockstep kernels of wt / bsj, ms per 4 M pairs of config 2): 3 fm-mers S apart 3.10 / 5.56, 6 fm-mers S / 3 apart 2.84 / 5.03, 4 fm-mers S / 2 apart
                            // in between: with S = 15 a stage of 6 decides 31 windows — the windows that cover one substitution — and a window holds three of the
                            // fm-mers, so the stretches where the read enters a region of the text (fm-mers present, k-mers not yet) leave 5 windows alive instead of 15
 #endif
@@ -358,11 +358,10 @@ CG_HD int q_walk(const IndexView& ix, const M& m, int L, int s, int o, int lim, 
     return -1;
 }
 
-// SACollectorCircall::operator() up to and including the strand vote, as three pieces so that a kernel can run the segments of
-// different reads side by side (k_*_thr keep their lanes busy: a lane that finishes a read takes the next one while its neighbours
-// are still inside theirs — the loop below is the ONLY loop of those kernels): q_begin (the four up-front look-ups), q_step (one
-// trip of the reference's scan loops: LOOK -> EXTEND -> LCE -> next position), q_vote (:442-490).  q_collect strings them together
-// for one read (host emulation, cg_collect).
+// SACollectorCircall::operator() up to and including the strand vote, as three pieces: q_begin (the four up-front look-ups), q_step
+// (one trip of the reference's scan loops: LOOK -> EXTEND -> LCE -> next position), q_vote (:442-490).  k_thr_col strings them
+// together for one read per thread, q_collect for the host emulation.  (The pieces exist because a persistent-lane kernel — a lane
+// that finishes a read draws the next one — was measured: 1.7 x slower, profiles/r2_experiments.md.)
 //   VOTE = false: reads whose hits lie on one strand (a look-up that scores for the other strand declines the read)
 //   VOTE = true : both strands — Phase B then Phase C when rcHit >= fwdHit (:332), the kmerScores list and its vote (:442-490)
 // Returns Q_FOUND (nF / nR post-vote intervals in the scratch, in the reference's order), Q_NOTFOUND (:204) or a QD_* reason.

@@ -109,6 +109,22 @@ def test_pipeline_parity_tier_subsets(gpu_world, off, monkeypatch):
         assert 0 < B.n_tier2_wt < 0.3 * 2 * r1.shape[0] and 0 < B.n_tier2_bsj < 0.4 * B.n_export
 
 
+@pytest.mark.parametrize("env", ["CG_NO_RETRY", "CG_NO_LCP", "CG_NO_SATID", "CG_FM=0", "CG_NO_LCP,CG_NO_SATID,CG_FM=0"])
+def test_pipeline_parity_without_the_shortcuts(small_world, env, monkeypatch):
+    """The exact shortcuts of round 2, switched off one by one: the second two-strand pass over the lean instantiation's
+    other-strand declines (session switch), and indices built without lcp bytes (every suffix of an interval compared with the
+    text), without the per-suffix transcript ids, without the seed filter.  Same outputs as the oracle every way."""
+    import circall_b200 as cg
+    T, otx, obsj = small_world
+    for v in env.split(","):
+        k, _, val = v.partition("=")
+        monkeypatch.setenv(k, val or "1")
+    gtx, gbsj = cg.Index.build(T.tx_text), cg.Index.build(T.bsj_text)        # the index switches act at build time
+    r1, r2 = make_reads(T, 733, 20000, n_rate=0.0005, circ_frac=0.1)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, 0)
+    assert B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0
+
+
 def test_pipeline_ragged_and_edge_reads(gpu_world):
     cg, T, otx, obsj, gtx, gbsj = gpu_world
     r1, r2 = make_reads(T, 77, 6000, n_rate=0.01)
