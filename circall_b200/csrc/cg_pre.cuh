@@ -39,9 +39,6 @@ CG_HD int pre_match(const IndexView& ix, const cgt::TMem& m, int s, uint32_t p, 
     uint32_t curb = 0xffffffffu;
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
     cgt::u32x2 mk; mk.x = mk.y = 0;
-#ifdef CG_PF_TEXT
-    if (i0 < L) cgt::prefetch_text(ix.text, p + (uint32_t)i0, p + (uint32_t)L);
-#endif
     while (i < L) {
         const uint32_t tp = p + (uint32_t)i, b = tp >> 6;
         if (b != curb) { cc = CG_LDG(&ix.text[2 * (uint64_t)b]); mk = CG_LDG(cgt::mask_ptr(ix, b)); curb = b; }

@@ -112,9 +112,6 @@ CG_HDN int q_match(const u32x4* text, M m, int s, int q, uint32_t p, int i0, int
     uint32_t curb = 0xffffffffu;
     u32x4 cc; cc.x = cc.y = cc.z = cc.w = 0;
     cgt::u32x2 mk; mk.x = mk.y = 0;
-#ifdef CG_PF_TEXT
-    if (i0 < lim) cgt::prefetch_text(text, p + (uint32_t)i0, p + (uint32_t)lim);
-#endif
     while (i < lim) {
         CG_COST(4, 1);
         const uint32_t tp = p + (uint32_t)i, b = tp >> 6;

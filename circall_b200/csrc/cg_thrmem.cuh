@@ -21,16 +21,6 @@ CG_HD uint32_t fsr(uint32_t lo, uint32_t hi, int sh) {      // funnel shift righ
 #endif
 }
 
-// the text blocks a comparison over text positions [a, e) is going to read after its first one, asked of L2 up front: the loop reads
-// them one dependent load after the other.  Behind CG_PF_TEXT, off: measured 21.94 ms against 21.73 per 8 M pairs (no gain)
-CG_HD void prefetch_text(const u32x4* text, uint32_t a, uint32_t e) {
-#if defined(__CUDA_ARCH__)
-    for (uint32_t b = (a >> 6) + 1; b <= ((e - 1) >> 6) && b < (a >> 6) + 4; ++b) asm volatile("prefetch.global.L2 [%0];" :: "l"(&text[2 * (uint64_t)b]));
-#else
-    (void)text; (void)a; (void)e;
-#endif
-}
-
 // Per-thread scratch of 32-bit words, word j at base[j * stride] (stride = threads per block on the device, so
 // that the lanes of a warp touching the same word index hit 32 different banks; 1 on the host).
 //   [0, 2 W2)        forward code words, 16 bases each (W2 = 64-bit words incl. one zero pad word)
