@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcircall_gpu.so")
 SOURCES = ["cg_api.cu", "cg_index.cu", "cg_session.cu"]
-HEADERS = ["cg_common.h", "cg_core.cuh", "cg_pipeline.cuh", "cg_kernels.cuh", "cg_pack_swar.h", "cg_warp.cuh", "cg_thrmem.cuh", "cg_pre.cuh", "cg_thr.cuh", os.path.join("..", "..", "include", "circall_gpu.h")]
+HEADERS = ["cg_common.h", "cg_sortscan.cuh", "cg_core.cuh", "cg_pipeline.cuh", "cg_kernels.cuh", "cg_pack_swar.h", "cg_warp.cuh", "cg_thrmem.cuh", "cg_pre.cuh", "cg_thr.cuh", os.path.join("..", "..", "include", "circall_gpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-extended-lambda",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 

@@ -13,9 +13,9 @@
 //           (rank[i], rank[i+h]) sorts with h doubling until every suffix has its own rank
 //   khash   open addressing, 16-B slots {k-mer word, begin, end}: one slot per run of SA entries
 //           whose first k characters are equal and '$'-free
-// The sorts and scans here use CUB (index construction is set-up, not the timed hot path).
+// The sorts, scans and selections are cg_sortscan.cuh's (hand-written; index construction is set-up, not the timed hot path).
 #include "cg_common.h"
-#include <cub/cub.cuh>
+#include "cg_sortscan.cuh"
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -158,41 +158,35 @@ int build_sa(const unsigned char* d_ascii, uint64_t n, uint32_t** out_sa) {
     CG_CUDA(kA.alloc(n * 8)); CG_CUDA(kB.alloc(n * 8));
     CG_CUDA(sA.alloc(n * 4)); CG_CUDA(sB.alloc(n * 4));
     CG_CUDA(rk.alloc(n * 4)); CG_CUDA(cnt.alloc(8));
-    cub::DoubleBuffer<uint64_t> keys(kA.as<uint64_t>(), kB.as<uint64_t>());
-    cub::DoubleBuffer<uint32_t> vals(sA.as<uint32_t>(), sB.as<uint32_t>());
-    size_t tb_sort = 0, tb_scan = 0;
-    CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, keys, vals, (int64_t)n, 0, 64));
-    CG_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, cub::Max(), (int64_t)n));
-    CG_CUDA(tmp.alloc(tb_sort > tb_scan ? tb_sort : tb_scan));
+    cgs::SortBufs sb; sb.k[0] = kA.as<uint64_t>(); sb.k[1] = kB.as<uint64_t>(); sb.v[0] = sA.as<uint32_t>(); sb.v[1] = sB.as<uint32_t>(); sb.cur = 0;
+    const uint64_t te = std::max(cgs::sort_tmp_entries(n), cgs::scan_tmp_entries(n));
+    CG_CUDA(tmp.alloc(te * 4));
     const int BS = 256;
-    k_sa_init<<<grid_for(n, BS), BS>>>(d_ascii, n, keys.Current(), vals.Current());
+    k_sa_init<<<grid_for(n, BS), BS>>>(d_ascii, n, sb.k[0], sb.v[0]);
     CG_CUDA(cudaGetLastError());
-    size_t tb = tmp.bytes;
-    CG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys, vals, (int64_t)n, 0, 63));
+    CG_CUDA(cgs::sort_pairs(sb, n, 0, 63, tmp.as<uint32_t>()));
     const int rbits = bits_for(n + 1);
     uint64_t h = 21;
     for (int round = 0; round < 64; ++round) {
-        uint32_t* head = (uint32_t*)keys.Alternate();   // free scratch until the next sort
+        uint32_t* head = (uint32_t*)sb.k[sb.cur ^ 1];   // free scratch until the next sort
         CG_CUDA(cudaMemset(cnt.p, 0, 8));
-        k_sa_heads<<<grid_for(n, BS), BS>>>(keys.Current(), n, head, cnt.as<unsigned long long>());
+        k_sa_heads<<<grid_for(n, BS), BS>>>(sb.k[sb.cur], n, head, cnt.as<unsigned long long>());
         CG_CUDA(cudaGetLastError());
         unsigned long long ngroups = 0;
         CG_CUDA(cudaMemcpy(&ngroups, cnt.p, 8, cudaMemcpyDeviceToHost));
         if (ngroups == n) break;
         if (h >= n) CG_FAIL(CG_ERR_STATE, "suffix array construction did not converge");
-        tb = tmp.bytes;
-        CG_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, head, head, cub::Max(), (int64_t)n));
-        k_sa_scatter_rank<<<grid_for(n, BS), BS>>>(vals.Current(), head, n, rk.as<uint32_t>());
+        CG_CUDA((cgs::scan_u32<cgs::OpMax, true>(head, head, n, tmp.as<uint32_t>(), nullptr)));
+        k_sa_scatter_rank<<<grid_for(n, BS), BS>>>(sb.v[sb.cur], head, n, rk.as<uint32_t>());
         CG_CUDA(cudaGetLastError());
-        k_sa_keys<<<grid_for(n, BS), BS>>>(vals.Current(), rk.as<uint32_t>(), n, h, keys.Current());
+        k_sa_keys<<<grid_for(n, BS), BS>>>(sb.v[sb.cur], rk.as<uint32_t>(), n, h, sb.k[sb.cur]);
         CG_CUDA(cudaGetLastError());
-        tb = tmp.bytes;
-        CG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys, vals, (int64_t)n, 0, 32 + rbits));
+        CG_CUDA(cgs::sort_pairs(sb, n, 0, 32 + rbits, tmp.as<uint32_t>()));
         h *= 2;
     }
     CG_CUDA(cudaDeviceSynchronize());
     // hand the buffer that holds the result to the caller
-    if (vals.Current() == sA.as<uint32_t>()) { *out_sa = sA.as<uint32_t>(); sA.p = nullptr; }
+    if (sb.v[sb.cur] == sA.as<uint32_t>()) { *out_sa = sA.as<uint32_t>(); sA.p = nullptr; }
     else { *out_sa = sB.as<uint32_t>(); sB.p = nullptr; }
     return CG_OK;
 }
@@ -207,11 +201,8 @@ int build_khash(cg_index* idx) {
     CG_CUDA(cudaGetLastError());
     k_boundary<<<grid_for(n, BS), BS>>>(km.as<uint64_t>(), n, bnd.as<uint8_t>());
     CG_CUDA(cudaGetLastError());
-    size_t tb = 0;
-    cub::CountingInputIterator<uint32_t> it(0);
-    CG_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, bnd.as<uint8_t>(), B.as<uint32_t>(), nsel.as<uint64_t>(), (int64_t)n));
-    CG_CUDA(tmp.alloc(tb));
-    CG_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, it, bnd.as<uint8_t>(), B.as<uint32_t>(), nsel.as<uint64_t>(), (int64_t)n));
+    CG_CUDA(tmp.alloc((cgs::scan_tmp_entries(n) + 2) * 4));
+    CG_CUDA(cgs::select_flagged(bnd.as<uint8_t>(), n, B.as<uint32_t>(), nsel.as<unsigned long long>(), tmp.as<uint32_t>()));
     uint64_t nB = 0;
     CG_CUDA(cudaMemcpy(&nB, nsel.p, 8, cudaMemcpyDeviceToHost));
     CG_CUDA(cudaMemset(cnt.p, 0, 8));
@@ -370,11 +361,10 @@ int build_impl(int device, const char* text, uint64_t n, int k, const std::vecto
     k_text_blocks<<<grid_for(idx->n_blocks, BS), BS>>>(ascii.as<unsigned char>(), n, idx->n_blocks, idx->d_text, cnt.as<uint32_t>(), bad.as<int>());
     CG_TRY(cudaGetLastError());
     {
-        size_t tb = 0;
         DevBuf tmp;
-        CG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<uint32_t>(), cnt.as<uint32_t>(), (int64_t)idx->n_blocks));
-        CG_TRY(tmp.alloc(tb));
-        CG_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.as<uint32_t>(), cnt.as<uint32_t>(), (int64_t)idx->n_blocks));
+        CG_TRY(tmp.alloc(cgs::scan_tmp_entries(idx->n_blocks) * 4));
+        CG_TRY((cgs::scan_u32<cgs::OpSum, false>(cnt.as<uint32_t>(), cnt.as<uint32_t>(), idx->n_blocks, tmp.as<uint32_t>(), nullptr)));
+        CG_TRY(cudaDeviceSynchronize());
     }
     k_text_finish<<<grid_for(idx->n_blocks, BS), BS>>>(idx->d_text, cnt.as<uint32_t>(), idx->d_offsets, idx->n_tx, idx->n_blocks);
     CG_TRY(cudaGetLastError());
