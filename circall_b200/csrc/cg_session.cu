@@ -678,6 +678,7 @@ k_thr_col(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     const int L = lens[r];
     const IndexView& ix = cgw::c_ix[BSJ ? 1 : 0];
     cgq::QMemT<VOTE> m; m.base = thr_smem + threadIdx.x; m.stride = THR_THREADS; m.W2 = g.W2f + 1;
+    if (!VOTE) { m.giv = iv + x; m.gcap = cap; }
     cgq::QState st; st.nF = st.nR = 0;
     int status = thr_stage(pk + r * (uint64_t)g.WT, g, L, m) ? cgq::q_begin<VOTE>(ix, m, L, cls ? (int)cls[item] - 1 : -1, st) : (int)cgq::QD_N;
     while (status == cgq::Q_CONT) status = cgq::q_step<VOTE>(ix, m, lceMode, st);
@@ -685,7 +686,7 @@ k_thr_col(const uint64_t* __restrict__ pk, const uint16_t* __restrict__ lens, Pa
     int nF = status == cgq::Q_FOUND ? st.nF : 0, nR = status == cgq::Q_FOUND ? st.nR : 0;
     if (VOTE && nF + nR > cgq::Q_FI) { status = cgq::QD_NINT; nF = nR = 0; }
     res[x] = (uint32_t)(status & 0xff) | ((uint32_t)nF << 8) | ((uint32_t)nR << 16);
-    for (int i = 0; i < nF + nR; ++i) {
+    if (VOTE) for (int i = 0; i < nF + nR; ++i) {
         const int at = i < nF ? m.iv(0, i) : m.iv(1, i - nF);
         iv[(uint64_t)(3 * i) * cap + x] = m.ld(at); iv[(uint64_t)(3 * i + 1) * cap + x] = m.ld(at + 1); iv[(uint64_t)(3 * i + 2) * cap + x] = m.ld(at + 2);
     }

@@ -43,10 +43,11 @@
                            // 16 registers less and halves the unrolled code; the number of rounds does not matter
 #endif
 #ifndef CG_THR_MINB
-#define CG_THR_MINB 6      // resident blocks per SM (x 128 threads) asked of the lockstep kernels.  Round 1, DRAM-bound kernels: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5,
+#define CG_THR_MINB 7      // resident blocks per SM (x 128 threads) asked of the lockstep kernels.  Round 1, DRAM-bound kernels: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5,
                            // 6 -> 5.46 / 10.8.  Round 2 (seed filter, lcp bytes: a quarter of the DRAM bytes, the kernels wait on latency), step of 8 M pairs:
                            // 4 -> 30.14 ms, 5 -> 29.85, 6 -> 29.33 (80 registers), 7 -> 30.59 (72, spills), 8 -> 31.28; asking for the largest shared-memory
-                           // carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors
+                           // carve-out instead costs 25 %: the kernels live on L1 hits for text / SA sectors.  After the collector / finish split and with the lean
+                           // collector's intervals written straight to global memory (20 words of shared memory per read): 5 -> 21.41 ms, 6 -> 20.81, 7 -> 20.50, 8 -> 20.54
 #endif
 
 namespace cgq {
@@ -66,7 +67,10 @@ static const int QW = CG_THR_WALK;
 #define CG_THR_EXT 4       // suffixes per round of the extension
 #endif
 static const int QX = CG_THR_EXT;
-static const int Q_FI = 8;        // intervals kept (one strand)
+#ifndef CG_THR_FI
+#define CG_THR_FI 8
+#endif
+static const int Q_FI = CG_THR_FI;        // intervals kept (one strand)
 static const int Q_W = 16;        // widest k-mer interval the extension compares suffix by suffix with the text (an index without lcp bytes)
 static const int Q_WL = 256;      // widest k-mer interval the extension walks with the lcp bytes (a byte per suffix, the text only where two lengths tie)
 static const int Q_WH = 32;       // widest maximal interval in the hit enumeration (candidates, intersection: one bit per candidate)
@@ -83,13 +87,21 @@ static const int Q_FK = 16;       // kmerScores entries (two-strand instantiatio
 template <bool VOTE>
 struct QMemT {
     uint32_t* base; int stride; int W2;
+    // the lean collector kernel writes its intervals straight to its hand-over slot in global memory (word j of the slot at giv[j * gcap]):
+    // it never reads them back, and the shared memory they took (a third of the kernel's footprint) is worth more as L1
+    uint32_t* giv = nullptr; uint64_t gcap = 0;
     CG_HD uint32_t ld(int j) const { return base[(size_t)j * stride]; }
     CG_HD void st(int j, uint32_t v) const { base[(size_t)j * stride] = v; }
+    // interval n of strand s (a single-strand read keeps one list: entry n of the slot)
+    CG_HD void put_iv(int s, int n, uint32_t lb, uint32_t ub, uint32_t lq) const {
+        if (!VOTE && giv) { giv[(uint64_t)(3 * n) * gcap] = lb; giv[(uint64_t)(3 * n + 1) * gcap] = ub; giv[(uint64_t)(3 * n + 2) * gcap] = lq; }
+        else { st(iv(s, n), lb); st(iv(s, n) + 1, ub); st(iv(s, n) + 2, lq); }
+    }
     CG_HD int iv(int s, int i) const { return 4 * W2 + 3 * ((VOTE ? s * Q_FI : 0) + i); }
     CG_HD int ks(int j) const { return 4 * W2 + 3 * Q_FI * 2 + j; }
     CG_HD int cb(int s) const { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + s * Q_WH : 0); }
     CG_HD static int words(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK + 2 * Q_WH : Q_WH); }
-    CG_HD static int words_col(int W2) { return 4 * W2 + 3 * Q_FI * (VOTE ? 2 : 1) + (VOTE ? Q_FK : 0); }      // the collector alone: no candidates
+    CG_HD static int words_col(int W2) { return 4 * W2 + (VOTE ? 3 * Q_FI * 2 + Q_FK : 0); }      // the collector kernel: no candidates, and the lean one keeps no intervals (put_iv)
     // 32-base window of strand s at oriented position i (i < L)
     CG_HD uint64_t chunk(int s, int i) const {
         int p = (s ? 2 * W2 : 0) + (i >> 4), sh = (i & 15) * 2;
@@ -518,7 +530,7 @@ CG_HD int q_step(const IndexView& ix, const QMemT<VOTE>& m, int lceMode, QState&
             if (valid) {
                 const int n = s == 0 ? st.nF : st.nR;
                 if (n >= Q_FI) return QD_NINT;
-                m.st(m.iv(s, n), lb); m.st(m.iv(s, n) + 1, ub); m.st(m.iv(s, n) + 2, (uint32_t)matched | ((uint32_t)o << 16));
+                m.put_iv(s, n, lb, ub, (uint32_t)matched | ((uint32_t)o << 16));
                 if (s == 0) st.nF = n + 1; else st.nR = n + 1;
             }
             if (st.firstB) {                                                   // Phase A's bookkeeping (:149-191)
