@@ -54,6 +54,10 @@ def _worker(rank, world, port, q):
 
 
 def test_sharded_counts_allreduce_world2():
+    import oracle
+    import synth
+    from tests import emu
+    oracle.build(); synth.build(); emu.build()          # build once here: two ranks rebuilding a stale library at the same time race on the file
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
