@@ -43,7 +43,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
         if rc != 0:
             raise RuntimeError("nvcc failed on " + src)
     if force or procs or _stale(SO, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", SO] + objs + ["-lcudart", "-ldl"])
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs + ["-lcudart", "-ldl"])
     return SO
 
 
