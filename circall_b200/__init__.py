@@ -97,6 +97,8 @@ def lib():
     L.cg_index_close.restype = None
     L.cg_index_get_info.argtypes = [vp, ctypes.POINTER(_IndexInfo)]
     L.cg_index_dir_info.argtypes = [ctypes.c_char_p, ctypes.POINTER(_IndexInfo), ctypes.POINTER(ctypes.c_int)]
+    L.cg_debug_sort_pairs.argtypes = [ctypes.c_int, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+    L.cg_debug_scan.argtypes = [ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_int, vp, vp]
     L.cg_index_tx_name.argtypes = [vp, u32]
     L.cg_index_tx_name.restype = cp
     L.cg_index_set_tx_name.argtypes = [vp, u32, cp]
@@ -168,6 +170,26 @@ def flatten_reads(reads):
     a = np.ascontiguousarray(reads, np.uint8)
     n, L = a.shape
     return a.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+
+
+def debug_sort_pairs(keys, vals, begin_bit=0, end_bit=64, device=0):
+    """The index builder's radix sort on host arrays: returns (keys, vals) sorted stably by key bits [begin_bit, end_bit)."""
+    k = np.ascontiguousarray(keys, np.uint64).copy()
+    v = np.ascontiguousarray(vals, np.uint32).copy()
+    _check(lib().cg_debug_sort_pairs(device, k.ctypes.data, v.ctypes.data, k.size, begin_bit, end_bit))
+    return k, v
+
+
+def debug_scan(data, mode, device=0):
+    """mode 0: exclusive sum, 1: inclusive max (uint32, wraps like the device); 2: indices of the non-zero flags."""
+    d = np.ascontiguousarray(data, np.uint32).copy()
+    if mode == 2:
+        out = np.zeros(d.size, np.uint32)
+        n = ctypes.c_uint64(0)
+        _check(lib().cg_debug_scan(device, d.ctypes.data, d.size, 2, out.ctypes.data, ctypes.byref(n)))
+        return out[:n.value]
+    _check(lib().cg_debug_scan(device, d.ctypes.data, d.size, mode, None, None))
+    return d
 
 
 class Index:

@@ -785,4 +785,54 @@ int cg_index_copy_sa(const cg_index* idx, int32_t* out) {
     return CG_OK;
 }
 
+// The index builder's own primitives (cg_sortscan.cuh) on caller-provided data, results back on the host: the tests compare them with
+// numpy at sizes around the tile boundaries (the suffix-array tests only see them through the finished index).
+//   keys / vals (n each): sorted in place by key bits [begin_bit, end_bit), stably
+int cg_debug_sort_pairs(int device, uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
+    if ((n && (!keys || !vals)) || begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) CG_FAIL(CG_ERR_ARG, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return CG_OK;
+    DevBuf kA, kB, vA, vB, tmp;
+    CG_CUDA(kA.alloc(n * 8)); CG_CUDA(kB.alloc(n * 8)); CG_CUDA(vA.alloc(n * 4)); CG_CUDA(vB.alloc(n * 4));
+    CG_CUDA(tmp.alloc(cgs::sort_tmp_entries(n) * 4));
+    CG_CUDA(cudaMemcpy(kA.p, keys, n * 8, cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMemcpy(vA.p, vals, n * 4, cudaMemcpyHostToDevice));
+    cgs::SortBufs sb; sb.k[0] = kA.as<uint64_t>(); sb.k[1] = kB.as<uint64_t>(); sb.v[0] = vA.as<uint32_t>(); sb.v[1] = vB.as<uint32_t>(); sb.cur = 0;
+    CG_CUDA(cgs::sort_pairs(sb, n, begin_bit, end_bit, tmp.as<uint32_t>()));
+    CG_CUDA(cudaDeviceSynchronize());
+    CG_CUDA(cudaMemcpy(keys, sb.k[sb.cur], n * 8, cudaMemcpyDeviceToHost));
+    CG_CUDA(cudaMemcpy(vals, sb.v[sb.cur], n * 4, cudaMemcpyDeviceToHost));
+    return CG_OK;
+}
+//   mode 0: exclusive sum, 1: inclusive max of data[0..n) in place; mode 2: data = flags (one byte each in the low byte of every word):
+//   out_idx receives the indices of the non-zero ones, *n_out their number
+int cg_debug_scan(int device, uint32_t* data, uint64_t n, int mode, uint32_t* out_idx, uint64_t* n_out) {
+    if ((n && !data) || mode < 0 || mode > 2 || (mode == 2 && (!out_idx || !n_out))) CG_FAIL(CG_ERR_ARG, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) { if (n_out) *n_out = 0; return CG_OK; }
+    DevBuf d, tmp, f, o, cnt;
+    CG_CUDA(d.alloc(n * 4)); CG_CUDA(tmp.alloc((cgs::scan_tmp_entries(n) + 2) * 4));
+    CG_CUDA(cudaMemcpy(d.p, data, n * 4, cudaMemcpyHostToDevice));
+    if (mode == 0) CG_CUDA((cgs::scan_u32<cgs::OpSum, false>(d.as<uint32_t>(), d.as<uint32_t>(), n, tmp.as<uint32_t>(), nullptr)));
+    else if (mode == 1) CG_CUDA((cgs::scan_u32<cgs::OpMax, true>(d.as<uint32_t>(), d.as<uint32_t>(), n, tmp.as<uint32_t>(), nullptr)));
+    else {
+        std::vector<uint8_t> hf(n);
+        for (uint64_t i = 0; i < n; ++i) hf[i] = (uint8_t)(data[i] & 0xffu);
+        CG_CUDA(f.alloc(n)); CG_CUDA(o.alloc(n * 4)); CG_CUDA(cnt.alloc(8));
+        CG_CUDA(cudaMemcpy(f.p, hf.data(), n, cudaMemcpyHostToDevice));
+        CG_CUDA(cgs::select_flagged(f.as<uint8_t>(), n, o.as<uint32_t>(), cnt.as<unsigned long long>(), tmp.as<uint32_t>()));
+        CG_CUDA(cudaDeviceSynchronize());
+        unsigned long long c = 0;
+        CG_CUDA(cudaMemcpy(&c, cnt.p, 8, cudaMemcpyDeviceToHost));
+        *n_out = c;
+        CG_CUDA(cudaMemcpy(out_idx, o.p, c * 4, cudaMemcpyDeviceToHost));
+        return CG_OK;
+    }
+    CG_CUDA(cudaDeviceSynchronize());
+    CG_CUDA(cudaMemcpy(data, d.p, n * 4, cudaMemcpyDeviceToHost));
+    return CG_OK;
+}
+
 } // extern "C"

@@ -233,6 +233,14 @@ int cg_bench_gather_mode(int device, uint64_t bytes, uint32_t per_thread, int it
 int cg_pack_reads(int device, const char* r1, const uint64_t* off1, const char* r2, const uint64_t* off2, uint64_t n_pairs,
                   int max_len, int general, int iters, uint64_t* packed, uint16_t* lens, int* status, double* ms_per_launch);
 
+/* The index builder's sort / scan / selection primitives on caller-provided host data (cg_sortscan.cuh; test surface of row N2:
+ * the reference's indexer sorts with libdivsufsort, src/TxIndexer.cpp:202-227 -> SailfishIndex::build [U]).
+ * cg_debug_sort_pairs: stable sort of (keys[i], vals[i]) by key bits [begin_bit, end_bit), in place.
+ * cg_debug_scan: mode 0 exclusive sum, 1 inclusive max of data[0..n) in place; 2: data holds flags, out_idx receives the indices of
+ * the non-zero ones in ascending order, *n_out their number. */
+int cg_debug_sort_pairs(int device, uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
+int cg_debug_scan(int device, uint32_t* data, uint64_t n, int mode, uint32_t* out_idx, uint64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif
