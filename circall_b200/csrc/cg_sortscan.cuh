@@ -3,10 +3,11 @@
 // selection of the indices of set byte flags.  Round 1 used CUB for these (a third of the index build's device time); they are
 // set-up, not the timed path, so the aim here is correctness at 10^9 elements and streaming-rate passes, not the last 30 %.
 //
-//   radix sort   8-bit digits, one pass = histogram kernel (one 256-bin histogram per 4096-pair tile, digit-major in global memory),
+//   radix sort   8-bit digits, one pass = histogram kernel (one 256-bin histogram per 2048-pair tile, digit-major in global memory),
 //                one exclusive scan over all (digit, tile) counts, one scatter kernel.  Stability inside a tile: every warp owns a
-//                contiguous 512-pair slice and walks it 32 pairs at a time; __match_any_sync groups the lanes of a step by digit, the
-//                rank of a pair is its warp's running count for the digit plus the number of lower lanes in its group.
+//                contiguous 256-pair slice and walks it 32 pairs at a time; __match_any_sync groups the lanes of a step by digit, the
+//                rank of a pair is its warp's running count for the digit plus the number of lower lanes in its group.  The tile is put in
+//                sorted order in shared memory first, so that the pairs of a digit leave as one contiguous run.
 //   scans        three phases: per-chunk reduction, single-block scan of the chunk totals, per-chunk scan + carry-in.
 //   select       flag count per tile, scan, ordered write (as cg_session.cu's compaction, over up to 2^32 flags).
 #pragma once
@@ -15,7 +16,7 @@
 
 namespace cgs {
 
-static const int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_PER_WARP = 512, RS_TILE = RS_WARPS * RS_PER_WARP;      // 4096 pairs per block
+static const int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_PER_WARP = 256, RS_TILE = RS_WARPS * RS_PER_WARP;      // 2048 pairs per block
 static const int SC_THREADS = 256, SC_ITEMS = 16, SC_CHUNK = SC_THREADS * SC_ITEMS;                                        // 4096 entries per block
 
 struct OpSum { __device__ __forceinline__ static uint32_t id() { return 0u; } __device__ __forceinline__ static uint32_t ap(uint32_t a, uint32_t b) { return a + b; } };
@@ -170,11 +171,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
 }
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, int shift, uint32_t mask,
                                                           const uint32_t* __restrict__ offs, uint32_t nb, uint64_t* __restrict__ okeys, uint32_t* __restrict__ ovals) {
-    __shared__ uint32_t cnt[RS_WARPS][256];          // first the slice histograms, then the running output cursors of every warp
+    __shared__ uint32_t cnt[RS_WARPS][256];          // first the slice histograms, then the running local cursors of every warp
+    __shared__ uint32_t gbase[256];                  // global position of a pair = gbase[digit] + its position in the tile's sorted order
+    __shared__ uint32_t sh[32];
+    __shared__ uint64_t skeys[RS_TILE];              // the tile in sorted order: the pairs of a digit leave as one contiguous run
+    __shared__ uint32_t svals[RS_TILE];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t wbase = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_PER_WARP;
+    const uint64_t tbase = (uint64_t)blockIdx.x * RS_TILE, wbase = tbase + (uint64_t)w * RS_PER_WARP;
     // phase A: histogram of the warp's slice
     for (int c = 0; c < RS_PER_WARP / 32; ++c) {
         const uint64_t i = wbase + (uint64_t)c * 32 + lane;
@@ -185,15 +190,21 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
         __syncwarp();
     }
     __syncthreads();
-    // phase B: cursor of (warp, digit) = global offset of (digit, tile) + the slices of the warps before it
+    // phase B: where the digit's run starts inside the tile (scan over the digits), the local cursor of every (warp, digit), and the
+    // global base of the run
     {
         const int d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * nb + blockIdx.x];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int x = 0; x < RS_WARPS; ++x) tot += cnt[x][d];
+        const uint32_t lstart = block_scan<OpSum>(tot, sh, nullptr) - tot;
+        uint32_t run = lstart;
 #pragma unroll
         for (int x = 0; x < RS_WARPS; ++x) { const uint32_t t = cnt[x][d]; cnt[x][d] = run; run += t; }
+        gbase[d] = offs[(size_t)d * nb + blockIdx.x] - lstart;
     }
     __syncthreads();
-    // phase C: the slice again, in order
+    // phase C: the slice again, in order, into the tile's sorted order
     for (int c = 0; c < RS_PER_WARP / 32; ++c) {
         const uint64_t i = wbase + (uint64_t)c * 32 + lane;
         const bool in = i < n;
@@ -206,7 +217,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
         __syncwarp();
         if (in && lane == __ffs(peers) - 1) cnt[w][d] += __popc(peers);
         __syncwarp();
-        if (in) { okeys[pos] = key; ovals[pos] = val; }
+        if (in) { skeys[pos] = key; svals[pos] = val; }
+    }
+    __syncthreads();
+    // phase D: out, run by run
+    const uint32_t have = (uint32_t)(n - tbase < (uint64_t)RS_TILE ? n - tbase : (uint64_t)RS_TILE);
+    for (uint32_t i = threadIdx.x; i < have; i += RS_THREADS) {
+        const uint64_t key = skeys[i];
+        const uint32_t g = gbase[(uint32_t)(key >> shift) & mask] + i;
+        okeys[g] = key; ovals[g] = svals[i];
     }
 }
 
