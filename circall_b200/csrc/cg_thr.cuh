@@ -38,9 +38,9 @@
 #include "cg_thrmem.cuh"
 
 #ifndef CG_THR_WALK
-#define CG_THR_WALK 4      // table look-ups per thread in a walk round.  Measured in round 1 (lockstep kernels of wt / bsj, ms per 4 M pairs): 8 -> 4.93 / 9.28,
-                           // 4 -> 4.72 / 8.17, 2 -> 4.92 / 8.60 at 5 blocks per SM: the narrower round over-fetches less when the walk ends, needs
-                           // 16 registers less and halves the unrolled code; the number of rounds does not matter
+#define CG_THR_WALK 2      // table look-ups per thread in a walk round.  Round 1 (lockstep kernels of wt / bsj, ms per 4 M pairs): 8 -> 4.93 / 9.28,
+                           // 4 -> 4.72 / 8.17, 2 -> 4.92 / 8.60.  Round 2, with the seed filter leaving 1.5 table rounds per read (step of 8 M pairs):
+                           // 2 -> 20.44 ms, 4 -> 20.68, 8 -> 27.02 (spills): the narrower round over-fetches less when the walk ends and is less code
 #endif
 #ifndef CG_THR_MINB
 #define CG_THR_MINB 7      // resident blocks per SM (x 128 threads) asked of the lockstep kernels.  Round 1, DRAM-bound kernels: 4 -> 5.85 / 11.4 ms, 5 -> 5.39 / 10.5,
