@@ -153,7 +153,7 @@ __device__ __forceinline__ GenPtrs gen_ptrs(unsigned char* base, uint64_t warp) 
     return g;
 }
 
-// K2-K6: one warp per mate (persistent warps, grid-stride).
+// K2-K6: one warp per mate (persistent warps drawing their mates from a counter).
 //   GEN = false: over all n mates, state in shared memory; ovf[r] = 1 hands the mate to the general kernel
 //   GEN = true : over list[0..*n_list), worst-case state in global scratch
 #ifndef CG_GEN_MINB
