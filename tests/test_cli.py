@@ -157,8 +157,19 @@ def test_two_process_pipeline_and_fused_files(exe, tmp_path):
     # ---- the two-process pipeline of Circall_source.sh:273-305
     wt, bs = str(tmp_path / "wt"), str(tmp_path / "bs")
     run([exe + "/Circall_wt", "-i", str(tmp_path / "txIdx"), "-1", str(tmp_path / "r1.fq"), "-2", str(tmp_path / "r2_0.fa"), str(tmp_path / "r2_1.fa"),
-         "-o", wt, "-p", "4", "--batch", "2500"])
+         "-o", wt, "-p", "4", "--batch", "2500", "--wt-classes"])
     check_wt(wt)
+    # Circall_wt's own rawCount.txt (opt-in: nothing downstream reads it): mate 1's transcripts, then mate 1's + mate 2's — the reference
+    # does not clear the list between the mates (Circall_wt.cpp:247-252,369-465,544-640) — keyed in hit order, weights 1 / class size
+    rows = [ln.split("\t") for ln in open(os.path.join(wt, "rawCount.txt")).read().split("\n")[1:-1]]
+    got = {}
+    for name, w, cnt, _e, rl, _e2, cls in rows:
+        got.setdefault(int(cls), []).append((name, float(w), int(cnt)))
+    weq = {}
+    for members in got.values():
+        assert all(abs(m[1] - 1.0 / len(members)) < 1e-5 for m in members) and len({m[2] for m in members}) == 1
+        weq[tuple(txn.index(m[0]) for m in members)] = members[0][2]
+    assert weq == R.eq_classes(0) and len(weq) > 50
     m1, m2 = str(tmp_path / "Unmapped_readM_1.fa"), str(tmp_path / "Unmapped_readM_2.fa")
     for m, pat in ((m1, "UN_read1_"), (m2, "UN_read2_")):
         with open(m, "w") as f:

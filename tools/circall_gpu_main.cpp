@@ -34,6 +34,7 @@ struct Args {
     int k = 31, gpu = 0, gpus = 1, threads = 4, lce = 0;
     uint64_t batch = 1u << 20;
     bool force = false;
+    bool wt_classes = false;      // also write Circall_wt's own rawCount.txt (its equivalence classes; nothing downstream reads it)
 };
 
 Args parse_args(int argc, char** argv, int first) {
@@ -56,6 +57,7 @@ Args parse_args(int argc, char** argv, int first) {
         else if (o == "--gpus") a.gpus = atoi(val().c_str());
         else if (o == "--batch") a.batch = strtoull(val().c_str(), nullptr, 10);
         else if (o == "--lce-mode") a.lce = atoi(val().c_str());
+        else if (o == "--wt-classes") a.wt_classes = true;
         else if (o.size() > 1 && o[0] == '-') { if (i + 1 < argc && argv[i + 1][0] != '-') ++i; }   // accepted and ignored
         else die("unexpected argument " + o);
     }
@@ -163,10 +165,33 @@ int run_mapper(int stage, const Args& a) {
     uint64_t pairs = 0;
     int cur = 0;
     std::vector<char> pending(NU, 0);
+    // Circall_wt's own equivalence classes (src/Circall_wt.cpp:369-465,544-640; opt-in, --wt-classes): the transcripts of mate 1's hits
+    // form a group, and mate 2's are APPENDED to them for a second group — txpIDsCompat is not cleared between the mates (:247-252).
+    // Nothing downstream reads the file, and the mapping kernels do not keep hit lists, so the lists come from the collector surface
+    // (cg_collect) in a second pass over the batch: a switch for completeness, not the fast path.
+    cgh::EqClasses wt_eq;
+    auto wt_classes_of = [&](int x) {
+        const cgh::Batch& b = B[x];
+        std::vector<std::vector<uint32_t>> left((size_t)b.n);
+        cg_collect_result cr;
+        ck(cg_collect(txs[x % ND], b.b1, b.off1.data(), b.n, 1, a.lce, &cr), "collecting mate 1's hits");
+        for (uint64_t i = 0; i < b.n; ++i) {
+            const uint64_t h0 = cr.hits_off[i], h1 = cr.hits_off[i + 1];
+            if (h1 > h0 && h1 - h0 <= 200) left[(size_t)i].assign(cr.hit_tid + h0, cr.hit_tid + h1);      // maxReadOccs (:372)
+        }
+        ck(cg_collect(txs[x % ND], b.b2, b.off2.data(), b.n, 1, a.lce, &cr), "collecting mate 2's hits");
+        for (uint64_t i = 0; i < b.n; ++i) {
+            std::vector<uint32_t>& g = left[(size_t)i];
+            if (!g.empty()) ++wt_eq[g];                                                                   // :450-451
+            const uint64_t h0 = cr.hits_off[i], h1 = cr.hits_off[i + 1];
+            if (h1 > h0 && h1 - h0 <= 200) { g.insert(g.end(), cr.hit_tid + h0, cr.hit_tid + h1); ++wt_eq[g]; }   // :625-626
+        }
+    };
     auto finish = [&](int x) {
         cg_batch_result r;
         ck(cg_session_fetch(S[x], 1, &r), "mapping a batch");
         emit(stage, B[x], r, bsj, o);
+        if (a.wt_classes && stage != 2) wt_classes_of(x);
         pending[x] = 0;
     };
     try {
@@ -200,6 +225,21 @@ int run_mapper(int stage, const Args& a) {
     if (tx) cg_index_get_info(tx, &ti);
     if (stage != 2 && !cgh::write_fragment_info(out_wt + "/fragmentInfo.txt", tot.wt_read_len, fp, tot.wt_num_observed, tot.wt_num_mapped, tot.wt_num_hits, ti.k))
         die("cannot write fragmentInfo.txt");
+    if (stage != 2 && a.wt_classes) {
+        FILE* f = fopen((out_wt + "/rawCount.txt").c_str(), "w");
+        if (!f) die("cannot write rawCount.txt");
+        fprintf(f, "Transcript\tWeight\tCount\teffLens\tRefLength\tEffectiveLength\teqClass\n");       // ExportFeq.cpp:88
+        uint32_t cls = 0;
+        for (auto& kv : wt_eq) {
+            ++cls;
+            for (uint32_t t : kv.first) {                                                    // weights 1/classSize (EquivalenceClassBuilder.hpp:32-40)
+                const uint32_t len = cg_index_tx_len(tx, t);
+                const double e = fp.effective_length(len);
+                fprintf(f, "%s\t%g\t%llu\t%g\t%u\t%g\t%u\n", cg_index_tx_name(tx, t), 1.0 / (double)kv.first.size(), (unsigned long long)kv.second, e, len, e, cls);
+            }
+        }
+        fclose(f);
+    }
     if (stage != 1) {
         if (!cgh::write_fragment_info(out_bsj + "/fragmentInfo.txt", tot.bsj_read_len, fp, tot.bsj_num_observed, tot.bsj_num_mapped, tot.bsj_num_hits, bi.k))
             die("cannot write fragmentInfo.txt");
