@@ -163,3 +163,15 @@ def test_lcp_extension_exact(small_world, monkeypatch):
             tot += int(a.reshape(-1, 10)[:, 2 + 4].sum())        # q_match word steps
         words[no_lcp] = tot
     assert 0 < words[False] < 0.6 * words[True], words
+
+
+@pytest.mark.parametrize("k", [21, 25, 29])
+def test_pipeline_other_kmer_lengths(small_world, k):
+    """TxIndexer takes -k (odd, <= 31; TxIndexer.cpp:87,208-214).  The tiers, the seed filter (stage geometry follows k - 16) and the lcp
+    extension at other k-mer lengths than the pipeline's 31."""
+    T, _, _ = small_world
+    otx, obsj = oracle.Index.from_text(T.tx_text, k=k), oracle.Index.from_text(T.bsj_text, k=k)
+    etx, ebsj = emu.EmuIndex(T.tx_text, otx.sa, k), emu.EmuIndex(T.bsj_text, obsj.sa, k)
+    assert etx.n_kmers == otx.n_kmers and ebsj.n_kmers == obsj.n_kmers
+    r1, r2 = make_reads(T, 300 + k, 2500, n_rate=0.001, circ_frac=0.1)
+    _pipeline((T, otx, obsj, etx, ebsj), r1, r2, 0)

@@ -125,6 +125,21 @@ def test_pipeline_parity_without_the_shortcuts(small_world, env, monkeypatch):
     assert B.n_export > 0 and B.n_junc > 0 and B.n_cand > 0
 
 
+@pytest.mark.parametrize("k", [21, 25, 29])
+def test_pipeline_other_kmer_lengths(small_world, k):
+    """TxIndexer takes -k (odd, <= 31; TxIndexer.cpp:87,208-214): indices, tiers, seed filter (its stage geometry follows k - 16) and the lcp
+    extension at other k-mer lengths than the pipeline's 31, interval lists of the production tiers included."""
+    import circall_b200 as cg
+    import oracle
+    T, _, _ = small_world
+    otx, obsj = oracle.Index.from_text(T.tx_text, k=k), oracle.Index.from_text(T.bsj_text, k=k)
+    gtx, gbsj = cg.Index.build(T.tx_text, k=k), cg.Index.build(T.bsj_text, k=k)
+    assert gtx.n_kmers == otx.n_kmers and gbsj.n_kmers == obsj.n_kmers and np.array_equal(gtx.suffix_array(), otx.sa)
+    r1, r2 = make_reads(T, 300 + k, 12000, n_rate=0.001, circ_frac=0.1)
+    B, R = _cmp_pipeline(cg, T, otx, obsj, gtx, gbsj, r1, r2, 0)
+    assert B.n_export > 0 and B.n_junc > 0
+
+
 def test_pipeline_ragged_and_edge_reads(gpu_world):
     cg, T, otx, obsj, gtx, gbsj = gpu_world
     r1, r2 = make_reads(T, 77, 6000, n_rate=0.01)
